@@ -170,9 +170,9 @@ ORC_API void orc_update_multivalued(int32_t *idx, float *dist, int *count, int k
  *         list ascending by (distance, train index), at most k entries.
  * Output: idx[nq*k] (-1 padded), dist[nq*k] (+inf padded... written as 0 with
  *         idx -1), count[nq]. */
-ORC_API void orc_knn(const float *query, size_t nq, size_t q_stride,
-                     const float *train, size_t nt, size_t t_stride,
-                     int dim, int k, int32_t *idx, float *dist, int32_t *count) {
+ORC_API void orc_knn_scalar(const float *query, size_t nq, size_t q_stride,
+                            const float *train, size_t nt, size_t t_stride,
+                            int dim, int k, int32_t *idx, float *dist, int32_t *count) {
     uint8_t *tvalid = (uint8_t *) malloc(nt ? nt : 1);
 #pragma omp parallel for schedule(static)
     for (long j = 0; j < (long) nt; ++j) tvalid[j] = (uint8_t) orc_is_valid(row_at(train, t_stride, j), dim);
@@ -206,6 +206,85 @@ ORC_API void orc_knn(const float *query, size_t nq, size_t q_stride,
             orc_knn_result_add(&r, d, (int32_t) j);
         }
         count[i] = r.count;
+    }
+    free(tvalid);
+}
+
+/* Same function, same per-pair arithmetic (bit-identical output, asserted in
+ * tests/test_oracle.py), laid out for the CPU baseline timing: 8 train rows per
+ * SIMD vector (one lane == one (query, train) pair, still a sequential
+ * pcl::L2_Norm chain over d), train rows transposed per block so the loads are
+ * contiguous, 4 vectors in flight to hide FP latency.  This is what bench.py
+ * times as "the reference's CPU matcher" -- roughly the speed class of OpenCV's
+ * SIMD batchDistance that matchBF calls. */
+typedef float v8f __attribute__((vector_size(32)));
+#define ORC_TB 512 /* train rows per transposed block (multiple of 32) */
+#define ORC_QB 32  /* query rows per work item */
+
+ORC_API void orc_knn(const float *query, size_t nq, size_t q_stride,
+                     const float *train, size_t nt, size_t t_stride,
+                     int dim, int k, int32_t *idx, float *dist, int32_t *count) {
+    uint8_t *tvalid = (uint8_t *) malloc(nt ? nt : 1);
+#pragma omp parallel for schedule(static)
+    for (long j = 0; j < (long) nt; ++j) tvalid[j] = (uint8_t) orc_is_valid(row_at(train, t_stride, j), dim);
+    long n_qb = (long) ((nq + ORC_QB - 1) / ORC_QB);
+
+#pragma omp parallel
+    {
+        /* tr[g][d] = vector of train rows j0+8g .. j0+8g+7 at dimension d */
+        v8f *tr = (v8f *) aligned_alloc(32, sizeof(v8f) * (size_t) (ORC_TB / 8) * (size_t) dim);
+        uint8_t qvalid[ORC_QB];
+#pragma omp for schedule(dynamic, 1)
+        for (long qb = 0; qb < n_qb; ++qb) {
+            size_t i0 = (size_t) qb * ORC_QB;
+            size_t i1 = i0 + ORC_QB < nq ? i0 + ORC_QB : nq;
+            for (size_t i = i0; i < i1; ++i) {
+                for (int m = 0; m < k; ++m) { idx[i * k + m] = -1; dist[i * k + m] = 0.f; }
+                count[i] = 0;
+                qvalid[i - i0] = (uint8_t) orc_is_valid(row_at(query, q_stride, i), dim);
+            }
+            for (size_t j0 = 0; j0 < nt; j0 += ORC_TB) {
+                size_t jn = j0 + ORC_TB < nt ? ORC_TB : nt - j0;
+                size_t ng = (jn + 7) / 8;
+                for (size_t g = 0; g < ng; ++g)
+                    for (int l = 0; l < 8; ++l) {
+                        size_t j = j0 + 8 * g + l;
+                        const float *t = row_at(train, t_stride, j < nt ? j : nt - 1);
+                        for (int d = 0; d < dim; ++d) ((float *) &tr[g * dim + d])[l] = t[d];
+                    }
+                for (size_t i = i0; i < i1; ++i) {
+                    if (!qvalid[i - i0]) continue;
+                    const float *q = row_at(query, q_stride, i);
+                    int32_t *oi = idx + i * k;
+                    float *od = dist + i * k;
+                    orc_knn_result r;
+                    r.capacity = k; r.count = count[i]; r.indices = oi; r.dists = od;
+                    for (size_t g = 0; g < ng; g += 4) {
+                        size_t gn = g + 4 <= ng ? 4 : ng - g;
+                        v8f s0 = {0}, s1 = {0}, s2 = {0}, s3 = {0};
+                        const v8f *t0 = tr + (g + 0) * dim, *t1 = tr + (g + (gn > 1 ? 1 : 0)) * dim;
+                        const v8f *t2 = tr + (g + (gn > 2 ? 2 : 0)) * dim, *t3 = tr + (g + (gn > 3 ? 3 : 0)) * dim;
+                        for (int d = 0; d < dim; ++d) {
+                            float qd = q[d];
+                            v8f qv = {qd, qd, qd, qd, qd, qd, qd, qd};
+                            v8f d0 = qv - t0[d], d1 = qv - t1[d], d2 = qv - t2[d], d3 = qv - t3[d];
+                            s0 = s0 + d0 * d0; s1 = s1 + d1 * d1; s2 = s2 + d2 * d2; s3 = s3 + d3 * d3;
+                        }
+                        float sq[32];
+                        memcpy(sq, &s0, 32); memcpy(sq + 8, &s1, 32); memcpy(sq + 16, &s2, 32); memcpy(sq + 24, &s3, 32);
+                        for (size_t u = 0; u < gn * 8; ++u) {
+                            size_t j = j0 + 8 * g + u;
+                            if (j >= nt || !tvalid[j]) continue;
+                            float dd = sqrtf(sq[u]);
+                            if (r.count == k && !(dd < od[k - 1])) continue;
+                            orc_knn_result_add(&r, dd, (int32_t) j);
+                        }
+                    }
+                    count[i] = r.count;
+                }
+            }
+        }
+        free(tr);
     }
     free(tvalid);
 }

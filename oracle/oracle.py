@@ -44,6 +44,8 @@ def lib():
         sz = C.c_size_t
         _lib.orc_knn.argtypes = [fp, sz, sz, fp, sz, sz, C.c_int, C.c_int, ip, fp, ip]
         _lib.orc_knn.restype = None
+        _lib.orc_knn_scalar.argtypes = _lib.orc_knn.argtypes
+        _lib.orc_knn_scalar.restype = None
         _lib.orc_match_bf.argtypes = [fp, sz, sz, fp, sz, sz, C.c_int, C.c_int, C.c_int, ip, fp, ip]
         _lib.orc_match_bf.restype = None
         _lib.orc_l2_norm.argtypes = [fp, fp, C.c_int]
@@ -88,17 +90,18 @@ def num_threads():
     return lib().orc_num_threads()
 
 
-def knn(query, train, k):
+def knn(query, train, k, scalar=False):
     """Canonical exact kNN == matchLocal(radius=inf) == matchFLANN result set
     (include/matching.h:637-678, :562-592).  Returns (idx[nq,k] int32 -1 padded,
-    dist[nq,k] float32, count[nq] int32)."""
+    dist[nq,k] float32, count[nq] int32).  scalar=True runs the plain loop nest
+    (orc_knn_scalar); the default is the SIMD-blocked layout of the same arithmetic."""
     q, nq, qs = _rows(query)
     t, nt, ts = _rows(train)
     dim = query.shape[1]
     idx = np.empty((nq, k), np.int32)
     dist = np.empty((nq, k), np.float32)
     cnt = np.empty((nq,), np.int32)
-    lib().orc_knn(_fp(q), nq, qs, _fp(t), nt, ts, dim, k, _ip(idx), _fp(dist), _ip(cnt))
+    (lib().orc_knn_scalar if scalar else lib().orc_knn)(_fp(q), nq, qs, _fp(t), nt, ts, dim, k, _ip(idx), _fp(dist), _ip(cnt))
     return idx, dist, cnt
 
 

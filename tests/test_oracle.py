@@ -191,3 +191,13 @@ def test_spatial_vote_prefers_clustered_candidates():
     cnt = np.array([4], np.int32)
     i2, d2, c2 = orc.spatial_vote(idx, dist, cnt, xyz, 0.05)
     assert c2[0] == 1 and i2[0, 0] == 0 and d2[0, 0] == np.float32(0.2)
+
+
+@pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 1000, 2051, 5), ("shot", 300, 1037, 2), ("rops", 200, 515, 3)])
+def test_simd_layout_is_bit_identical_to_scalar(desc, nq, nt, k):
+    from lidar_global_registration_b200 import synth
+    s, t, d = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    a = orc.knn(s[:, :d], t[:, :d], k)
+    b = orc.knn(s[:, :d], t[:, :d], k, scalar=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
