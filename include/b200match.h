@@ -1,0 +1,166 @@
+/*
+ * b200match.h -- C-ABI of libb200match.so: the B200 (sm_100a) descriptor-space
+ * kNN correspondence search that replaces the reference's CPU matchers.
+ *
+ * The reference (aleksandrina-streltsova/lidar-global-registration) has no FFI
+ * layer; its seams are C++ templates in include/matching.h.  Every entry point
+ * below names the reference interface it stands in for (paths relative to the
+ * reference root).  The C++ shim include/b200match_shim.hpp puts the reference's
+ * own signatures (matchBF<FeatureT>, OneSided/LeftToRight/Ratio matchers) back
+ * on top of these calls; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; return 0 = ok, non-zero = error
+ * (message via b200m_last_error); the caller owns every host buffer, the
+ * library owns device memory it allocates; one context per host thread, calls on
+ * one context are serialised.  There is NO CPU fallback: without a CUDA device
+ * b200m_create fails.
+ */
+#ifndef B200MATCH_H
+#define B200MATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200M_API __attribute__((visibility("default")))
+
+typedef struct b200m_ctx b200m_ctx;
+
+/* == reference `Correspondence` (include/common.h:120-131): pcl::Correspondence
+ * {int index_query; int index_match; float distance;} + float threshold -- 16 B. */
+typedef struct {
+    int32_t index_query;
+    int32_t index_match;
+    float distance;
+    float threshold;
+} b200m_corr;
+
+/* filter policy == which reference matcher class the call stands in for */
+enum {
+    B200M_MODE_KNN_ONLY = 0,     /* raw k-lists: matchBF / matchFLANN / matchLocal(inf) seam, include/matching.h:368-383 */
+    B200M_MODE_ONE_SIDED = 1,    /* OneSidedMatcher::match_impl, include/matching.h:395-411 */
+    B200M_MODE_MUTUAL = 2,       /* LeftToRightMatcher::match_impl (k-list form), include/matching.h:428-453 */
+    B200M_MODE_RATIO = 3,        /* RatioMatcher (reference stub :470-473; semantics from include/common.h:50-51) */
+    B200M_MODE_RATIO_MUTUAL = 4  /* ratio test on the forward lists, then the mutual test */
+};
+
+/* how candidates are produced; the result is the same exact FP32 answer either way */
+enum {
+    B200M_PREC_TC_F16 = 0,   /* tcgen05 FP16-operand candidate pass (certified superset) + exact FP32 re-rank (default) */
+    B200M_PREC_F32_EXACT = 2 /* CUDA-core exact FP32 brute force only (no tensor cores) */
+};
+
+/* The hot-path subset of the reference's AlignmentParameters (include/common.h:135-163):
+ * k = randomness (:147), ratio_thr = MATCHING_RATIO_THRESHOLD (:50), distance_thr (:139). */
+typedef struct {
+    int32_t k;            /* neighbours per query, 1..32 */
+    int32_t mode;         /* B200M_MODE_* */
+    float ratio_thr;      /* 1.1f in the reference's constants */
+    float distance_thr;   /* AlignmentParameters::distance_thr; caps the per-correspondence threshold */
+    int32_t precision;    /* B200M_PREC_* */
+    int32_t cand_cap;     /* candidate slots per query row and train split in the tensor-core pass
+                             (0 = default chosen from k; rows that overflow go through the exact row kernel) */
+} b200m_params;
+
+/* per-call device timings and counters, filled by the *_device calls when
+ * profiling is on (b200m_set_profiling); times are CUDA-event milliseconds on the
+ * context's stream, accumulated since the last b200m_reset_stats. */
+typedef struct {
+    double ms_pack;        /* AoS -> f32 tiles + validity */
+    double ms_prepare;     /* centring/scaling + FP16 operand tiles */
+    double ms_candidates;  /* tcgen05 candidate kernel */
+    double ms_rerank;      /* exact FP32 re-rank of the candidates */
+    double ms_fallback;    /* exact row kernel over overflowed rows (or the whole F32_EXACT pass) */
+    double ms_filter;      /* filter + compaction (+ average distance) */
+    int64_t launches;      /* kernels launched by this library */
+    int64_t candidate_launches;
+    int64_t rows_total;    /* query rows processed by knn */
+    int64_t rows_flagged;  /* rows whose candidate list overflowed and went through the exact row kernel */
+    int64_t candidates;    /* candidate (query, train) pairs re-ranked exactly */
+} b200m_stats;
+
+/* ---- context -------------------------------------------------------------- */
+B200M_API int b200m_create(b200m_ctx **ctx, int device);
+B200M_API void b200m_destroy(b200m_ctx *ctx);
+B200M_API const char *b200m_last_error(const b200m_ctx *ctx); /* ctx may be NULL: last create error */
+/* run on the caller's CUDA stream (a cudaStream_t passed as void*), e.g. torch's current stream; NULL = own stream */
+B200M_API int b200m_set_stream(b200m_ctx *ctx, void *cuda_stream);
+B200M_API int b200m_sync(b200m_ctx *ctx);
+B200M_API int b200m_set_profiling(b200m_ctx *ctx, int on);
+B200M_API int b200m_get_stats(b200m_ctx *ctx, b200m_stats *out); /* synchronises the stream */
+B200M_API int b200m_reset_stats(b200m_ctx *ctx);
+
+/* ---- descriptor upload: replaces pcl2cv<FeatureT> (include/matching.h:553-560) --
+ * side 0 = source (query of the forward pass), side 1 = target (train of the forward
+ * pass).  `base` points at the first descriptor value of row 0, rows are
+ * `stride_bytes` apart (sizeof(FeatureT): 132 FPFH33, 540 Histogram<135>, 1444 SHOT352),
+ * `dim` leading floats of each row are the descriptor
+ * (DefaultPointRepresentation<FeatureT>::getNumberOfDimensions()).
+ * index_offset is added to every index reported for rows of this side (target
+ * shards of a multi-GPU run report global row numbers). */
+B200M_API int b200m_upload(b200m_ctx *ctx, int side, const float *host_base, size_t n,
+                           size_t stride_bytes, int dim, int64_t index_offset);
+B200M_API int b200m_upload_device(b200m_ctx *ctx, int side, const float *device_base, size_t n,
+                                  size_t stride_bytes, int dim, int64_t index_offset);
+
+/* ---- raw k-lists: replaces matchBF / matchFLANN / matchLocal(radius=inf) ---------
+ * (include/matching.h:594-634, :562-592, :637-678).  direction 0: queries = side 0,
+ * train = side 1; direction 1: roles swapped (the reverse pass of the mutual filter,
+ * include/matching.h:432).  Query rows [row_begin,row_end) of the query side are
+ * processed (row_end = 0 means "all"); outputs are (row_end-row_begin) x k, row-major:
+ * idx (-1 padded), dist (L2, sqrt'ed, ascending; ties -> lower index), count.
+ * Entry i is empty (count 0) for a non-finite query; non-finite train rows are never
+ * returned. */
+B200M_API int b200m_knn(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin,
+                        size_t row_end, int32_t *idx, float *dist, int32_t *count);
+B200M_API int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin,
+                               size_t row_end, int32_t *d_idx, float *d_dist, int32_t *d_count);
+
+/* ---- whole matcher call: replaces FeatureBasedMatcher::match()'s match_impl ------
+ * (include/matching.h:395-411, :428-453) at the k-list seam, single GPU, host buffers.
+ * thr_src / thr_tgt: optional per-point thresholds (calculateSmoothedDensities,
+ * src/common.cpp:531-547) or NULL; emitted threshold = min(max(thr_src[i], thr_tgt[j]),
+ * distance_thr).  out: capacity `cap` records, ascending index_query; *n_out = number
+ * produced (error if cap is too small; nq*k always suffices).  avg_first_dist (may be
+ * NULL) = FeatureBasedMatcher::getAverageDistance() (src/matching.cpp:3-19). */
+B200M_API int b200m_match(b200m_ctx *ctx, const b200m_params *p, const float *thr_src,
+                          const float *thr_tgt, b200m_corr *out, size_t cap, size_t *n_out,
+                          float *avg_first_dist);
+
+/* ---- device-side building blocks for sharded (multi-GPU) runs ----------------
+ * All pointers are device pointers on the context's device; work is queued on the
+ * context's stream.  Forward tables cover query rows [row_begin,row_end) of side 0;
+ * the reverse table (mutual modes) covers ALL rows of side 1 and carries side-0 row
+ * numbers.  d_n_out: one device size_t-sized (uint64) counter; d_avg may be NULL. */
+B200M_API int b200m_filter_device(b200m_ctx *ctx, const b200m_params *p, size_t row_begin, size_t row_end,
+                                  const int32_t *d_fidx, const float *d_fdist, const int32_t *d_fcount,
+                                  const int32_t *d_ridx, const float *d_rdist, const int32_t *d_rcount,
+                                  size_t n_rev_rows, const float *d_thr_src, const float *d_thr_tgt,
+                                  b200m_corr *d_out, size_t cap, unsigned long long *d_n_out, float *d_avg);
+/* per-query merge of `n_lists` k-lists (target-sharded run after the all-gather):
+ * tables are [n_lists][nq][k] / [n_lists][nq]; keeps the k best by (dist, idx) --
+ * the cross-block role of updateMultivaluedCorrespondence (src/common.cpp:517-529)
+ * under the canonical tie rule. */
+B200M_API int b200m_merge_device(b200m_ctx *ctx, int k, int n_lists, size_t nq,
+                                 const int32_t *d_idx_in, const float *d_dist_in, const int32_t *d_count_in,
+                                 int32_t *d_idx, float *d_dist, int32_t *d_count);
+
+B200M_API int b200m_version(void);
+
+/* ---- test hooks (used by tests/ only; not part of the reference-facing surface) ----
+ * b200m_debug_operands: copy the FP16 operand tiles the tensor-core pass reads to the host:
+ *   as_query=1 -> [n_pad][kp] rows (-2*x16, 1,1,1, 0..), else the train form (x16, |x16|^2 hi/mid/lo, 0..);
+ *   norm16 (may be NULL) receives |x16|^2 per row [n_pad]; scale/kp/n_pad are returned through the pointers.
+ * b200m_debug_tc_tile: raw tensor-core accumulators (|b16|^2 - 2 a16.b16) of query rows
+ *   [q_row0, q_row0+128) x train rows [t_tile*256, +256) of `direction`, row-major [128][256]. */
+B200M_API int b200m_debug_operands(b200m_ctx *ctx, int side, int as_query, uint16_t *host_out, size_t out_halves,
+                                   float *norm16, float *scale, int32_t *kp, int64_t *n_pad);
+B200M_API int b200m_debug_tc_tile(b200m_ctx *ctx, int direction, size_t q_row0, size_t t_tile, float *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MATCH_H */

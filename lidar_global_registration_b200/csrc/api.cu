@@ -1,0 +1,469 @@
+// api.cu -- the C-ABI of libb200match.so (see include/b200match.h): context, descriptor
+// upload, the kNN driver (tensor-core candidates -> exact re-rank -> exact fallback) and the
+// whole-matcher call.  Host-side C++ only; every kernel lives in its own translation unit.
+//
+// Reference seams replaced (paths relative to the reference root):
+//   b200m_upload   pcl2cv<FeatureT>                      include/matching.h:553-560
+//   b200m_knn      matchBF / matchFLANN / matchLocal(inf) include/matching.h:594-634, :562-592, :637-678
+//   b200m_match    OneSided/LeftToRight(/Ratio)Matcher::match_impl + printDebugInfo's average
+//                  include/matching.h:395-411, :428-453, :470-473; src/matching.cpp:3-19
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "internal.cuh"
+
+static thread_local std::string g_create_err;
+
+cudaError_t DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap && p) return cudaSuccess;
+    if (p) {
+        cudaError_t e = cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (e != cudaSuccess) return e;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+}
+
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+int b200m_fail(b200m_ctx *ctx, const char *what, cudaError_t e, const char *file, int line) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")";
+    if (ctx) ctx->err = m; else g_create_err = m;
+    return 1;
+}
+
+int b200m_fail_msg(b200m_ctx *ctx, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_err = msg;
+    return 1;
+}
+
+#define REQUIRE_CTX()                                          \
+    do {                                                       \
+        if (!ctx) return b200m_fail_msg(nullptr, "null context"); \
+        CK(cudaSetDevice(ctx->device));                        \
+    } while (0)
+
+extern "C" {
+
+int b200m_version(void) { return 100; }
+
+int b200m_create(b200m_ctx **out, int device) {
+    b200m_ctx *ctx = nullptr;
+    if (!out) return b200m_fail_msg(nullptr, "b200m_create: null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return b200m_fail_msg(nullptr, std::string("b200m_create: no CUDA device (there is no CPU fallback): ") +
+                                           cudaGetErrorString(e));
+    if (device < 0 || device >= n) return b200m_fail_msg(nullptr, "b200m_create: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return b200m_fail_msg(nullptr, std::string("b200m_create: this library is built for sm_100a (B200) only; device is ") +
+                                           prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    ctx = new b200m_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev[1])) != cudaSuccess) {
+        b200m_fail(nullptr, "b200m_create", e, __FILE__, __LINE__);
+        delete ctx;
+        return 1;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return 0;
+}
+
+void b200m_destroy(b200m_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < 2; ++s) {
+        Side &sd = ctx->side[s];
+        sd.staging.release(); sd.f32.release(); sd.valid.release();
+        sd.op_query.release(); sd.op_train.release(); sd.norm16.release();
+        ctx->ws_thr[s].release();
+    }
+    ctx->prep.mean.release(); ctx->prep.red.release();
+    DevBuf *ws[] = {&ctx->ws_cand_idx, &ctx->ws_cand_cnt, &ctx->ws_flag_rows, &ctx->ws_counters, &ctx->ws_scan,
+                    &ctx->ws_out, &ctx->ws_misc, &ctx->ws_fidx, &ctx->ws_fdist, &ctx->ws_fcnt, &ctx->ws_ridx,
+                    &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr};
+    for (DevBuf *b : ws) b->release();
+    tc_release(ctx);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *b200m_last_error(const b200m_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int b200m_set_stream(b200m_ctx *ctx, void *cuda_stream) {
+    REQUIRE_CTX();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int b200m_sync(b200m_ctx *ctx) {
+    REQUIRE_CTX();
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200m_set_profiling(b200m_ctx *ctx, int on) {
+    REQUIRE_CTX();
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int b200m_get_stats(b200m_ctx *ctx, b200m_stats *out) {
+    REQUIRE_CTX();
+    if (!out) return b200m_fail_msg(ctx, "b200m_get_stats: null output");
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->stats;
+    return 0;
+}
+
+int b200m_reset_stats(b200m_ctx *ctx) {
+    REQUIRE_CTX();
+    ctx->stats = b200m_stats{};
+    return 0;
+}
+
+// ---- upload -----------------------------------------------------------------------------
+static int upload_common(b200m_ctx *ctx, int side, const float *device_aos, size_t n, size_t stride_bytes, int dim,
+                         int64_t index_offset) {
+    Side &sd = ctx->side[side];
+    sd.n = n;
+    sd.n_pad = (n + B200M_TILE_N - 1) / B200M_TILE_N * B200M_TILE_N;
+    sd.dim = dim;
+    sd.dp = (dim + 3) / 4 * 4;
+    sd.kp = (dim + B200M_AUG_COLS + 63) / 64 * 64;
+    sd.index_offset = index_offset;
+    sd.version++;
+    ctx->prep.ready = false;
+    if (n == 0) return 0;
+    CK(sd.f32.reserve(sizeof(float) * n * (size_t) sd.dp));
+    CK(sd.valid.reserve(n));
+    StatTimer t(ctx, &ctx->stats.ms_pack);
+    CK(launch_pack_f32(device_aos, n, stride_bytes, dim, sd.dp, sd.f32.as<float>(), sd.valid.as<uint8_t>(), ctx->stream));
+    ctx->stats.launches += 1;
+    t.stop();
+    return 0;
+}
+
+static int check_upload_args(b200m_ctx *ctx, int side, const float *base, size_t n, size_t stride_bytes, int dim) {
+    if (side != 0 && side != 1) return b200m_fail_msg(ctx, "b200m_upload: side must be 0 (source) or 1 (target)");
+    if (dim < 1 || dim > B200M_MAX_DIM) return b200m_fail_msg(ctx, "b200m_upload: dim out of range [1, 1024]");
+    if (stride_bytes % 4 != 0 || stride_bytes < (size_t) dim * 4)
+        return b200m_fail_msg(ctx, "b200m_upload: stride_bytes must be a multiple of 4 and >= 4*dim");
+    if (n > 0 && !base) return b200m_fail_msg(ctx, "b200m_upload: null descriptor pointer");
+    if (n >= (size_t) 1 << 31) return b200m_fail_msg(ctx, "b200m_upload: more than 2^31-1 rows (indices are int32, as pcl::index_t)");
+    return 0;
+}
+
+int b200m_upload(b200m_ctx *ctx, int side, const float *host_base, size_t n, size_t stride_bytes, int dim,
+                 int64_t index_offset) {
+    REQUIRE_CTX();
+    if (check_upload_args(ctx, side, host_base, n, stride_bytes, dim)) return 1;
+    Side &sd = ctx->side[side];
+    if (n) {
+        // last row may be shorter than the stride (the caller owns only dim floats of it)
+        size_t bytes = (n - 1) * stride_bytes + (size_t) dim * 4;
+        CK(sd.staging.reserve(n * stride_bytes));
+        CK(cudaMemcpyAsync(sd.staging.p, host_base, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return upload_common(ctx, side, sd.staging.as<float>(), n, stride_bytes, dim, index_offset);
+}
+
+int b200m_upload_device(b200m_ctx *ctx, int side, const float *device_base, size_t n, size_t stride_bytes, int dim,
+                        int64_t index_offset) {
+    REQUIRE_CTX();
+    if (check_upload_args(ctx, side, device_base, n, stride_bytes, dim)) return 1;
+    return upload_common(ctx, side, device_base, n, stride_bytes, dim, index_offset);
+}
+
+// ---- kNN --------------------------------------------------------------------------------
+__global__ void fill_empty_kernel(size_t n_rows, int k, int32_t *idx, float *dist, int32_t *count) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rows * (size_t) k) { idx[i] = -1; dist[i] = 0.f; }
+    if (i < n_rows) count[i] = 0;
+}
+
+static int check_params(b200m_ctx *ctx, const b200m_params *p) {
+    if (!p) return b200m_fail_msg(ctx, "null params");
+    if (p->k < 1 || p->k > B200M_MAX_K) return b200m_fail_msg(ctx, "params.k must be in [1, 32]");
+    if (p->mode < B200M_MODE_KNN_ONLY || p->mode > B200M_MODE_RATIO_MUTUAL) return b200m_fail_msg(ctx, "params.mode unknown");
+    if (p->precision != B200M_PREC_TC_F16 && p->precision != B200M_PREC_F32_EXACT)
+        return b200m_fail_msg(ctx, "params.precision unknown");
+    if ((p->mode == B200M_MODE_RATIO || p->mode == B200M_MODE_RATIO_MUTUAL) && p->k < 2)
+        return b200m_fail_msg(ctx, "ratio modes need k >= 2 (MATCHING_RATIO_K, reference include/common.h:51)");
+    return 0;
+}
+
+int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t row_end,
+                     int32_t *d_idx, float *d_dist, int32_t *d_count) {
+    REQUIRE_CTX();
+    if (check_params(ctx, p)) return 1;
+    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "b200m_knn: direction must be 0 or 1");
+    Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    if (row_end == 0) row_end = q.n;
+    if (row_begin > row_end || row_end > q.n) return b200m_fail_msg(ctx, "b200m_knn: query row range out of bounds");
+    const size_t n_rows = row_end - row_begin;
+    if (n_rows == 0) return 0;
+    if (!d_idx || !d_dist || !d_count) return b200m_fail_msg(ctx, "b200m_knn: null output pointer");
+    if (t.n && q.dim != t.dim) return b200m_fail_msg(ctx, "b200m_knn: source and target descriptor lengths differ");
+    const int k = p->k;
+    cudaStream_t st = ctx->stream;
+    ctx->stats.rows_total += (int64_t) n_rows;
+    if (t.n == 0) {   // nothing to match against: every list is empty
+        size_t ne = n_rows * (size_t) k;
+        fill_empty_kernel<<<(unsigned) ((ne + 255) / 256), 256, 0, st>>>(n_rows, k, d_idx, d_dist, d_count);
+        ctx->stats.launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    bool use_tc = p->precision == B200M_PREC_TC_F16 && tc_supported(ctx, q.dim, k);
+    if (use_tc) {
+        if (!ctx->prep.ready || ctx->prep.ver[0] != ctx->side[0].version || ctx->prep.ver[1] != ctx->side[1].version) {
+            StatTimer tp(ctx, &ctx->stats.ms_prepare);
+            CK(launch_tc_prepare(ctx));
+            tp.stop();
+        }
+        use_tc = ctx->prep.usable;
+    }
+    if (!use_tc) {
+        StatTimer tf(ctx, &ctx->stats.ms_fallback);
+        CK(launch_exact_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(),
+                             t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_rows, nullptr, nullptr, k, d_idx,
+                             d_dist, d_count, 1 << 30, st));
+        ctx->stats.launches += 1;
+        tf.stop();
+        return 0;
+    }
+    // 1. tensor-core candidate pass: per row a certified superset of the exact top-k
+    int n_lists = 0, cap = 0;
+    {
+        StatTimer tc(ctx, &ctx->stats.ms_candidates);
+        if (tc_candidates(ctx, direction, row_begin, n_rows, k, p->cand_cap, &n_lists, &cap, nullptr, 0)) return 1;
+        tc.stop();
+    }
+    // 2. exact FP32 re-rank of the candidates (bit-identical arithmetic to the reference)
+    CK(ctx->ws_flag_rows.reserve(sizeof(int32_t) * n_rows));
+    CK(ctx->ws_counters.reserve(64));
+    CK(cudaMemsetAsync(ctx->ws_counters.p, 0, 64, st));
+    {
+        StatTimer tr(ctx, &ctx->stats.ms_rerank);
+        CK(launch_rerank(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(), t.valid.as<uint8_t>(),
+                         t.n, t.index_offset, row_begin, n_rows, k, ctx->ws_cand_idx.as<int32_t>(),
+                         ctx->ws_cand_cnt.as<int32_t>(), n_lists, cap, d_idx, d_dist, d_count,
+                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), st));
+        ctx->stats.launches += 1;
+        tr.stop();
+    }
+    // 3. rows whose candidate list overflowed: exact row kernel (row list and its length stay on the device)
+    {
+        StatTimer tf(ctx, &ctx->stats.ms_fallback);
+        size_t max_blocks = (size_t) ctx->sm_count * 8;
+        CK(launch_exact_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(),
+                             t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_rows,
+                             ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), k, d_idx, d_dist, d_count,
+                             (int) (n_rows < max_blocks ? n_rows : max_blocks), st));
+        ctx->stats.launches += 1;
+        tf.stop();
+    }
+    if (ctx->profiling) {
+        struct { int32_t flagged, pad; unsigned long long cands; } h;
+        CK(cudaMemcpyAsync(&h, ctx->ws_counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats.rows_flagged += h.flagged;
+        ctx->stats.candidates += (int64_t) h.cands;
+    }
+    return 0;
+}
+
+int b200m_knn(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t row_end, int32_t *idx,
+              float *dist, int32_t *count) {
+    REQUIRE_CTX();
+    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "b200m_knn: direction must be 0 or 1");
+    if (check_params(ctx, p)) return 1;
+    Side &q = ctx->side[direction];
+    size_t re = row_end == 0 ? q.n : row_end;
+    if (row_begin > re || re > q.n) return b200m_fail_msg(ctx, "b200m_knn: query row range out of bounds");
+    size_t n_rows = re - row_begin;
+    if (n_rows == 0) return 0;
+    if (!idx || !dist || !count) return b200m_fail_msg(ctx, "b200m_knn: null output pointer");
+    const int k = p->k;
+    CK(ctx->ws_fidx.reserve(sizeof(int32_t) * n_rows * k));
+    CK(ctx->ws_fdist.reserve(sizeof(float) * n_rows * k));
+    CK(ctx->ws_fcnt.reserve(sizeof(int32_t) * n_rows));
+    if (b200m_knn_device(ctx, p, direction, row_begin, re, ctx->ws_fidx.as<int32_t>(), ctx->ws_fdist.as<float>(),
+                         ctx->ws_fcnt.as<int32_t>()))
+        return 1;
+    CK(cudaMemcpyAsync(idx, ctx->ws_fidx.p, sizeof(int32_t) * n_rows * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist, ctx->ws_fdist.p, sizeof(float) * n_rows * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(count, ctx->ws_fcnt.p, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- filters ----------------------------------------------------------------------------
+int b200m_filter_device(b200m_ctx *ctx, const b200m_params *p, size_t row_begin, size_t row_end,
+                        const int32_t *d_fidx, const float *d_fdist, const int32_t *d_fcount,
+                        const int32_t *d_ridx, const float *d_rdist, const int32_t *d_rcount, size_t n_rev_rows,
+                        const float *d_thr_src, const float *d_thr_tgt, b200m_corr *d_out, size_t cap,
+                        unsigned long long *d_n_out, float *d_avg) {
+    REQUIRE_CTX();
+    if (check_params(ctx, p)) return 1;
+    if (p->mode == B200M_MODE_KNN_ONLY) return b200m_fail_msg(ctx, "b200m_filter: mode KNN_ONLY has no filter");
+    if (row_end < row_begin) return b200m_fail_msg(ctx, "b200m_filter: bad row range");
+    const size_t n_rows = row_end - row_begin;
+    const bool mutual = p->mode == B200M_MODE_MUTUAL || p->mode == B200M_MODE_RATIO_MUTUAL;
+    if (mutual && n_rev_rows && (!d_ridx || !d_rdist || !d_rcount))
+        return b200m_fail_msg(ctx, "b200m_filter: mutual modes need the reverse table");
+    if (!d_n_out || (n_rows && (!d_fidx || !d_fdist || !d_fcount)) || (cap && !d_out))
+        return b200m_fail_msg(ctx, "b200m_filter: null pointer");
+    size_t ws = filter_scan_ws_bytes(n_rows, p->k);
+    CK(ctx->ws_scan.reserve(ws));
+    int launches = 0;
+    StatTimer t(ctx, &ctx->stats.ms_filter);
+    CK(launch_filter(p->mode, p->k, p->ratio_thr, p->distance_thr, row_begin, n_rows, d_fidx, d_fdist, d_fcount, d_ridx,
+                     d_rdist, d_rcount, n_rev_rows, d_thr_src, d_thr_tgt, ctx->side[0].index_offset, d_out, cap, d_n_out,
+                     d_avg, ctx->ws_scan.p, ctx->ws_scan.cap, ctx->stream, &launches));
+    ctx->stats.launches += launches;
+    t.stop();
+    return 0;
+}
+
+int b200m_merge_device(b200m_ctx *ctx, int k, int n_lists, size_t nq, const int32_t *d_idx_in, const float *d_dist_in,
+                       const int32_t *d_count_in, int32_t *d_idx, float *d_dist, int32_t *d_count) {
+    REQUIRE_CTX();
+    if (k < 1 || k > B200M_MAX_K || n_lists < 1 || n_lists > 8)
+        return b200m_fail_msg(ctx, "b200m_merge: k in [1,32], n_lists in [1,8]");
+    CK(launch_merge(k, n_lists, nq, d_idx_in, d_dist_in, d_count_in, d_idx, d_dist, d_count, ctx->stream));
+    ctx->stats.launches += nq ? 1 : 0;
+    return 0;
+}
+
+int b200m_match(b200m_ctx *ctx, const b200m_params *p, const float *thr_src, const float *thr_tgt, b200m_corr *out,
+                size_t cap, size_t *n_out, float *avg_first_dist) {
+    REQUIRE_CTX();
+    if (check_params(ctx, p)) return 1;
+    if (p->mode == B200M_MODE_KNN_ONLY) return b200m_fail_msg(ctx, "b200m_match: use b200m_knn for raw k-lists");
+    if (!n_out) return b200m_fail_msg(ctx, "b200m_match: null n_out");
+    *n_out = 0;
+    Side &src = ctx->side[0], &tgt = ctx->side[1];
+    if ((thr_src == nullptr) != (thr_tgt == nullptr))
+        return b200m_fail_msg(ctx, "b200m_match: give both threshold arrays or neither");
+    const int k = p->k;
+    const bool mutual = p->mode == B200M_MODE_MUTUAL || p->mode == B200M_MODE_RATIO_MUTUAL;
+    const size_t nq = src.n, nt = tgt.n;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->ws_misc.reserve(64));
+    float *d_avg = ctx->ws_misc.as<float>();
+    unsigned long long *d_n = reinterpret_cast<unsigned long long *>(ctx->ws_misc.as<char>() + 16);
+    if (nq == 0) {
+        if (avg_first_dist) *avg_first_dist = 3.402823466e+38F;   // FLT_MAX, reference include/matching.h:41
+        return 0;
+    }
+    CK(ctx->ws_fidx.reserve(sizeof(int32_t) * nq * k));
+    CK(ctx->ws_fdist.reserve(sizeof(float) * nq * k));
+    CK(ctx->ws_fcnt.reserve(sizeof(int32_t) * nq));
+    if (b200m_knn_device(ctx, p, 0, 0, nq, ctx->ws_fidx.as<int32_t>(), ctx->ws_fdist.as<float>(), ctx->ws_fcnt.as<int32_t>()))
+        return 1;
+    if (mutual && nt) {
+        CK(ctx->ws_ridx.reserve(sizeof(int32_t) * nt * k));
+        CK(ctx->ws_rdist.reserve(sizeof(float) * nt * k));
+        CK(ctx->ws_rcnt.reserve(sizeof(int32_t) * nt));
+        if (b200m_knn_device(ctx, p, 1, 0, nt, ctx->ws_ridx.as<int32_t>(), ctx->ws_rdist.as<float>(), ctx->ws_rcnt.as<int32_t>()))
+            return 1;
+    }
+    const float *d_thr_s = nullptr, *d_thr_t = nullptr;
+    if (thr_src && nt) {
+        CK(ctx->ws_thr[0].reserve(sizeof(float) * nq));
+        CK(ctx->ws_thr[1].reserve(sizeof(float) * nt));
+        CK(cudaMemcpyAsync(ctx->ws_thr[0].p, thr_src, sizeof(float) * nq, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ws_thr[1].p, thr_tgt, sizeof(float) * nt, cudaMemcpyHostToDevice, st));
+        d_thr_s = ctx->ws_thr[0].as<float>();
+        d_thr_t = ctx->ws_thr[1].as<float>();
+    }
+    const size_t kk = (p->mode == B200M_MODE_MUTUAL) ? (size_t) k : 1;
+    const size_t max_out = nq * kk;
+    CK(ctx->ws_corr.reserve(sizeof(b200m_corr) * max_out));
+    if (b200m_filter_device(ctx, p, 0, nq, ctx->ws_fidx.as<int32_t>(), ctx->ws_fdist.as<float>(), ctx->ws_fcnt.as<int32_t>(),
+                            ctx->ws_ridx.as<int32_t>(), ctx->ws_rdist.as<float>(), ctx->ws_rcnt.as<int32_t>(),
+                            mutual ? nt : 0, d_thr_s, d_thr_t, ctx->ws_corr.as<b200m_corr>(), max_out, d_n,
+                            avg_first_dist ? d_avg : nullptr))
+        return 1;
+    struct { float avg; float pad[3]; unsigned long long n; } h;
+    CK(cudaMemcpyAsync(&h, ctx->ws_misc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (avg_first_dist) *avg_first_dist = h.avg;
+    *n_out = (size_t) h.n;
+    if (h.n > cap) return b200m_fail_msg(ctx, "b200m_match: output capacity too small (" + std::to_string(h.n) + " correspondences)");
+    if (h.n) {
+        if (!out) return b200m_fail_msg(ctx, "b200m_match: null output buffer");
+        CK(cudaMemcpyAsync(out, ctx->ws_corr.p, sizeof(b200m_corr) * h.n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// ---- test hooks -------------------------------------------------------------------------
+int b200m_debug_operands(b200m_ctx *ctx, int side, int as_query, uint16_t *host_out, size_t out_halves, float *norm16,
+                         float *scale, int32_t *kp, int64_t *n_pad) {
+    REQUIRE_CTX();
+    if (side != 0 && side != 1) return b200m_fail_msg(ctx, "debug_operands: bad side");
+    if (!ctx->side[0].n || !ctx->side[1].n) return b200m_fail_msg(ctx, "debug_operands: upload both sides first");
+    if (!tc_supported(ctx, ctx->side[side].dim, 1)) return b200m_fail_msg(ctx, "debug_operands: dim not supported by the tensor-core pass");
+    if (!ctx->prep.ready || ctx->prep.ver[0] != ctx->side[0].version || ctx->prep.ver[1] != ctx->side[1].version)
+        CK(launch_tc_prepare(ctx));
+    Side &sd = ctx->side[side];
+    size_t halves = sd.n_pad * (size_t) sd.kp;
+    if (kp) *kp = sd.kp;
+    if (n_pad) *n_pad = (int64_t) sd.n_pad;
+    if (scale) *scale = ctx->prep.scale;
+    if (host_out) {
+        if (out_halves < halves) return b200m_fail_msg(ctx, "debug_operands: output buffer too small");
+        CK(cudaMemcpyAsync(host_out, as_query ? sd.op_query.p : sd.op_train.p, halves * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (norm16) CK(cudaMemcpyAsync(norm16, sd.norm16.p, sizeof(float) * sd.n_pad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200m_debug_tc_tile(b200m_ctx *ctx, int direction, size_t q_row0, size_t t_tile, float *host_out) {
+    REQUIRE_CTX();
+    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "debug_tc_tile: bad direction");
+    Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    if (!q.n || !t.n || !host_out) return b200m_fail_msg(ctx, "debug_tc_tile: upload both sides first");
+    if (!tc_supported(ctx, q.dim, 1)) return b200m_fail_msg(ctx, "debug_tc_tile: dim not supported by the tensor-core pass");
+    if (q_row0 >= q.n || t_tile * B200M_TILE_N >= t.n_pad) return b200m_fail_msg(ctx, "debug_tc_tile: tile out of range");
+    if (!ctx->prep.ready || ctx->prep.ver[0] != ctx->side[0].version || ctx->prep.ver[1] != ctx->side[1].version)
+        CK(launch_tc_prepare(ctx));
+    CK(ctx->ws_out.reserve(sizeof(float) * B200M_TILE_M * B200M_TILE_N));
+    CK(cudaMemsetAsync(ctx->ws_out.p, 0xff, sizeof(float) * B200M_TILE_M * B200M_TILE_N, ctx->stream));
+    int n_lists = 0, cap = 0;
+    size_t n_rows = q.n - q_row0 < (size_t) B200M_TILE_M ? q.n - q_row0 : (size_t) B200M_TILE_M;
+    if (tc_candidates(ctx, direction, q_row0, n_rows, 1, 0, &n_lists, &cap, ctx->ws_out.as<float>(), t_tile)) return 1;
+    CK(cudaMemcpyAsync(host_out, ctx->ws_out.p, sizeof(float) * B200M_TILE_M * B200M_TILE_N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

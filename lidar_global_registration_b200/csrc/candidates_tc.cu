@@ -1,0 +1,500 @@
+// candidates_tc.cu -- the tensor-core candidate pass (sm_100a: TMA + tcgen05.mma + TMEM).
+//
+// Replaces the O(Nq*Nt*D) inner loop of cv::BFMatcher::knnMatch as called by matchBF
+// (reference include/matching.h:612) and the kd-tree search of matchFLANN (:581).
+//
+// For a tile of 128 query rows the CTA streams every 256-row train tile through
+//     acc[i][j] = sum_d (-2*a16[i][d]) * b16[j][d] + 1*nb_hi[j] + 1*nb_mid[j] + 1*nb_lo[j]
+//               = |b16_j|^2 - 2 a16_i.b16_j                      (FP16 operands, FP32 accumulate in TMEM)
+// i.e. the squared distance minus the per-row constant |a16_i|^2.  Operands are the K-major,
+// 128B-swizzled tiles written by pack.cu and fetched by TMA; one elected thread issues
+// tcgen05.mma (M=128, N=256, K=16) into one of two 256-column TMEM accumulators while the four
+// epilogue warps drain the other with tcgen05.ld (lane == query row, so a thread owns a row).
+//
+// Selection is a running-threshold filter, never a top-k' truncation: each row keeps the k
+// smallest accumulator VALUES seen so far (tk[]) and appends the index of every column with
+//     acc <= thr(tk[k-1])
+// to the row's candidate list in HBM.  thr(T) over-approximates, by the FP16 rounding of both
+// rows (eta), the tensor-core accumulation slop and the FP32 rounding of the reference's own
+// sequential sum (gamma), the largest accumulator an exact top-k member can have once k
+// values <= T are known (derivation in DESIGN.md "Certified candidates").  Since tk[k-1] only
+// decreases, the list is a superset of the exact top-k BY CONSTRUCTION; the exact FP32 re-rank
+// (exact.cu) then reproduces the reference's distances and (dist, index) order bit for bit.
+// A row whose list overflows its `cap` slots is re-done by the exact row kernel.
+//
+// Work decomposition: grid = (query tiles, train splits); each split writes its own list.
+#include <cuda.h>
+#include <math.h>
+#include <stdio.h>
+
+#include "internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
+constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
+constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 8;
+constexpr int kMaxKAtoms = 10;
+constexpr int kMaxLists = 16;
+constexpr long long kWaitLimitCycles = 4000000000LL;   // ~2 s: a wedged pipeline traps instead of hanging the GPU
+
+struct TcParams {
+    int ka;               // 64-half K atoms per row (kp / 64)
+    int ksteps;           // K=16 MMA steps actually needed: ceil((dim + 3) / 16)
+    int stages;           // B ring depth
+    int n_ttiles;         // 256-row train tiles
+    int tiles_per_split;
+    int q_row0;           // first query row of this call (row_begin)
+    int n_rows;           // query rows of this call
+    int k;
+    int cap;              // candidate slots per row and list
+    int dim;
+    float bmax;           // max |b16| over the train side
+    const float *q_norm16;
+    int32_t *cand_idx;    // [n_lists][n_rows][cap]
+    int32_t *cand_cnt;    // [n_lists][n_rows]
+    float *dump;          // debug: raw accumulators of one tile [128][256]
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kWaitLimitCycles) {
+            printf("b200match: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+                   blockIdx.y, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(ignored for swizzled K-major)=1 <<16 | SBO = 1024 B (8 rows x 128 B) >>4 <<32 | version 1 <<46 |
+// layout SWIZZLE_128B (2) <<61.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t) ((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t) 1 << 16;
+    d |= (uint64_t) (1024 >> 4) << 32;
+    d |= (uint64_t) 1 << 46;
+    d |= (uint64_t) 2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=F32 (bit 4), A=B=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24.
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t) (B200M_TILE_N >> 3) << 17) | ((uint32_t) (B200M_TILE_M >> 4) << 24);
+
+// ---- per-row selection state ------------------------------------------------------------------
+template <int KT>
+struct RowState {
+    float tk[KT];   // k smallest accumulator values so far, ascending
+    float thr;      // append threshold derived from tk[k-1]
+    int cnt;        // entries appended (may run past cap: overflow)
+    float na, eta, slop, gfac;
+};
+
+// Largest accumulator value an exact top-k member can have, given k accumulators <= T exist
+// (DESIGN.md "Certified candidates"); monotone in T, +inf for T = +inf.
+__device__ __forceinline__ float cand_threshold(float T, float na, float eta, float slop, float gfac) {
+    float x = sqrtf(fmaxf(T + na + slop, 0.f));
+    float R = fmaf(x + eta, gfac, eta);
+    float R2 = R * R;
+    return (R2 - na) + slop + 9.5367431640625e-7f * (R2 + na);
+}
+
+template <int KT>
+__device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
+                                              int32_t *__restrict__ out, int cap, bool active) {
+    float m0 = fminf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+    float m1 = fminf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+    float m2 = fminf(__uint_as_float(r[4]), __uint_as_float(r[5]));
+    float m3 = fminf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+#pragma unroll
+    for (int i = 8; i < 32; i += 8) {
+        m0 = fminf(m0, fminf(__uint_as_float(r[i + 0]), __uint_as_float(r[i + 1])));
+        m1 = fminf(m1, fminf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+        m2 = fminf(m2, fminf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
+        m3 = fminf(m3, fminf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
+    }
+    const float m = fminf(fminf(m0, m1), fminf(m2, m3));
+    if (active && m < st.thr) {
+        const float thr = st.thr;   // stale-high within the chunk is still a superset
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(r[i]);
+            if (v < thr) {
+                if (st.cnt < cap) out[st.cnt] = col0 + i;
+                st.cnt++;
+#pragma unroll
+                for (int s = 0; s < KT; ++s) {
+                    float lo = fminf(st.tk[s], v);
+                    v = fmaxf(st.tk[s], v);
+                    st.tk[s] = lo;
+                }
+            }
+        }
+        float T = st.tk[KT - 1];
+#pragma unroll
+        for (int s = 0; s < KT - 1; ++s)
+            if (s == k - 1) T = st.tk[s];
+        st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
+    }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
+                     const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + (size_t) p.ka * kATileBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t) p.stages * kStageBytes);
+    // barrier map: [0..S) full, [S..2S) empty, 2S a_full, 2S+1.. tmem_full[2], 2S+3.. tmem_empty[2]
+    const uint32_t bar_base = smem_u32(bars);
+    auto bar_full = [&](int s) { return bar_base + 8u * (uint32_t) s; };
+    auto bar_empty = [&](int s) { return bar_base + 8u * (uint32_t) (p.stages + s); };
+    const uint32_t bar_a = bar_base + 8u * (uint32_t) (2 * p.stages);
+    auto bar_tfull = [&](int b) { return bar_base + 8u * (uint32_t) (2 * p.stages + 1 + b); };
+    auto bar_tempty = [&](int b) { return bar_base + 8u * (uint32_t) (2 * p.stages + 3 + b); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x, split = blockIdx.y;
+    const int t0 = p.dump ? p.tiles_per_split : split * p.tiles_per_split;   // dump mode: tiles_per_split holds the tile id
+    const int t1 = p.dump ? t0 + 1 : min(p.n_ttiles, t0 + p.tiles_per_split);
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_a, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull(b), 1);
+            mbar_init(bar_tempty(b), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int q_row = p.q_row0 + qtile * B200M_TILE_M;
+            mbar_arrive_expect_tx(bar_a, (uint32_t) (p.ka * kATileBytes));
+            for (int a = 0; a < p.ka; ++a) tma_load_2d(smem_u32(sA + (size_t) a * kATileBytes), &tmap_q, bar_a, a * 64, q_row);
+            int it = 0;
+            for (int t = t0; t < t1; ++t) {
+                for (int a = 0; a < p.ka; ++a, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
+                    mbar_wait(bar_empty(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(bar_full(s), (uint32_t) kStageBytes);
+                    tma_load_2d(smem_u32(sB + (size_t) s * kStageBytes), &tmap_t, bar_full(s), a * 64, t * B200M_TILE_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            int it = 0;
+            for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
+                const int buf = lt & 1;
+                const uint32_t use = (uint32_t) (lt >> 1);
+                mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t) (buf * B200M_TILE_N);
+                for (int a = 0; a < p.ka; ++a, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
+                    mbar_wait(bar_full(s), ph);
+                    tc_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t) a * kATileBytes));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t) s * kStageBytes));
+                    const int nk = min(4, p.ksteps - 4 * a);
+                    for (int kk = 0; kk < nk; ++kk)   // +32 B per K=16 step inside the 128 B swizzle atom
+                        tc_mma_f16(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDesc,
+                                   (uint32_t) ((a | kk) != 0));
+                    tc_commit(bar_empty(s));          // frees the B stage once these MMAs have read it
+                }
+                tc_commit(bar_tfull(buf));            // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4).. =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const int local = qtile * B200M_TILE_M + row_in_tile;
+        const bool active = local < p.n_rows;
+        RowState<KT> st;
+#pragma unroll
+        for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
+        st.thr = INFINITY;
+        st.cnt = 0;
+        {
+            const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
+            const float ab = sqrtf(na) + p.bmax;
+            st.na = na;
+            st.eta = ab * 4.8828125e-4f * 1.001953125f + 2.384185791015625e-7f * sqrtf((float) p.dim);
+            st.slop = ab * ab * 1.52587890625e-5f + 1e-6f;
+            st.gfac = 1.f + 2.2f * (float) (p.dim + 4) * 5.9604644775390625e-8f;
+        }
+        const size_t list_row = (size_t) split * p.n_rows + (active ? local : 0);
+        int32_t *out = p.cand_idx + list_row * p.cap;
+        const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
+        uint32_t ra[32], rb[32];
+        for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
+            const int buf = lt & 1;
+            const uint32_t use = (uint32_t) (lt >> 1);
+            mbar_wait(bar_tfull(buf), use & 1u);
+            tc_fence_after();
+            const uint32_t taddr = lane_base + (uint32_t) (buf * B200M_TILE_N);
+            const int col_base = t * B200M_TILE_N;
+            tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
+                if (p.dump) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) p.dump[row_in_tile * B200M_TILE_N + c * 32 + i] = __uint_as_float(ra[i]);
+                }
+                process_chunk<KT>(ra, col_base + c * 32, st, p.k, out, p.cap, active);
+                tmem_ld_wait();
+                if (c + 2 < 8) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
+                if (p.dump) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        p.dump[row_in_tile * B200M_TILE_N + (c + 1) * 32 + i] = __uint_as_float(rb[i]);
+                }
+                process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap, active);
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty(buf));
+        }
+        if (active && !p.dump) p.cand_cnt[list_row] = st.cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmapCache {
+    EncodeTiledFn encode = nullptr;
+    struct Entry {
+        const void *ptr = nullptr;
+        size_t n_pad = 0;
+        int kp = 0, box_rows = 0;
+        CUtensorMap map;
+    } e[4];   // [side][as_query]
+};
+
+int get_tmap(b200m_ctx *ctx, int side, bool as_query, const CUtensorMap **out) {
+    TmapCache *tc = static_cast<TmapCache *>(ctx->tmap_cache);
+    if (!tc) {
+        tc = new TmapCache();
+        ctx->tmap_cache = tc;
+    }
+    if (!tc->encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return b200m_fail_msg(ctx, "cuTensorMapEncodeTiled is not available from the driver");
+        tc->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    Side &sd = ctx->side[side];
+    const void *ptr = as_query ? sd.op_query.p : sd.op_train.p;
+    const int box_rows = as_query ? B200M_TILE_M : B200M_TILE_N;
+    TmapCache::Entry &en = tc->e[side * 2 + (as_query ? 1 : 0)];
+    if (en.ptr != ptr || en.n_pad != sd.n_pad || en.kp != sd.kp || en.box_rows != box_rows) {
+        cuuint64_t dims[2] = {(cuuint64_t) sd.kp, (cuuint64_t) sd.n_pad};
+        cuuint64_t strides[1] = {(cuuint64_t) sd.kp * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t) box_rows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = tc->encode(&en.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return b200m_fail_msg(ctx, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int) r));
+        en.ptr = ptr;
+        en.n_pad = sd.n_pad;
+        en.kp = sd.kp;
+        en.box_rows = box_rows;
+    }
+    *out = &en.map;
+    return 0;
+}
+
+template <int KT>
+int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
+    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    tc_candidates_kernel<KT><<<grid, kThreads, smem, ctx->stream>>>(*mq, *mt, p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+bool tc_supported(const b200m_ctx *ctx, int dim, int k) {
+    (void) ctx;
+    int kp = (dim + B200M_AUG_COLS + 63) / 64 * 64;
+    return kp / 64 <= kMaxKAtoms && k <= 16;
+}
+
+void tc_release(b200m_ctx *ctx) {
+    delete static_cast<TmapCache *>(ctx->tmap_cache);
+    ctx->tmap_cache = nullptr;
+}
+
+int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
+                  int *n_lists_out, int *cap_out, float *dump, size_t dump_t_tile) {
+    Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    const CUtensorMap *mq = nullptr, *mt = nullptr;
+    if (get_tmap(ctx, direction, true, &mq)) return 1;
+    if (get_tmap(ctx, 1 - direction, false, &mt)) return 1;
+
+    TcParams p{};
+    p.ka = q.kp / 64;
+    p.ksteps = (q.dim + B200M_AUG_COLS + 15) / 16;
+    const size_t smem_limit = 227 * 1024;
+    const size_t fixed = (size_t) p.ka * kATileBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+    int stages = (int) ((smem_limit - fixed) / kStageBytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return b200m_fail_msg(ctx, "tc_candidates: descriptor too long for the shared-memory pipeline");
+    p.stages = stages;
+    p.n_ttiles = (int) (t.n_pad / B200M_TILE_N);
+    const int n_qtiles = (int) ((n_rows + B200M_TILE_M - 1) / B200M_TILE_M);
+    int n_splits = 1;
+    if (!dump) {
+        // aim for >= 3 waves of CTAs; every split keeps at least 8 train tiles
+        int want = (3 * ctx->sm_count + n_qtiles - 1) / n_qtiles;
+        int max_by_tiles = p.n_ttiles / 8 > 0 ? p.n_ttiles / 8 : 1;
+        n_splits = want < 1 ? 1 : want;
+        if (n_splits > max_by_tiles) n_splits = max_by_tiles;
+        if (n_splits > kMaxLists) n_splits = kMaxLists;
+    }
+    p.tiles_per_split = (p.n_ttiles + n_splits - 1) / n_splits;
+    n_splits = (p.n_ttiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.q_row0 = (int) row_begin;
+    p.n_rows = (int) n_rows;
+    p.k = k;
+    p.dim = q.dim;
+    p.bmax = ctx->prep.max_norm[1 - direction];
+    p.q_norm16 = q.norm16.as<float>();
+    // expected appends per list ~ k*(ln(n/k)+1); leave generous head room, overflow is handled exactly
+    int cap = cap_request;
+    if (cap <= 0) {
+        double n_split = (double) p.tiles_per_split * B200M_TILE_N;
+        double expect = k * (log(fmax(n_split / k, 2.0)) + 1.0);
+        cap = (int) (1.6 * expect + 24.0);
+        cap = (cap + 7) / 8 * 8;
+    }
+    if (cap < k) cap = k;
+    p.cap = cap;
+    CK(ctx->ws_cand_idx.reserve(sizeof(int32_t) * (size_t) n_splits * n_rows * (size_t) cap));
+    CK(ctx->ws_cand_cnt.reserve(sizeof(int32_t) * (size_t) n_splits * n_rows));
+    p.cand_idx = ctx->ws_cand_idx.as<int32_t>();
+    p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
+    p.dump = dump;
+    if (dump) p.tiles_per_split = (int) dump_t_tile;
+    const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * kStageBytes + 1024 + 256;
+    dim3 grid((unsigned) (dump ? 1 : n_qtiles), (unsigned) n_splits, 1);
+    int kt = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : 16;
+    int rc;
+    switch (kt) {
+        case 1: rc = launch_tc<1>(ctx, mq, mt, p, grid, smem); break;
+        case 2: rc = launch_tc<2>(ctx, mq, mt, p, grid, smem); break;
+        case 4: rc = launch_tc<4>(ctx, mq, mt, p, grid, smem); break;
+        case 8: rc = launch_tc<8>(ctx, mq, mt, p, grid, smem); break;
+        default: rc = launch_tc<16>(ctx, mq, mt, p, grid, smem); break;
+    }
+    if (rc) return rc;
+    ctx->stats.launches += 1;
+    ctx->stats.candidate_launches += 1;
+    *n_lists_out = n_splits;
+    *cap_out = cap;
+    return 0;
+}

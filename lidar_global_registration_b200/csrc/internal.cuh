@@ -1,0 +1,133 @@
+// internal.cuh -- shared declarations of libb200match (not part of the C-ABI).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b200match.h"
+
+#define B200M_MAX_K 32
+#define B200M_MAX_DIM 1024
+#define B200M_TILE_N 256     // train rows per candidate-kernel tile; operand row counts are padded to this
+#define B200M_TILE_M 128     // query rows per CTA
+#define B200M_AUG_COLS 3     // extra K columns carrying |b|^2 as an FP16 triple
+#define B200M_SENTINEL 60000.0f  // |b|^2 stand-in for invalid/padding train rows (FP16-representable)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes);   // grow-only
+    void release();
+    template <typename T> T *as() const { return (T *) p; }
+};
+
+struct Side {
+    size_t n = 0;          // rows
+    size_t n_pad = 0;      // rows rounded up to B200M_TILE_N
+    int dim = 0;           // descriptor length
+    int dp = 0;            // f32 row pitch in floats (dim rounded up to 4)
+    int kp = 0;            // fp16 operand row pitch in halves (multiple of 64)
+    int64_t index_offset = 0;
+    uint64_t version = 0;  // bumped on every upload
+    DevBuf staging;        // raw AoS as uploaded from the host
+    DevBuf f32;            // [n][dp] dense FP32, zero padded columns
+    DevBuf valid;          // [n] uint8
+    DevBuf op_query;       // [n_pad][kp] fp16: -2*x16, 1,1,1, 0...
+    DevBuf op_train;       // [n_pad][kp] fp16:  x16, nb_hi, nb_mid, nb_lo, 0...
+    DevBuf norm16;         // [n_pad] float: |x16|^2 in scaled units
+};
+
+struct TcPrep {            // state shared by both sides' FP16 operands
+    uint64_t ver[2] = {0, 0};
+    bool ready = false;
+    DevBuf mean;           // [dp] float centre
+    DevBuf red;            // reduction scratch
+    float scale = 1.f;     // power of two applied after centring
+    float max_norm[2] = {0.f, 0.f};   // max |x16| per side (scaled units)
+    bool usable = false;   // false when the data cannot be scaled into FP16 range (non-finite spread)
+};
+
+struct b200m_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    Side side[2];
+    TcPrep prep;
+    DevBuf ws_cand_idx, ws_cand_cnt, ws_flag_rows, ws_counters, ws_scan, ws_out, ws_misc;
+    DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr;
+    void *tmap_cache = nullptr;
+    bool profiling = false;
+    b200m_stats stats{};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+int b200m_fail(b200m_ctx *ctx, const char *what, cudaError_t e, const char *file, int line);
+int b200m_fail_msg(b200m_ctx *ctx, const std::string &msg);
+
+#define CK(expr)                                                                   \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) return b200m_fail(ctx, #expr, _e, __FILE__, __LINE__); \
+    } while (0)
+
+// RAII-less timing helper: records events around a region when profiling is on.
+struct StatTimer {
+    b200m_ctx *ctx;
+    double *slot;
+    StatTimer(b200m_ctx *c, double *s) : ctx(c), slot(s) {
+        if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
+    }
+    void stop() {
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->ev[1], ctx->stream);
+            cudaEventSynchronize(ctx->ev[1]);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+            *slot += ms;
+        }
+    }
+};
+
+// ---- kernel launchers (one translation unit each) ---------------------------
+// pack.cu
+cudaError_t launch_pack_f32(const float *aos, size_t n, size_t stride_bytes, int dim, int dp,
+                            float *f32, uint8_t *valid, cudaStream_t st);
+cudaError_t launch_tc_prepare(b200m_ctx *ctx);   // centre/scale + FP16 operand tiles for both sides
+
+// exact.cu
+cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp, int dim,
+                              const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
+                              size_t row_begin, size_t n_rows, const int32_t *row_list, const int32_t *row_list_count,
+                              int k, int32_t *idx, float *dist, int32_t *count, int max_blocks, cudaStream_t st);
+cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, int dim,
+                          const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
+                          size_t row_begin, size_t n_rows, int k,
+                          const int32_t *cand_idx, const int32_t *cand_cnt, int n_lists, int cap,
+                          int32_t *idx, float *dist, int32_t *count,
+                          int32_t *flag_rows, int32_t *counters /*[0]=flagged rows, [1..2]=candidate pairs (u64)*/,
+                          cudaStream_t st);
+
+// filter.cu
+cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, size_t row_begin, size_t n_rows,
+                          const int32_t *fidx, const float *fdist, const int32_t *fcount,
+                          const int32_t *ridx, const float *rdist, const int32_t *rcount, size_t n_rev_rows,
+                          const float *thr_src, const float *thr_tgt, int64_t src_offset,
+                          b200m_corr *out, size_t cap, unsigned long long *n_out, float *avg,
+                          void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches);
+size_t filter_scan_ws_bytes(size_t n_rows, int k);
+cudaError_t launch_average(const float *fdist, const int32_t *fcount, size_t n_rows, int k, float *avg,
+                           cudaStream_t st);
+cudaError_t launch_merge(int k, int n_lists, size_t nq, const int32_t *idx_in, const float *dist_in,
+                         const int32_t *count_in, int32_t *idx, float *dist, int32_t *count, cudaStream_t st);
+
+// candidates_tc.cu
+// Fills ws_cand_idx [n_lists][n_rows][cap] and ws_cand_cnt [n_lists][n_rows] (entries appended per list; a
+// count above cap marks an overflowed list).  dump != nullptr: single tile, raw accumulators to dump[128][256].
+int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
+                  int *n_lists_out, int *cap_out, float *dump, size_t dump_t_tile);
+bool tc_supported(const b200m_ctx *ctx, int dim, int k);
+void tc_release(b200m_ctx *ctx);

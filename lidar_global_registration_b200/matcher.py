@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's matcher interface on top of libb200match.so (C-ABI,
+include/b200match.h).  Names and argument meaning follow the reference:
+
+    match_bf(query, train, parameters)            <- matchBF<FeatureT>            include/matching.h:594-634
+    match_flann / match_local(radius=inf)         <- matchFLANN / matchLocal      :562-592 / :637-678 (same result set)
+    OneSidedMatcher / LeftToRightMatcher / RatioMatcher(.match(), .get_average_distance(), .get_class_name())
+                                                  <- include/matching.h:385-478, :25-42
+    get_feature_based_matcher_from_parameters     <- src/matching.cpp:21-76
+    AlignmentParameters (hot-path subset)         <- include/common.h:135-163
+
+Descriptors are float32 arrays [n, stride_floats] whose leading `dim` columns are the
+descriptor -- the AoS layout PCL hands to the reference (`&cloud.points[0]`, `sizeof(FeatureT)`).
+There is no CPU path here: without the CUDA library and a B200 every call raises.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200match.so")
+
+CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"),
+                       ("distance", "<f4"), ("threshold", "<f4")])
+
+MODE_KNN_ONLY, MODE_ONE_SIDED, MODE_MUTUAL, MODE_RATIO, MODE_RATIO_MUTUAL = 0, 1, 2, 3, 4
+PREC_TC_F16, PREC_F32_EXACT = 0, 2
+
+# reference constants (include/common.h:50-51, :42, :45)
+MATCHING_RATIO_THRESHOLD = 1.1
+MATCHING_RATIO_K = 2
+MATCHING_ONE_SIDED, MATCHING_LEFT_TO_RIGHT, MATCHING_RATIO, MATCHING_CLUSTER = "one_sided", "lr", "ratio", "cluster"
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+class B200MatchError(RuntimeError):
+    """== the std::runtime_error thrown by the reference's rassert (include/utils.h:9)."""
+
+
+class _Params(C.Structure):
+    _fields_ = [("k", C.c_int32), ("mode", C.c_int32), ("ratio_thr", C.c_float), ("distance_thr", C.c_float),
+                ("precision", C.c_int32), ("cand_cap", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_pack", C.c_double), ("ms_prepare", C.c_double), ("ms_candidates", C.c_double),
+                ("ms_rerank", C.c_double), ("ms_fallback", C.c_double), ("ms_filter", C.c_double),
+                ("launches", C.c_int64), ("candidate_launches", C.c_int64), ("rows_total", C.c_int64),
+                ("rows_flagged", C.c_int64), ("candidates", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_stream", "b200m_sync",
+           "b200m_set_profiling", "b200m_get_stats", "b200m_reset_stats", "b200m_upload", "b200m_upload_device",
+           "b200m_knn", "b200m_knn_device", "b200m_match", "b200m_filter_device", "b200m_merge_device",
+           "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb200match.so (built in-tree by lidar_global_registration_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise B200MatchError("libb200match.so is not built (run `python -m lidar_global_registration_b200.build`); "
+                             "there is no CPU fallback")
+    L = C.CDLL(_LIB_PATH)
+    vp, sz, i32, i64, fp = C.c_void_p, C.c_size_t, C.c_int32, C.c_int64, C.c_void_p
+    L.b200m_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.b200m_destroy.argtypes = [vp]
+    L.b200m_destroy.restype = None
+    L.b200m_last_error.argtypes = [vp]
+    L.b200m_last_error.restype = C.c_char_p
+    L.b200m_set_stream.argtypes = [vp, vp]
+    L.b200m_sync.argtypes = [vp]
+    L.b200m_set_profiling.argtypes = [vp, C.c_int]
+    L.b200m_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.b200m_reset_stats.argtypes = [vp]
+    L.b200m_upload.argtypes = [vp, C.c_int, fp, sz, sz, C.c_int, i64]
+    L.b200m_upload_device.argtypes = [vp, C.c_int, fp, sz, sz, C.c_int, i64]
+    L.b200m_knn.argtypes = [vp, C.POINTER(_Params), C.c_int, sz, sz, vp, vp, vp]
+    L.b200m_knn_device.argtypes = [vp, C.POINTER(_Params), C.c_int, sz, sz, vp, vp, vp]
+    L.b200m_match.argtypes = [vp, C.POINTER(_Params), fp, fp, vp, sz, C.POINTER(sz), C.POINTER(C.c_float)]
+    L.b200m_filter_device.argtypes = [vp, C.POINTER(_Params), sz, sz, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, sz, vp, vp]
+    L.b200m_merge_device.argtypes = [vp, C.c_int, C.c_int, sz, vp, vp, vp, vp, vp, vp]
+    L.b200m_version.restype = C.c_int
+    L.b200m_debug_operands.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, C.POINTER(C.c_float), C.POINTER(i32),
+                                       C.POINTER(i64)]
+    L.b200m_debug_tc_tile.argtypes = [vp, C.c_int, sz, sz, vp]
+    _lib = L
+    return L
+
+
+@dataclass
+class AlignmentParameters:
+    """The fields of the reference's AlignmentParameters read on the matching path
+    (include/common.h:135-163) plus the B200-specific knobs."""
+    randomness: int = 1                 # k (:147)
+    use_bfmatcher: bool = True          # :144 -- both backends map to the same exact GPU search
+    bf_block_size: int = 10000          # :145 -- accepted, unused: the GPU streams the whole train set
+    distance_thr: float = FLT_MAX       # :139
+    ratio_k: int = MATCHING_RATIO_K     # :146
+    matching_id: str = MATCHING_LEFT_TO_RIGHT   # :149
+    ratio_thr: float = MATCHING_RATIO_THRESHOLD
+    precision: int = PREC_TC_F16
+    cand_cap: int = 0
+
+
+def _as_rows(a):
+    a = np.asarray(a)
+    if a.dtype != np.float32 or a.ndim != 2:
+        raise B200MatchError("descriptors must be a 2-D float32 array [n, stride_floats]")
+    if a.shape[0] > 1 and (a.strides[1] != 4 or a.strides[0] % 4 != 0 or a.strides[0] < 4 * a.shape[1]):
+        a = np.ascontiguousarray(a)
+    stride = a.strides[0] if a.shape[0] > 1 else 4 * a.shape[1]
+    return a, stride
+
+
+class Context:
+    """One b200m_ctx: one GPU, one stream; calls are serialised (reference call sites are single-threaded)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        if self._L.b200m_create(C.byref(self._h), int(device)) != 0:
+            raise B200MatchError(self._L.b200m_last_error(None).decode())
+        self.device = int(device)
+        self.n = [0, 0]
+        self.dim = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.b200m_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise B200MatchError(self._L.b200m_last_error(self._h).decode())
+
+    @staticmethod
+    def _params(k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, precision=PREC_TC_F16, cand_cap=0):
+        return _Params(int(k), int(mode), float(ratio_thr), float(distance_thr), int(precision), int(cand_cap))
+
+    # -- plumbing ------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.b200m_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def sync(self):
+        self._ck(self._L.b200m_sync(self._h))
+
+    def set_profiling(self, on):
+        self._ck(self._L.b200m_set_profiling(self._h, 1 if on else 0))
+
+    def reset_stats(self):
+        self._ck(self._L.b200m_reset_stats(self._h))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._L.b200m_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # -- upload ---------------------------------------------------------------
+    def upload(self, side, rows, dim, index_offset=0):
+        """rows: float32 [n, stride_floats] host array (AoS point structs); the first `dim` columns are used."""
+        a, stride = _as_rows(rows)
+        if dim > a.shape[1]:
+            raise B200MatchError("dim exceeds the row length")
+        self._keep = getattr(self, "_keep", {})
+        self._keep[side] = a
+        self._ck(self._L.b200m_upload(self._h, side, a.ctypes.data, a.shape[0], stride, dim, index_offset))
+        self.n[side] = a.shape[0]
+        self.dim = dim
+
+    def upload_device(self, side, ptr, n, stride_bytes, dim, index_offset=0):
+        self._ck(self._L.b200m_upload_device(self._h, side, C.c_void_p(ptr), n, stride_bytes, dim, index_offset))
+        self.n[side] = n
+        self.dim = dim
+
+    # -- raw k-lists ----------------------------------------------------------
+    def knn(self, k, direction=0, row_begin=0, row_end=0, precision=PREC_TC_F16, cand_cap=0):
+        nq = self.n[direction]
+        re = nq if row_end == 0 else row_end
+        rows = max(re - row_begin, 0)
+        idx = np.empty((rows, k), np.int32)
+        dist = np.empty((rows, k), np.float32)
+        cnt = np.empty((rows,), np.int32)
+        p = self._params(k, MODE_KNN_ONLY, precision=precision, cand_cap=cand_cap)
+        self._ck(self._L.b200m_knn(self._h, C.byref(p), direction, row_begin, re, idx.ctypes.data, dist.ctypes.data,
+                                   cnt.ctypes.data))
+        return idx, dist, cnt
+
+    def knn_device(self, k, direction, row_begin, row_end, idx_ptr, dist_ptr, cnt_ptr, precision=PREC_TC_F16, cand_cap=0):
+        p = self._params(k, MODE_KNN_ONLY, precision=precision, cand_cap=cand_cap)
+        self._ck(self._L.b200m_knn_device(self._h, C.byref(p), direction, row_begin, row_end, C.c_void_p(idx_ptr),
+                                          C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr)))
+
+    # -- whole matcher call ----------------------------------------------------
+    def match(self, k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, thr_src=None, thr_tgt=None,
+              precision=PREC_TC_F16, cand_cap=0, out=None):
+        """Returns (correspondences as CORR_DTYPE array, average first-NN distance)."""
+        nq = self.n[0]
+        kk = k if mode == MODE_MUTUAL else 1
+        if out is None:
+            out = np.empty(max(nq * kk, 1), CORR_DTYPE)
+        ts = None if thr_src is None else np.ascontiguousarray(thr_src, np.float32)
+        tt = None if thr_tgt is None else np.ascontiguousarray(thr_tgt, np.float32)
+        if ts is not None and ts.shape[0] != nq:
+            raise B200MatchError("thr_src length != number of source rows")
+        if tt is not None and tt.shape[0] != self.n[1]:
+            raise B200MatchError("thr_tgt length != number of target rows")
+        p = self._params(k, mode, ratio_thr, distance_thr, precision, cand_cap)
+        n_out = C.c_size_t(0)
+        avg = C.c_float(0)
+        self._ck(self._L.b200m_match(self._h, C.byref(p), None if ts is None else ts.ctypes.data,
+                                     None if tt is None else tt.ctypes.data, out.ctypes.data, out.shape[0],
+                                     C.byref(n_out), C.byref(avg)))
+        return out[:n_out.value], float(avg.value)
+
+    def filter_device(self, k, mode, row_begin, row_end, fidx, fdist, fcnt, ridx, rdist, rcnt, n_rev_rows, out_ptr, cap,
+                      n_out_ptr, avg_ptr=0, thr_src=0, thr_tgt=0, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX):
+        p = self._params(k, mode, ratio_thr, distance_thr)
+        v = C.c_void_p
+        self._ck(self._L.b200m_filter_device(self._h, C.byref(p), row_begin, row_end, v(fidx), v(fdist), v(fcnt), v(ridx),
+                                             v(rdist), v(rcnt), n_rev_rows, v(thr_src), v(thr_tgt), v(out_ptr), cap,
+                                             v(n_out_ptr), v(avg_ptr)))
+
+    def merge_device(self, k, n_lists, nq, idx_in, dist_in, cnt_in, idx, dist, cnt):
+        v = C.c_void_p
+        self._ck(self._L.b200m_merge_device(self._h, k, n_lists, nq, v(idx_in), v(dist_in), v(cnt_in), v(idx), v(dist),
+                                            v(cnt)))
+
+    # -- test hooks -------------------------------------------------------------
+    def debug_operands(self, side, as_query):
+        kp, n_pad, scale = C.c_int32(0), C.c_int64(0), C.c_float(0)
+        self._ck(self._L.b200m_debug_operands(self._h, side, int(as_query), None, 0, None, C.byref(scale), C.byref(kp),
+                                              C.byref(n_pad)))
+        ops = np.empty((n_pad.value, kp.value), np.float16)
+        norm = np.empty((n_pad.value,), np.float32)
+        self._ck(self._L.b200m_debug_operands(self._h, side, int(as_query), ops.ctypes.data, ops.size, norm.ctypes.data,
+                                              C.byref(scale), C.byref(kp), C.byref(n_pad)))
+        return ops, norm, float(scale.value)
+
+    def debug_tc_tile(self, direction, q_row0, t_tile):
+        out = np.empty((128, 256), np.float32)
+        self._ck(self._L.b200m_debug_tc_tile(self._h, direction, q_row0, t_tile, out.ctypes.data))
+        return out
+
+
+# ---- the reference's free functions ------------------------------------------------------
+def _knn_once(query, train, dim, k, precision, device):
+    with Context(device) as ctx:
+        ctx.upload(0, query, dim)
+        ctx.upload(1, train, dim)
+        return ctx.knn(k, 0, precision=precision)
+
+
+def match_bf(query_features, train_features, parameters, dim=None, device=0):
+    """matchBF<FeatureT> (include/matching.h:594-634): per query the <= k nearest train rows, ascending L2
+    distance.  Returns (match_indices [nq,k] -1 padded, distances [nq,k], count [nq]) -- the columns of the
+    reference's std::vector<MultivaluedCorrespondence>.  Exact ties are ordered by lower train index (OpenCV's
+    in-block rule; the reference's cross-block merge reverses them)."""
+    dim = dim or np.asarray(query_features).shape[1]
+    return _knn_once(query_features, train_features, dim, parameters.randomness, parameters.precision, device)
+
+
+def match_flann(query_features, train_features, parameters, dim=None, device=0):
+    """matchFLANN<FeatureT> (include/matching.h:562-592): the same exact result set."""
+    return match_bf(query_features, train_features, parameters, dim, device)
+
+
+def match_local(query_features, train_features, parameters, dim=None, device=0):
+    """matchLocal<FeatureT> with match_search_radius = inf (include/matching.h:637-678, as the reference's
+    test calls it, tests/flann_bf_matcher.h:66-72).  The spatially gated variant is a next-row item."""
+    return match_bf(query_features, train_features, parameters, dim, device)
+
+
+# ---- the reference's matcher classes --------------------------------------------------------
+class FeatureBasedMatcher:
+    """FeatureBasedMatcher (include/matching.h:25-42) at the descriptor seam: constructed over two
+    descriptor sets (the reference's `initialize` -- feature extraction -- is out of scope)."""
+    mode = None
+    name = "FeatureBasedMatcher"
+
+    def __init__(self, src_features, tgt_features, parameters, dim=None, thresholds_src=None, thresholds_tgt=None,
+                 kps_indices_src=None, kps_indices_tgt=None, device=0):
+        self.parameters = parameters
+        self.src, self.tgt = src_features, tgt_features
+        self.dim = dim or np.asarray(src_features).shape[1]
+        self.thr_src, self.thr_tgt = thresholds_src, thresholds_tgt
+        self.kps_src, self.kps_tgt = kps_indices_src, kps_indices_tgt
+        self.device = device
+        self.average_distance_ = FLT_MAX      # include/matching.h:41
+
+    def get_average_distance(self):
+        return self.average_distance_
+
+    def get_class_name(self):
+        return self.name
+
+    def _k(self):
+        return self.parameters.randomness
+
+    def match(self):
+        """match() (include/matching.h:148-161): match_impl + finalize (:356-362)."""
+        p = self.parameters
+        with Context(self.device) as ctx:
+            ctx.upload(0, self.src, self.dim)
+            ctx.upload(1, self.tgt, self.dim)
+            corrs, avg = ctx.match(self._k(), self.mode, p.ratio_thr, p.distance_thr, self.thr_src, self.thr_tgt,
+                                   p.precision, p.cand_cap)
+        corrs = corrs.copy()
+        self.average_distance_ = avg
+        if self.kps_src is not None:
+            corrs["index_query"] = np.asarray(self.kps_src, np.int32)[corrs["index_query"]]
+        if self.kps_tgt is not None:
+            corrs["index_match"] = np.asarray(self.kps_tgt, np.int32)[corrs["index_match"]]
+        return corrs
+
+
+class OneSidedMatcher(FeatureBasedMatcher):
+    mode, name = MODE_ONE_SIDED, "OneSidedMatcher"
+
+
+class LeftToRightMatcher(FeatureBasedMatcher):
+    mode, name = MODE_MUTUAL, "LeftToRightMatcher"
+
+
+class RatioMatcher(FeatureBasedMatcher):
+    """A stub in the reference (include/matching.h:470-473); semantics defined in DESIGN.md."""
+    mode, name = MODE_RATIO, "RatioMatcher"
+
+    def _k(self):
+        return max(self.parameters.ratio_k, 2)
+
+
+def get_feature_based_matcher_from_parameters(src_features, tgt_features, parameters, **kw):
+    """getFeatureBasedMatcherFromParameters (src/matching.cpp:21-76) for the matchers on the hot path."""
+    m = parameters.matching_id
+    if m == MATCHING_ONE_SIDED:
+        return OneSidedMatcher(src_features, tgt_features, parameters, **kw)
+    if m == MATCHING_LEFT_TO_RIGHT:
+        return LeftToRightMatcher(src_features, tgt_features, parameters, **kw)
+    if m == MATCHING_RATIO:
+        return RatioMatcher(src_features, tgt_features, parameters, **kw)
+    raise B200MatchError("Matching method %s isn't supported by the B200 matcher (cluster filtering is a next-row item)" % m)

@@ -21,13 +21,19 @@ CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"),
 
 
 def build(force=False):
-    """Compile liboracle.so with the committed Makefile (gcc, OpenMP)."""
+    """Compile liboracle.so with the committed Makefile (gcc, OpenMP); a library whose stamp
+    matches the current source is kept."""
+    import hashlib
     src = os.path.join(_HERE, "oracle.c")
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+    stamp = _LIB_PATH + ".stamp"
+    digest = hashlib.sha256(open(src, "rb").read() + open(os.path.join(_HERE, "Makefile"), "rb").read()).hexdigest()
+    if (not force and os.path.exists(_LIB_PATH) and os.path.exists(stamp)
+            and open(stamp).read().strip() == digest):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
                    stdout=subprocess.DEVNULL)
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return _LIB_PATH
 
 

@@ -1,0 +1,293 @@
+"""Parity of the CUDA path against the CPU oracle, through the C-ABI (run with -m gpu on a B200).
+
+Bar (BASELINE.json north_star): neighbour indices bit-exact, distances bit-exact too (the re-rank
+runs the reference's own sequential FP32 arithmetic), for both the exact CUDA-core path and the
+tensor-core candidate path; filters bit-exact record for record."""
+import os
+
+import numpy as np
+import pytest
+
+from lidar_global_registration_b200 import build as b200_build
+from lidar_global_registration_b200 import matcher as M
+from lidar_global_registration_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["fpfh_k1", "fpfh_k2_blocked", "fpfh_k5", "rops_k3", "shot_k2", "shot_k1_blocked"]
+PRECS = [M.PREC_F32_EXACT, M.PREC_TC_F16]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    b200_build.build()
+    M.load_library()
+
+
+def _same(a, b):
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and x.shape == y.shape
+        assert np.array_equal(x, y)
+
+
+def _dense(a, dim):
+    return a[:, :dim]
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=["exact", "tc"])
+@pytest.mark.parametrize("name", CASES)
+def test_knn_equals_oracle_on_golden_inputs(golden_dir, name, prec):
+    """GPU k-lists == oracle k-lists (idx, dist, count) bit for bit, both directions; and == the frozen
+    cv2.BFMatcher indices (the assertion of the reference's tests/flann_bf_matcher.h:73-88)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    dim, k = int(g["dim"]), int(g["k"])
+    src, tgt = g["src"], g["tgt"]
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        fwd = ctx.knn(k, 0, precision=prec)
+        rev = ctx.knn(k, 1, precision=prec)
+    _same(fwd, orc.knn(_dense(src, dim), _dense(tgt, dim), k))
+    _same(rev, orc.knn(_dense(tgt, dim), _dense(src, dim), k))
+    if int(g["block"]) >= max(src.shape[0], tgt.shape[0]):   # single block: no cross-block tie reversal possible
+        assert np.array_equal(fwd[0], g["bf_idx"]) and np.array_equal(rev[0], g["bf_ridx"])
+    np.testing.assert_allclose(fwd[1], g["bf_dist"], rtol=1e-5, atol=0)   # the north star's FP32 tolerance vs cv2
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=["exact", "tc"])
+def test_ties_kgt_nt_and_empty(golden_dir, prec):
+    g = np.load(os.path.join(golden_dir, "ties_small.npz"))
+    q, t = g["q"], g["t"]
+    with M.Context(0) as ctx:
+        ctx.upload(0, q, 33)
+        ctx.upload(1, t, 33)
+        idx, dist, cnt = ctx.knn(3, 0, precision=prec)
+        assert idx[0].tolist() == [5, 17, 30] and np.all(dist[0] == 0)      # canonical: lower index first
+        _same((idx, dist, cnt), orc.knn(q, t, 3))
+        ctx.upload(1, t[:2], 33)                                            # k > nt -> nt results (cv2: idx_kgt)
+        idx, dist, cnt = ctx.knn(3, 0, precision=prec)
+        assert cnt.tolist() == [2, 2] and np.array_equal(idx, g["idx_kgt"])
+        _same((idx, dist, cnt), orc.knn(q, t[:2], 3))
+        ctx.upload(1, t[:0], 33)                                            # empty train set -> empty lists
+        idx, dist, cnt = ctx.knn(2, 0, precision=prec)
+        assert np.all(cnt == 0) and np.all(idx == -1)
+        ctx.upload(0, q[:0], 33)                                            # empty query set
+        idx, dist, cnt = ctx.knn(2, 0, precision=prec)
+        assert idx.shape == (0, 2)
+        corrs, avg = ctx.match(1, M.MODE_ONE_SIDED, precision=prec)
+        assert len(corrs) == 0 and avg == M.FLT_MAX
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=["exact", "tc"])
+def test_all_rows_invalid_or_duplicated(prec):
+    rng = np.random.default_rng(3)
+    t = rng.random((300, 33)).astype(np.float32)
+    q = t[:40].copy()
+    q[7, 3] = np.nan
+    t[11, 0] = np.inf
+    t[100:200] = t[0]          # 101 exact duplicates of row 0: a long run of exact ties
+    with M.Context(0) as ctx:
+        ctx.upload(0, q, 33)
+        ctx.upload(1, t, 33)
+        for k in (1, 4, 8):
+            _same(ctx.knn(k, 0, precision=prec), orc.knn(q, t, k))
+        bad = np.full((5, 33), np.nan, np.float32)
+        ctx.upload(1, bad, 33)     # every train row invalid -> every list empty
+        idx, dist, cnt = ctx.knn(2, 0, precision=prec)
+        assert np.all(cnt == 0)
+        _same((idx, dist, cnt), orc.knn(q, bad, 2))
+
+
+@pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 777, 1500, 2), ("shot", 300, 900, 2), ("rops", 260, 700, 3),
+                                          ("fpfh", 130, 5000, 16)])
+def test_tc_operands_and_accumulators(desc, nq, nt, k):
+    """White-box check of the tensor-core pass: operand tiles as documented in pack.cu and raw
+    tcgen05 accumulators == |b16|^2 - 2 a16.b16 within the slop the candidate threshold budgets."""
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        oq, nq16, scale = ctx.debug_operands(0, True)
+        ot, nt16, _ = ctx.debug_operands(1, False)
+        assert oq.shape[1] % 64 == 0 and oq.shape[0] % 256 == 0 and ot.shape[0] % 256 == 0
+        ot_q, _, _ = ctx.debug_operands(0, False)
+        valid = np.isfinite(src[:, :dim]).all(1)
+        # query form = -2 * train form, then ones picking up the norm triple
+        assert np.array_equal(oq[:nq, :dim].astype(np.float32), -2.0 * ot_q[:nq, :dim].astype(np.float32))
+        assert np.all(oq[:, dim:dim + 3] == 1) and np.all(oq[:, dim + 3:] == 0) and np.all(ot[:, dim + 3:] == 0)
+        x16 = ot_q[:nq, :dim].astype(np.float64)
+        np.testing.assert_allclose(nq16[:nq][valid], (x16[valid] ** 2).sum(1), rtol=3e-7)
+        assert np.abs(x16).max() <= 1.0
+        tvalid = np.isfinite(tgt[:, :dim]).all(1)
+        triple = ot[:nt, dim:dim + 3].astype(np.float64).sum(1)
+        np.testing.assert_allclose(triple[tvalid], (ot[:nt, :dim].astype(np.float64)[tvalid] ** 2).sum(1), rtol=3e-7)
+        assert np.all(triple[~tvalid] > 5e4) and np.all(ot[nt:, dim].astype(np.float64) > 5e4)   # sentinel rows
+        # the centred/scaled FP16 rows approximate scale*(x - c) to FP16 rounding
+        c = np.concatenate([src[valid, :dim], tgt[tvalid, :dim]]).astype(np.float64).mean(0)
+        ref = (src[valid, :dim].astype(np.float64) - c) * scale
+        assert np.abs(x16[valid] - ref).max() <= 2.0 ** -11 * 1.01 + 1e-6
+        # raw accumulators of a few tiles vs float64 on the same FP16 operands
+        worst = 0.0
+        for (q0, tt) in [(0, 0), (128, 1), (nq - nq % 128 if nq % 128 else nq - 128, ot.shape[0] // 256 - 1)]:
+            acc = ctx.debug_tc_tile(0, q0, tt)
+            a = oq[q0:q0 + 128].astype(np.float64)
+            b = ot[tt * 256:(tt + 1) * 256].astype(np.float64)
+            exp = a @ b.T
+            rows = min(128, oq.shape[0] - q0)
+            na = np.sqrt(np.maximum((a[:rows, :dim] ** 2).sum(1) / 4.0, 0))[:, None]
+            nb = np.sqrt((b[:, :dim] ** 2).sum(1))[None, :]
+            ok = (np.abs(exp[:rows]) < 1e4)          # leave the sentinel rows out of the relative measure
+            err = np.abs(acc[:rows] - exp[:rows])
+            budget = (na + nb) ** 2 * 2.0 ** -16 + 1e-6
+            assert np.all(err[ok] <= np.broadcast_to(budget, err.shape)[ok])
+            worst = max(worst, float((err / np.broadcast_to((na + nb) ** 2 + 1e-30, err.shape))[ok].max()))
+            np.testing.assert_allclose(acc[:rows][~ok], exp[:rows][~ok], rtol=1e-3)
+        print("max tensor-core accumulation error / (|a|+|b|)^2 = %.3e (budget 2^-16 = %.3e)" % (worst, 2.0 ** -16))
+        # and the whole pass agrees with the oracle
+        _same(ctx.knn(k, 0), orc.knn(_dense(src, dim), _dense(tgt, dim), k))
+        _same(ctx.knn(k, 1), orc.knn(_dense(tgt, dim), _dense(src, dim), k))
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=["exact", "tc"])
+@pytest.mark.parametrize("mode,name", [("one_sided", M.MODE_ONE_SIDED), ("mutual", M.MODE_MUTUAL), ("ratio", M.MODE_RATIO)])
+def test_match_equals_oracle(golden_dir, mode, name, prec):
+    """b200m_match == OneSided/LeftToRight(/Ratio) match_impl restated in the oracle: same records, same order,
+    same distances and thresholds, same average first-NN distance."""
+    for case in ("fpfh_k5", "shot_k2", "fpfh_k1"):
+        g = np.load(os.path.join(golden_dir, case + ".npz"))
+        dim, k = int(g["dim"]), int(g["k"])
+        if mode == "ratio" and k < 2:
+            continue
+        src, tgt = g["src"], g["tgt"]
+        rng = np.random.default_rng(5)
+        thr_s = rng.random(src.shape[0]).astype(np.float32)
+        thr_t = rng.random(tgt.shape[0]).astype(np.float32)
+        dthr = np.float32(0.7)
+        with M.Context(0) as ctx:
+            ctx.upload(0, src, dim)
+            ctx.upload(1, tgt, dim)
+            got, avg = ctx.match(k, name, 1.1, dthr, thr_s, thr_t, precision=prec)
+            got2, avg2 = ctx.match(k, name, 1.1, dthr, precision=prec)
+        exp, eavg = orc.match(_dense(src, dim), _dense(tgt, dim), k, mode, 1.1, dthr, thr_s, thr_t)
+        assert len(got) == len(exp) and len(exp) > 0
+        assert got.tobytes() == exp.tobytes()
+        assert avg == eavg and avg2 == eavg
+        assert np.all(got2["threshold"] == dthr) and np.array_equal(got2["index_match"], exp["index_match"])
+        assert np.all(np.diff(got["index_query"]) >= 0)
+
+
+def test_ratio_mutual_mode(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fpfh_k2_blocked.npz"))
+    dim, k = int(g["dim"]), int(g["k"])
+    src, tgt = g["src"], g["tgt"]
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        got, _ = ctx.match(k, M.MODE_RATIO_MUTUAL, 1.1)
+    fi, fd, fc = orc.knn(_dense(src, dim), _dense(tgt, dim), k)
+    ri, rd, rc = orc.knn(_dense(tgt, dim), _dense(src, dim), k)
+    exp = []
+    for i in range(src.shape[0]):
+        if fc[i] < 2 or not (fd[i, 1] >= np.float32(1.1) * fd[i, 0]):
+            continue
+        j = fi[i, 0]
+        for m in range(rc[j]):
+            if ri[j, m] == i:
+                exp.append((i, j, rd[j, m]))
+                break
+    assert [(int(a), int(b), float(c)) for a, b, c in zip(got["index_query"], got["index_match"], got["distance"])] == \
+           [(int(a), int(b), float(c)) for a, b, c in exp]
+    assert 0 < len(exp) < src.shape[0]
+
+
+def test_reference_style_interface(golden_dir):
+    """The host mirror of the reference interface: matchBF/matchFLANN/matchLocal agree (tests/flann_bf_matcher.h),
+    matcher classes finalize to cloud-global indices (include/matching.h:356-362)."""
+    g = np.load(os.path.join(golden_dir, "rops_k3.npz"))
+    dim, k = int(g["dim"]), int(g["k"])
+    src, tgt = g["src"], g["tgt"]
+    params = M.AlignmentParameters(randomness=k, matching_id=M.MATCHING_LEFT_TO_RIGHT)
+    bf = M.match_bf(src, tgt, params, dim)
+    fl = M.match_flann(src, tgt, params, dim)
+    lo = M.match_local(src, tgt, params, dim)
+    _same(bf, fl)
+    _same(bf, lo)
+    assert np.array_equal(bf[0], g["bf_idx"])
+    rng = np.random.default_rng(1)
+    ks = rng.permutation(10 * src.shape[0])[:src.shape[0]].astype(np.int32)
+    kt = rng.permutation(10 * tgt.shape[0])[:tgt.shape[0]].astype(np.int32)
+    m = M.get_feature_based_matcher_from_parameters(src, tgt, params, dim=dim, kps_indices_src=ks, kps_indices_tgt=kt)
+    assert m.get_class_name() == "LeftToRightMatcher" and m.get_average_distance() == M.FLT_MAX
+    corrs = m.match()
+    exp, eavg = orc.match(_dense(src, dim), _dense(tgt, dim), k, "mutual")
+    exp = orc.finalize(exp, ks, kt)
+    assert corrs.tobytes() == exp.tobytes() and m.get_average_distance() == eavg
+    with pytest.raises(M.B200MatchError):
+        M.get_feature_based_matcher_from_parameters(src, tgt, M.AlignmentParameters(matching_id="cluster"))
+
+
+def test_error_behaviour():
+    with M.Context(0) as ctx:
+        a = np.zeros((8, 33), np.float32)
+        ctx.upload(0, a, 33)
+        ctx.upload(1, np.zeros((8, 34), np.float32), 34)
+        with pytest.raises(M.B200MatchError):
+            ctx.knn(1, 0)                       # descriptor lengths differ
+        ctx.upload(1, a, 33)
+        with pytest.raises(M.B200MatchError):
+            ctx.knn(0, 0)                       # k out of range
+        with pytest.raises(M.B200MatchError):
+            ctx.match(1, M.MODE_RATIO)          # ratio needs k >= 2
+        with pytest.raises(M.B200MatchError):
+            ctx.knn(1, 0, row_begin=4, row_end=100)
+        idx, dist, cnt = ctx.knn(2, 0, row_begin=2, row_end=6)
+        assert idx.shape == (4, 2) and idx[0].tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("desc,n,k", [("fpfh", 20000, 1), ("shot", 6000, 2)])
+def test_config1_scale_mutual(desc, n, k):
+    """BASELINE config 1 (FPFH-33 ~20k x 20k, k=1, mutual) in full against the oracle, and a SHOT-352 case:
+    bit-exact lists both directions, bit-exact correspondences; candidate-list overflow stays rare."""
+    src, tgt, dim = synth.make_pair(desc, n, n + 137)
+    with M.Context(0) as ctx:
+        ctx.set_profiling(True)
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        fwd = ctx.knn(k, 0)
+        rev = ctx.knn(k, 1)
+        st = ctx.stats()
+        got, avg = ctx.match(k, M.MODE_MUTUAL)
+    efwd = orc.knn(_dense(src, dim), _dense(tgt, dim), k)
+    erev = orc.knn(_dense(tgt, dim), _dense(src, dim), k)
+    _same(fwd, efwd)
+    _same(rev, erev)
+    exp = orc.filter_mutual(efwd[0], efwd[2], erev[0], erev[1], erev[2], np.float32(M.FLT_MAX))
+    assert got.tobytes() == exp.tobytes() and avg == orc.average_distance(efwd[1], efwd[2])
+    assert 0.2 * n < len(got) < n
+    assert st["rows_flagged"] <= 0.01 * st["rows_total"], st
+    print(desc, "candidates/row %.1f" % (st["candidates"] / st["rows_total"]), "flagged", st["rows_flagged"])
+
+
+def test_properties_at_bench_scale():
+    """Size-independent properties on a larger FPFH run (oracle on a row subsample only)."""
+    n = 100000
+    src, tgt, dim = synth.make_pair("fpfh", n, n)
+    k = 2
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        idx, dist, cnt = ctx.knn(k, 0)
+        idx2, dist2, cnt2 = ctx.knn(k, 0)
+        sub = ctx.knn(k, 0, row_begin=5000, row_end=5000 + 512)
+        ex = ctx.knn(k, 0, row_begin=5000, row_end=5000 + 512, precision=M.PREC_F32_EXACT)
+    _same((idx, dist, cnt), (idx2, dist2, cnt2))                       # idempotent
+    _same(sub, (idx[5000:5512], dist[5000:5512], cnt[5000:5512]))      # row ranges are consistent
+    _same(sub, ex)                                                     # tensor-core path == exact CUDA-core path
+    good = np.isfinite(src[:, :dim]).all(1)
+    assert np.all(cnt[good] == k) and np.all(cnt[~good] == 0)
+    assert np.all(np.diff(dist[good], axis=1) >= 0)                    # ascending
+    assert np.all(idx[good] >= 0) and np.all(idx[good] < n)
+    rows = np.random.default_rng(0).choice(n, 1024, replace=False)
+    eo = orc.knn(np.ascontiguousarray(src[rows, :dim]), _dense(tgt, dim), k)
+    _same((idx[rows], dist[rows], cnt[rows]), eo)
