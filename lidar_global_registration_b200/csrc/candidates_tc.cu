@@ -178,11 +178,10 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0,
     }
     const float m = fminf(fminf(m0, m1), fminf(m2, m3));
     if (active && m < st.thr) {
-        const float thr = st.thr;   // stale-high within the chunk is still a superset
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             float v = __uint_as_float(r[i]);
-            if (v < thr) {
+            if (v < st.thr) {
                 if (st.cnt < cap) out[st.cnt] = col0 + i;
                 st.cnt++;
 #pragma unroll
@@ -191,13 +190,14 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0,
                     v = fmaxf(st.tk[s], v);
                     st.tk[s] = lo;
                 }
+                // tighten at once: the first k columns would otherwise drag a whole chunk in
+                float T = st.tk[KT - 1];
+#pragma unroll
+                for (int s = 0; s < KT - 1; ++s)
+                    if (s == k - 1) T = st.tk[s];
+                st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
             }
         }
-        float T = st.tk[KT - 1];
-#pragma unroll
-        for (int s = 0; s < KT - 1; ++s)
-            if (s == k - 1) T = st.tk[s];
-        st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
     }
 }
 

@@ -1,0 +1,185 @@
+"""Device-resident and multi-GPU drivers of the matcher (torch tensors for HBM buffers, the
+current torch stream, torch.distributed/NCCL for the one exchange step the path has).
+
+    GpuBackend      one b200m context working on torch device buffers (no host copies)
+    ShardedMatcher  SURVEY 8e: query-sharded / target-replicated matcher (forward rows and reverse rows
+                    split across ranks, ONE all-gather of the reverse table for the mutual test), and the
+                    target-sharded kNN (per-rank exact top-k with global indices, all-gather, merge kernel).
+
+The sharding logic is backend-agnostic: tests drive it on CPU with gloo and a stand-in backend; on the
+GPU box the backend is GpuBackend and the process group is NCCL over NVLink.
+"""
+import numpy as np
+import torch
+
+from . import matcher as M
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced row ranges: rank r owns [lo, hi)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GpuBackend:
+    """kNN / filter / merge on device buffers through the C-ABI *_device entry points."""
+
+    def __init__(self, device_index=0, precision=M.PREC_TC_F16, cand_cap=0):
+        self.device = torch.device("cuda", device_index)
+        torch.cuda.set_device(self.device)
+        self.ctx = M.Context(device_index)
+        self.precision = precision
+        self.cand_cap = cand_cap
+        self.use_torch_stream()
+
+    def use_torch_stream(self):
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        self.ctx.close()
+
+    @property
+    def n(self):
+        return self.ctx.n
+
+    # -- descriptors ----------------------------------------------------------
+    def upload_device(self, side, aos, dim, index_offset=0):
+        """aos: float32 CUDA tensor [n, stride_floats] (AoS point structs resident in HBM)."""
+        assert aos.is_cuda and aos.dtype == torch.float32 and aos.dim() == 2 and aos.stride(1) == 1
+        self.ctx.upload_device(side, aos.data_ptr(), aos.shape[0], aos.stride(0) * 4, dim, index_offset)
+
+    def upload_host(self, side, aos_host, dim, index_offset=0):
+        """aos_host: float32 CPU tensor (pinned for a true async copy) [n, stride_floats]."""
+        assert not aos_host.is_cuda and aos_host.dtype == torch.float32 and aos_host.stride(1) == 1
+        self.ctx._ck(self.ctx._L.b200m_upload(self.ctx._h, side, aos_host.data_ptr(), aos_host.shape[0],
+                                              aos_host.stride(0) * 4, dim, index_offset))
+        self.ctx.n[side] = aos_host.shape[0]
+        self.ctx.dim = dim
+
+    # -- kernels ----------------------------------------------------------------
+    def knn(self, k, direction, row_begin, row_end):
+        rows = row_end - row_begin
+        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((rows, k), dtype=torch.float32, device=self.device)
+        cnt = torch.empty((rows,), dtype=torch.int32, device=self.device)
+        if rows:
+            self.ctx.knn_device(k, direction, row_begin, row_end, idx.data_ptr(), dist.data_ptr(), cnt.data_ptr(),
+                                self.precision, self.cand_cap)
+        return idx, dist, cnt
+
+    def filter(self, k, mode, row_begin, row_end, fwd, rev, n_rev_rows, ratio_thr=M.MATCHING_RATIO_THRESHOLD,
+               distance_thr=M.FLT_MAX, thr_src=None, thr_tgt=None, want_avg=False):
+        """-> (records int32 [cap, 4] (reinterpret as CORR_DTYPE), n_out uint64-as-int64 [1], avg float32 [1] or None)."""
+        rows = row_end - row_begin
+        kk = k if mode == M.MODE_MUTUAL else 1
+        cap = max(rows * kk, 1)
+        out = torch.empty((cap, 4), dtype=torch.int32, device=self.device)
+        n_out = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        avg = torch.zeros((1,), dtype=torch.float32, device=self.device) if want_avg else None
+        r = rev if rev is not None else (None, None, None)
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        self.ctx.filter_device(k, mode, row_begin, row_end, ptr(fwd[0]), ptr(fwd[1]), ptr(fwd[2]), ptr(r[0]), ptr(r[1]),
+                               ptr(r[2]), n_rev_rows, out.data_ptr(), cap, n_out.data_ptr(), ptr(avg), ptr(thr_src),
+                               ptr(thr_tgt), ratio_thr, distance_thr)
+        return out, n_out, avg
+
+    def merge(self, k, idx_in, dist_in, cnt_in):
+        """idx_in/dist_in [n_lists, nq, k], cnt_in [n_lists, nq] -> the k best per query by (dist, idx)."""
+        n_lists, nq = cnt_in.shape
+        idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=self.device)
+        self.ctx.merge_device(k, n_lists, nq, idx_in.data_ptr(), dist_in.data_ptr(), cnt_in.data_ptr(), idx.data_ptr(),
+                              dist.data_ptr(), cnt.data_ptr())
+        return idx, dist, cnt
+
+    def match_device(self, k, mode, ratio_thr=M.MATCHING_RATIO_THRESHOLD, distance_thr=M.FLT_MAX, want_avg=False):
+        """Whole matcher call on one GPU, everything resident in HBM."""
+        nq, nt = self.n
+        fwd = self.knn(k, 0, 0, nq)
+        rev = None
+        if mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL):
+            rev = self.knn(k, 1, 0, nt)
+        return self.filter(k, mode, 0, nq, fwd, rev, nt if rev is not None else 0, ratio_thr, distance_thr,
+                           want_avg=want_avg)
+
+
+def records_to_numpy(records, n_out):
+    """int32 [cap,4] device tensor + count -> CORR_DTYPE host array."""
+    n = int(n_out.item())
+    return records[:n].contiguous().cpu().numpy().view(M.CORR_DTYPE).reshape(-1)
+
+
+class ShardedMatcher:
+    """One process per GPU.  `dist` is torch.distributed (or None for a single process)."""
+
+    def __init__(self, backend, rank=0, world=1, group=None):
+        self.b = backend
+        self.rank, self.world, self.group = rank, world, group
+
+    # -- collectives ------------------------------------------------------------
+    def _all_gather_rows(self, t, n_total):
+        """All-gather row-sharded tensors (shard_bounds layout) into the full [n_total, ...] tensor."""
+        if self.world == 1:
+            return t
+        import torch.distributed as dist
+        max_rows = (n_total + self.world - 1) // self.world
+        pad = torch.zeros((max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        out = torch.empty((self.world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        if n_total % self.world == 0:
+            return out
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(n_total, r, self.world)
+            parts.append(out[r * max_rows:r * max_rows + (hi - lo)])
+        return torch.cat(parts, 0)
+
+    # -- query-sharded, target replicated -----------------
+    def match_query_sharded(self, k, mode, ratio_thr=M.MATCHING_RATIO_THRESHOLD, distance_thr=M.FLT_MAX):
+        """Both descriptor sets are resident on every rank.  Returns this rank's slice of the
+        correspondence list (records, n_out): concatenating the slices in rank order gives the
+        single-GPU output (ascending index_query)."""
+        nq, nt = self.b.n
+        q0, q1 = shard_bounds(nq, self.rank, self.world)
+        fwd = self.b.knn(k, 0, q0, q1)
+        rev = None
+        if mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL):
+            t0, t1 = shard_bounds(nt, self.rank, self.world)
+            r = self.b.knn(k, 1, t0, t1)
+            rev = tuple(self._all_gather_rows(x, nt) for x in r)     # the path's one exchange step
+        return self.b.filter(k, mode, q0, q1, fwd, rev, nt if rev is not None else 0, ratio_thr, distance_thr)
+
+    def gather_records(self, records, n_out):
+        """Concatenate every rank's correspondence slice in rank order on all ranks -> (records, n)."""
+        if self.world == 1:
+            return records[:int(n_out.item())], int(n_out.item())
+        import torch.distributed as dist
+        counts = torch.empty((self.world,), dtype=torch.int64, device=records.device)
+        dist.all_gather_into_tensor(counts, n_out.to(torch.int64), group=self.group)
+        counts_h = counts.cpu().tolist()
+        mx = max(max(counts_h), 1)
+        pad = torch.zeros((mx, 4), dtype=records.dtype, device=records.device)
+        pad[:counts_h[self.rank]] = records[:counts_h[self.rank]]
+        out = torch.empty((self.world * mx, 4), dtype=records.dtype, device=records.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        parts = [out[r * mx:r * mx + counts_h[r]] for r in range(self.world)]
+        return torch.cat(parts, 0), sum(counts_h)
+
+    # -- target-sharded (config C5): each rank holds a slice of the target set ---------
+    def knn_target_sharded(self, k):
+        """The backend's side 1 holds THIS rank's target shard (uploaded with index_offset = shard start), side 0
+        all queries.  Exact local top-k with global indices -> all-gather -> merge kernel (canonical tie rule)."""
+        nq = self.b.n[0]
+        local = self.b.knn(k, 0, 0, nq)
+        if self.world == 1:
+            return local
+        import torch.distributed as dist
+        gathered = []
+        for x in local:
+            out = torch.empty((self.world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+            dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
+            gathered.append(out)
+        return self.b.merge(k, gathered[0], gathered[1], gathered[2])
