@@ -8,6 +8,7 @@
 //   b200m_match    OneSided/LeftToRight(/Ratio)Matcher::match_impl + printDebugInfo's average
 //                  include/matching.h:395-411, :428-453, :470-473; src/matching.cpp:3-19
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -84,6 +85,10 @@ int b200m_create(b200m_ctx **out, int device) {
         return 1;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *e = getenv("B200M_TC_CLUSTER")) {
+        int c = atoi(e);
+        if (c == 1 || c == 2 || c == 4) ctx->tc_cluster = c;
+    }
     *out = ctx;
     return 0;
 }

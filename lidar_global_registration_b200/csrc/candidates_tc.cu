@@ -44,6 +44,7 @@ struct TcParams {
     int ka;               // 64-half K atoms per row (kp / 64)
     int ksteps;           // K=16 MMA steps actually needed: ceil((dim + 3) / 16)
     int stages;           // B ring depth
+    int cluster;          // CTAs per cluster sharing every train tile by TMA multicast (1, 2 or 4)
     int n_ttiles;         // 256-row train tiles
     int tiles_per_split;
     int q_row0;           // first query row of this call (row_begin)
@@ -100,10 +101,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tma
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -162,26 +185,25 @@ __device__ __forceinline__ float cand_threshold(float T, float na, float eta, fl
     return (R2 - na) + slop + 9.5367431640625e-7f * (R2 + na);
 }
 
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }   // one FMNMX3
+
 template <int KT>
 __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
-                                              int32_t *__restrict__ out, int cap, bool active) {
-    float m0 = fminf(__uint_as_float(r[0]), __uint_as_float(r[1]));
-    float m1 = fminf(__uint_as_float(r[2]), __uint_as_float(r[3]));
-    float m2 = fminf(__uint_as_float(r[4]), __uint_as_float(r[5]));
-    float m3 = fminf(__uint_as_float(r[6]), __uint_as_float(r[7]));
-#pragma unroll
-    for (int i = 8; i < 32; i += 8) {
-        m0 = fminf(m0, fminf(__uint_as_float(r[i + 0]), __uint_as_float(r[i + 1])));
-        m1 = fminf(m1, fminf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
-        m2 = fminf(m2, fminf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
-        m3 = fminf(m3, fminf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
-    }
-    const float m = fminf(fminf(m0, m1), fminf(m2, m3));
-    if (active && m < st.thr) {
+                                              int32_t *__restrict__ out, int cap) {
+#define F(i) __uint_as_float(r[i])
+    // fast path: 32 accumulators -> their minimum in 16 three-input min ops, one compare
+    const float a0 = min3(F(0), F(1), F(2)), a1 = min3(F(3), F(4), F(5)), a2 = min3(F(6), F(7), F(8));
+    const float a3 = min3(F(9), F(10), F(11)), a4 = min3(F(12), F(13), F(14)), a5 = min3(F(15), F(16), F(17));
+    const float a6 = min3(F(18), F(19), F(20)), a7 = min3(F(21), F(22), F(23)), a8 = min3(F(24), F(25), F(26));
+    const float a9 = min3(F(27), F(28), F(29)), a10 = fminf(F(30), F(31));
+    const float b0 = min3(a0, a1, a2), b1 = min3(a3, a4, a5), b2 = min3(a6, a7, a8), b3 = min3(a9, a10, b0);
+    const float m = min3(b1, b2, b3);
+    if (m < st.thr) {   // rare once the row's threshold has settled (inactive rows carry thr = -inf)
+        float thr = st.thr;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(r[i]);
-            if (v < st.thr) {
+            float v = F(i);
+            if (v < thr) {
                 if (st.cnt < cap) out[st.cnt] = col0 + i;
                 st.cnt++;
 #pragma unroll
@@ -190,15 +212,23 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0,
                     v = fmaxf(st.tk[s], v);
                     st.tk[s] = lo;
                 }
-                // tighten at once: the first k columns would otherwise drag a whole chunk in
-                float T = st.tk[KT - 1];
+                if (!(thr < 3.0e38f)) {   // list just filled up: leave the accept-everything regime at once
+                    float T = st.tk[KT - 1];
 #pragma unroll
-                for (int s = 0; s < KT - 1; ++s)
-                    if (s == k - 1) T = st.tk[s];
-                st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
+                    for (int s = 0; s < KT - 1; ++s)
+                        if (s == k - 1) T = st.tk[s];
+                    thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
+                }
             }
         }
+        // otherwise the threshold is refreshed once per chunk (a stale, larger one only admits a superset)
+        float T = st.tk[KT - 1];
+#pragma unroll
+        for (int s = 0; s < KT - 1; ++s)
+            if (s == k - 1) T = st.tk[s];
+        st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
     }
+#undef F
 }
 
 template <int KT>
@@ -229,7 +259,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), 1);
+            mbar_init(bar_empty(s), (uint32_t) p.cluster);   // every CTA of the cluster must have read the stage
         }
         mbar_init(bar_a, 1);
         for (int b = 0; b < 2; ++b) {
@@ -246,9 +276,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t) ((1u << p.cluster) - 1u);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -263,7 +296,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
                     mbar_wait(bar_empty(s), ph ^ 1u);
                     mbar_arrive_expect_tx(bar_full(s), (uint32_t) kStageBytes);
-                    tma_load_2d(smem_u32(sB + (size_t) s * kStageBytes), &tmap_t, bar_full(s), a * 64, t * B200M_TILE_N);
+                    if (p.cluster == 1) {
+                        tma_load_2d(smem_u32(sB + (size_t) s * kStageBytes), &tmap_t, bar_full(s), a * 64, t * B200M_TILE_N);
+                    } else {
+                        // this CTA fetches its 1/cluster slice of the tile and multicasts it into every peer
+                        const int slice = B200M_TILE_N / p.cluster;
+                        tma_load_2d_mcast(smem_u32(sB + (size_t) s * kStageBytes + (size_t) crank * slice * 128), &tmap_t,
+                                          bar_full(s), a * 64, t * B200M_TILE_N + (int) crank * slice, cmask);
+                    }
                 }
             }
         }
@@ -290,7 +330,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     for (int kk = 0; kk < nk; ++kk)   // +32 B per K=16 step inside the 128 B swizzle atom
                         tc_mma_f16(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDesc,
                                    (uint32_t) ((a | kk) != 0));
-                    tc_commit(bar_empty(s));          // frees the B stage once these MMAs have read it
+                    if (p.cluster == 1) tc_commit(bar_empty(s));   // frees the B stage once these MMAs have read it
+                    else tc_commit_mcast(bar_empty(s), cmask);     // ... in every CTA that multicasts into it
                 }
                 tc_commit(bar_tfull(buf));            // accumulator complete
             }
@@ -304,7 +345,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         RowState<KT> st;
 #pragma unroll
         for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
-        st.thr = INFINITY;
+        st.thr = active ? INFINITY : -INFINITY;
         st.cnt = 0;
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
@@ -334,7 +375,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
                     for (int i = 0; i < 32; ++i) p.dump[row_in_tile * B200M_TILE_N + c * 32 + i] = __uint_as_float(ra[i]);
                 }
-                process_chunk<KT>(ra, col_base + c * 32, st, p.k, out, p.cap, active);
+                process_chunk<KT>(ra, col_base + c * 32, st, p.k, out, p.cap);
                 tmem_ld_wait();
                 if (c + 2 < 8) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
                 if (p.dump) {
@@ -342,7 +383,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     for (int i = 0; i < 32; ++i)
                         p.dump[row_in_tile * B200M_TILE_N + (c + 1) * 32 + i] = __uint_as_float(rb[i]);
                 }
-                process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap, active);
+                process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
             }
             tc_fence_before();
             mbar_arrive(bar_tempty(buf));
@@ -350,7 +391,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (active && !p.dump) p.cand_cnt[list_row] = st.cnt;
     }
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -372,7 +414,7 @@ struct TmapCache {
     } e[4];   // [side][as_query]
 };
 
-int get_tmap(b200m_ctx *ctx, int side, bool as_query, const CUtensorMap **out) {
+int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtensorMap **out) {
     TmapCache *tc = static_cast<TmapCache *>(ctx->tmap_cache);
     if (!tc) {
         tc = new TmapCache();
@@ -388,7 +430,7 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, const CUtensorMap **out) {
     }
     Side &sd = ctx->side[side];
     const void *ptr = as_query ? sd.op_query.p : sd.op_train.p;
-    const int box_rows = as_query ? B200M_TILE_M : B200M_TILE_N;
+    const int box_rows = as_query ? B200M_TILE_M : B200M_TILE_N / cluster;
     TmapCache::Entry &en = tc->e[side * 2 + (as_query ? 1 : 0)];
     if (en.ptr != ptr || en.n_pad != sd.n_pad || en.kp != sd.kp || en.box_rows != box_rows) {
         cuuint64_t dims[2] = {(cuuint64_t) sd.kp, (cuuint64_t) sd.n_pad};
@@ -411,8 +453,19 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, const CUtensorMap **out) {
 template <int KT>
 int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
     CK(cudaFuncSetAttribute(tc_candidates_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    tc_candidates_kernel<KT><<<grid, kThreads, smem, ctx->stream>>>(*mq, *mt, p);
-    CK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned) p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT>, *mq, *mt, p));
     return 0;
 }
 
@@ -432,11 +485,17 @@ void tc_release(b200m_ctx *ctx) {
 int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
                   int *n_lists_out, int *cap_out, float *dump, size_t dump_t_tile) {
     Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    const int n_qtiles = (int) ((n_rows + B200M_TILE_M - 1) / B200M_TILE_M);
+    // CTAs of a cluster walk the same train tiles, so each fetches 1/cluster of every tile from L2 and
+    // multicasts it to its peers: L2->SM traffic (the limiter of a 128-row tile) drops by the cluster size.
+    int cluster = ctx->tc_cluster > 0 ? ctx->tc_cluster : 2;
+    if (dump || n_qtiles < 2 * cluster) cluster = 1;
     const CUtensorMap *mq = nullptr, *mt = nullptr;
-    if (get_tmap(ctx, direction, true, &mq)) return 1;
-    if (get_tmap(ctx, 1 - direction, false, &mt)) return 1;
+    if (get_tmap(ctx, direction, true, 1, &mq)) return 1;
+    if (get_tmap(ctx, 1 - direction, false, cluster, &mt)) return 1;
 
     TcParams p{};
+    p.cluster = cluster;
     p.ka = q.kp / 64;
     p.ksteps = (q.dim + B200M_AUG_COLS + 15) / 16;
     const size_t smem_limit = 227 * 1024;
@@ -446,7 +505,6 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     if (stages < 2) return b200m_fail_msg(ctx, "tc_candidates: descriptor too long for the shared-memory pipeline");
     p.stages = stages;
     p.n_ttiles = (int) (t.n_pad / B200M_TILE_N);
-    const int n_qtiles = (int) ((n_rows + B200M_TILE_M - 1) / B200M_TILE_M);
     int n_splits = 1;
     if (!dump) {
         // aim for >= 3 waves of CTAs; every split keeps at least 8 train tiles
@@ -481,7 +539,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.dump = dump;
     if (dump) p.tiles_per_split = (int) dump_t_tile;
     const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * kStageBytes + 1024 + 256;
-    dim3 grid((unsigned) (dump ? 1 : n_qtiles), (unsigned) n_splits, 1);
+    dim3 grid((unsigned) (dump ? 1 : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
     int kt = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : 16;
     int rc;
     switch (kt) {

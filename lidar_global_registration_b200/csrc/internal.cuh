@@ -60,6 +60,7 @@ struct b200m_ctx {
     DevBuf ws_cand_idx, ws_cand_cnt, ws_flag_rows, ws_counters, ws_scan, ws_out, ws_misc;
     DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr;
     void *tmap_cache = nullptr;
+    int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     bool profiling = false;
     b200m_stats stats{};
     cudaEvent_t ev[2] = {nullptr, nullptr};

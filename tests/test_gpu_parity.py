@@ -291,3 +291,17 @@ def test_properties_at_bench_scale():
     rows = np.random.default_rng(0).choice(n, 1024, replace=False)
     eo = orc.knn(np.ascontiguousarray(src[rows, :dim]), _dense(tgt, dim), k)
     _same((idx[rows], dist[rows], cnt[rows]), eo)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 3000, 9000, 2), ("shot", 1100, 2600, 5)])
+def test_multicast_cluster_sizes(monkeypatch, cluster, desc, nq, nt, k):
+    """The train tile is shared across a thread-block cluster by TMA multicast; every cluster size gives the
+    same (oracle-exact) lists."""
+    monkeypatch.setenv("B200M_TC_CLUSTER", str(cluster))
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        _same(ctx.knn(k, 0), orc.knn(_dense(src, dim), _dense(tgt, dim), k))
+        _same(ctx.knn(k, 1), orc.knn(_dense(tgt, dim), _dense(src, dim), k))
