@@ -177,20 +177,62 @@ struct RowState {
 };
 
 // Largest accumulator value an exact top-k member can have, given k accumulators <= T exist
-// (DESIGN.md "Certified candidates"); monotone in T, +inf for T = +inf.
+// (DESIGN.md "Certified candidates"); monotone in T, +inf for T = +inf.  sqrt.approx (2^-22 rel.)
+// is covered by the 2^-20 guard terms.
 __device__ __forceinline__ float cand_threshold(float T, float na, float eta, float slop, float gfac) {
-    float x = sqrtf(fmaxf(T + na + slop, 0.f));
-    float R = fmaf(x + eta, gfac, eta);
+    float x;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(x) : "f"(fmaxf(T + na + slop, 0.f)));
+    float R = fmaf(x * 1.0000009537f + eta, gfac, eta);
     float R2 = R * R;
     return (R2 - na) + slop + 9.5367431640625e-7f * (R2 + na);
 }
 
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }   // one FMNMX3
 
+#define F(i) __uint_as_float(r[i])
+// Rare path, kept compact (it is instantiated twice inside the tile loop and the loop has to stay in the
+// instruction cache): bit mask of the columns under the threshold, then one iteration per set bit with the
+// value fetched through a select tree (no dynamic register indexing, no local memory).
+template <int KT>
+__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
+                                           int32_t *__restrict__ out, int cap) {
+    const float thr0 = st.thr;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mask |= (F(i) < thr0) ? (1u << i) : 0u;
+    while (mask) {
+        const int i = __ffs((int) mask) - 1;
+        mask &= mask - 1;
+        float s16[16], s8[8], s4[4];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s16[j] = (i & 16) ? F(16 + j) : F(j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s8[j] = (i & 8) ? s16[8 + j] : s16[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s4[j] = (i & 4) ? s8[4 + j] : s8[j];
+        const float s2a = (i & 2) ? s4[2] : s4[0], s2b = (i & 2) ? s4[3] : s4[1];
+        float v = (i & 1) ? s2b : s2a;
+        if (v < st.thr) {   // the threshold may have tightened since the mask was taken
+            if (st.cnt < cap) out[st.cnt] = col0 + i;
+            st.cnt++;
+#pragma unroll
+            for (int s = 0; s < KT; ++s) {
+                float lo = fminf(st.tk[s], v);
+                v = fmaxf(st.tk[s], v);
+                st.tk[s] = lo;
+            }
+            float T = st.tk[KT - 1];
+#pragma unroll
+            for (int s = 0; s < KT - 1; ++s)
+                if (s == k - 1) T = st.tk[s];
+            st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
+        }
+    }
+}
+
 template <int KT>
 __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
                                               int32_t *__restrict__ out, int cap) {
-#define F(i) __uint_as_float(r[i])
     // fast path: 32 accumulators -> their minimum in 16 three-input min ops, one compare
     const float a0 = min3(F(0), F(1), F(2)), a1 = min3(F(3), F(4), F(5)), a2 = min3(F(6), F(7), F(8));
     const float a3 = min3(F(9), F(10), F(11)), a4 = min3(F(12), F(13), F(14)), a5 = min3(F(15), F(16), F(17));
@@ -198,38 +240,9 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0,
     const float a9 = min3(F(27), F(28), F(29)), a10 = fminf(F(30), F(31));
     const float b0 = min3(a0, a1, a2), b1 = min3(a3, a4, a5), b2 = min3(a6, a7, a8), b3 = min3(a9, a10, b0);
     const float m = min3(b1, b2, b3);
-    if (m < st.thr) {   // rare once the row's threshold has settled (inactive rows carry thr = -inf)
-        float thr = st.thr;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float v = F(i);
-            if (v < thr) {
-                if (st.cnt < cap) out[st.cnt] = col0 + i;
-                st.cnt++;
-#pragma unroll
-                for (int s = 0; s < KT; ++s) {
-                    float lo = fminf(st.tk[s], v);
-                    v = fmaxf(st.tk[s], v);
-                    st.tk[s] = lo;
-                }
-                if (!(thr < 3.0e38f)) {   // list just filled up: leave the accept-everything regime at once
-                    float T = st.tk[KT - 1];
-#pragma unroll
-                    for (int s = 0; s < KT - 1; ++s)
-                        if (s == k - 1) T = st.tk[s];
-                    thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
-                }
-            }
-        }
-        // otherwise the threshold is refreshed once per chunk (a stale, larger one only admits a superset)
-        float T = st.tk[KT - 1];
-#pragma unroll
-        for (int s = 0; s < KT - 1; ++s)
-            if (s == k - 1) T = st.tk[s];
-        st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
-    }
-#undef F
+    if (m < st.thr) slow_chunk<KT>(r, col0, st, k, out, cap);   // inactive rows carry thr = -inf
 }
+#undef F
 
 template <int KT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -366,23 +379,25 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tc_fence_after();
             const uint32_t taddr = lane_base + (uint32_t) (buf * B200M_TILE_N);
             const int col_base = t * B200M_TILE_N;
-            tmem_ld_32x32b_x32(taddr, ra);
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
-                if (p.dump) {
+            if (p.dump) {   // debug: raw accumulators of this tile
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    tmem_ld_32x32b_x32(taddr + (uint32_t) (c * 32), ra);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) p.dump[row_in_tile * B200M_TILE_N + c * 32 + i] = __uint_as_float(ra[i]);
                 }
+            }
+            // two register buffers: the TMEM read of the next 32 columns is in flight while these are filtered;
+            // the loop stays rolled so that its body (two copies of the chunk code) fits the instruction cache
+            tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
                 process_chunk<KT>(ra, col_base + c * 32, st, p.k, out, p.cap);
                 tmem_ld_wait();
                 if (c + 2 < 8) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
-                if (p.dump) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        p.dump[row_in_tile * B200M_TILE_N + (c + 1) * 32 + i] = __uint_as_float(rb[i]);
-                }
                 process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
             }
             tc_fence_before();
