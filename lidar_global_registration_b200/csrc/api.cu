@@ -49,6 +49,36 @@ int b200m_fail_msg(b200m_ctx *ctx, const std::string &msg) {
     return 1;
 }
 
+// ---- event-pool timing ----------------------------------------------------------------------
+void b200m_resolve_events(b200m_ctx *ctx) {
+    EventPool *pl = ctx->pool;
+    if (!pl || pl->used == 0) return;
+    cudaEventSynchronize(pl->ev[2 * (pl->used - 1) + 1]);
+    for (int i = 0; i < pl->used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pl->ev[2 * i], pl->ev[2 * i + 1]) == cudaSuccess) *pl->slot[i] += ms;
+    }
+    pl->used = 0;
+}
+
+StatTimer::StatTimer(b200m_ctx *c, double *s) : ctx(c) {
+    if (!ctx->profiling) return;
+    if (!ctx->pool) ctx->pool = new EventPool();
+    EventPool *pl = ctx->pool;
+    if (!pl->created) {
+        for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventCreate(&pl->ev[i]);
+        pl->created = true;
+    }
+    if (pl->used == EventPool::kPairs) b200m_resolve_events(ctx);
+    pair = pl->used++;
+    pl->slot[pair] = s;
+    cudaEventRecord(pl->ev[2 * pair], ctx->stream);
+}
+
+void StatTimer::stop() {
+    if (pair >= 0) cudaEventRecord(ctx->pool->ev[2 * pair + 1], ctx->stream);
+}
+
 #define REQUIRE_CTX()                                          \
     do {                                                       \
         if (!ctx) return b200m_fail_msg(nullptr, "null context"); \
@@ -106,9 +136,14 @@ void b200m_destroy(b200m_ctx *ctx) {
     ctx->prep.mean.release(); ctx->prep.red.release();
     DevBuf *ws[] = {&ctx->ws_cand_idx, &ctx->ws_cand_cnt, &ctx->ws_flag_rows, &ctx->ws_counters, &ctx->ws_scan,
                     &ctx->ws_out, &ctx->ws_misc, &ctx->ws_fidx, &ctx->ws_fdist, &ctx->ws_fcnt, &ctx->ws_ridx,
-                    &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr};
+                    &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr, &ctx->ws_totals};
     for (DevBuf *b : ws) b->release();
     tc_release(ctx);
+    if (ctx->pool) {
+        if (ctx->pool->created)
+            for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventDestroy(ctx->pool->ev[i]);
+        delete ctx->pool;
+    }
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -140,13 +175,22 @@ int b200m_get_stats(b200m_ctx *ctx, b200m_stats *out) {
     REQUIRE_CTX();
     if (!out) return b200m_fail_msg(ctx, "b200m_get_stats: null output");
     CK(cudaStreamSynchronize(ctx->stream));
+    b200m_resolve_events(ctx);
+    if (ctx->totals_init) {
+        unsigned long long h[2] = {0, 0};
+        CK(cudaMemcpy(h, ctx->ws_totals.p, sizeof(h), cudaMemcpyDeviceToHost));
+        ctx->stats.rows_flagged = (int64_t) h[0];
+        ctx->stats.candidates = (int64_t) h[1];
+    }
     *out = ctx->stats;
     return 0;
 }
 
 int b200m_reset_stats(b200m_ctx *ctx) {
     REQUIRE_CTX();
+    b200m_resolve_events(ctx);
     ctx->stats = b200m_stats{};
+    if (ctx->totals_init) CK(cudaMemsetAsync(ctx->ws_totals.p, 0, 64, ctx->stream));
     return 0;
 }
 
@@ -204,6 +248,11 @@ int b200m_upload_device(b200m_ctx *ctx, int side, const float *device_base, size
 }
 
 // ---- kNN --------------------------------------------------------------------------------
+__global__ void accumulate_counters_kernel(const int32_t *counters, unsigned long long *totals) {
+    totals[0] += (unsigned long long) counters[0];
+    totals[1] += *reinterpret_cast<const unsigned long long *>(counters + 2);
+}
+
 __global__ void fill_empty_kernel(size_t n_rows, int k, int32_t *idx, float *dist, int32_t *count) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_rows * (size_t) k) { idx[i] = -1; dist[i] = 0.f; }
@@ -292,12 +341,15 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
         ctx->stats.launches += 1;
         tf.stop();
     }
-    if (ctx->profiling) {
-        struct { int32_t flagged, pad; unsigned long long cands; } h;
-        CK(cudaMemcpyAsync(&h, ctx->ws_counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->stats.rows_flagged += h.flagged;
-        ctx->stats.candidates += (int64_t) h.cands;
+    if (ctx->profiling) {   // fold this call's counters into the running totals on the device (read at get_stats)
+        CK(ctx->ws_totals.reserve(64));
+        if (!ctx->totals_init) {
+            CK(cudaMemsetAsync(ctx->ws_totals.p, 0, 64, st));
+            ctx->totals_init = true;
+        }
+        accumulate_counters_kernel<<<1, 1, 0, st>>>(ctx->ws_counters.as<int32_t>(),
+                                                    ctx->ws_totals.as<unsigned long long>());
+        CK(cudaGetLastError());
     }
     return 0;
 }

@@ -58,12 +58,14 @@ struct b200m_ctx {
     Side side[2];
     TcPrep prep;
     DevBuf ws_cand_idx, ws_cand_cnt, ws_flag_rows, ws_counters, ws_scan, ws_out, ws_misc;
-    DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr;
+    DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr, ws_totals;
+    bool totals_init = false;
     void *tmap_cache = nullptr;
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     bool profiling = false;
     b200m_stats stats{};
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    struct EventPool *pool = nullptr;
 };
 
 int b200m_fail(b200m_ctx *ctx, const char *what, cudaError_t e, const char *file, int line);
@@ -75,22 +77,23 @@ int b200m_fail_msg(b200m_ctx *ctx, const std::string &msg);
         if (_e != cudaSuccess) return b200m_fail(ctx, #expr, _e, __FILE__, __LINE__); \
     } while (0)
 
-// RAII-less timing helper: records events around a region when profiling is on.
+// Per-region device timing without host synchronisation: when profiling is on, a region records a pair of
+// events from the context's pool on the stream; pairs are resolved (cudaEventElapsedTime) when the stats are
+// read or the pool fills up, so the timed program runs exactly as it does unprofiled.
+struct EventPool {
+    static const int kPairs = 128;
+    cudaEvent_t ev[2 * kPairs] = {};
+    double *slot[kPairs] = {};
+    int used = 0;
+    bool created = false;
+};
+void b200m_resolve_events(b200m_ctx *ctx);
+
 struct StatTimer {
     b200m_ctx *ctx;
-    double *slot;
-    StatTimer(b200m_ctx *c, double *s) : ctx(c), slot(s) {
-        if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
-    }
-    void stop() {
-        if (ctx->profiling) {
-            cudaEventRecord(ctx->ev[1], ctx->stream);
-            cudaEventSynchronize(ctx->ev[1]);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-            *slot += ms;
-        }
-    }
+    int pair = -1;
+    StatTimer(b200m_ctx *c, double *s);
+    void stop();
 };
 
 // ---- kernel launchers (one translation unit each) ---------------------------
