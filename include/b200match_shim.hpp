@@ -1,0 +1,250 @@
+// b200match_shim.hpp -- header-only C++ host mirror of the reference's matcher interface on top of
+// the C-ABI in b200match.h.  It puts the reference's own names and signatures back:
+//
+//   matchBF<FeatureT> / matchFLANN<FeatureT> / matchLocal<FeatureT>(radius = inf)
+//                                  reference include/matching.h:368-383, :562-678
+//   MultivaluedCorrespondence      reference include/common.h:192-195
+//   Correspondence                 reference include/common.h:120-127
+//   FeatureBasedMatcher, OneSidedMatcher / LeftToRightMatcher / RatioMatcher  (match(), getAverageDistance(),
+//   getClassName())                reference include/matching.h:25-42, :385-478
+//
+// With -DB200MATCH_WITH_PCL the feature types are PCL's (pcl::FPFHSignature33, pcl::SHOT352,
+// pcl::Histogram<135>) and clouds are pcl::PointCloud<FeatureT>::ConstPtr exactly as in the reference; without
+// it (this repository's tests: PCL is not installed) layout-identical mirror structs are used and a "cloud"
+// is a std::vector<FeatureT>.  Errors surface as std::runtime_error -- the convention of the reference's
+// rassert (include/utils.h:9).  There is no CPU fallback anywhere below.
+#pragma once
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200match.h"
+
+#ifdef B200MATCH_WITH_PCL
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <pcl/point_representation.h>
+#endif
+
+namespace b200match {
+
+#ifndef B200MATCH_WITH_PCL
+// Layout mirrors of the PCL point structs the reference matches on (sizeof must equal PCL's).
+struct FPFHSignature33 { float histogram[33]; static constexpr int descriptorSize() { return 33; } };
+struct SHOT352 { float descriptor[352]; float rf[9]; static constexpr int descriptorSize() { return 352; } };
+struct Histogram135 { float histogram[135]; static constexpr int descriptorSize() { return 135; } };
+static_assert(sizeof(FPFHSignature33) == 132, "pcl::FPFHSignature33 is 132 bytes");
+static_assert(sizeof(SHOT352) == 1444, "pcl::SHOT352 is 1444 bytes");
+static_assert(sizeof(Histogram135) == 540, "pcl::Histogram<135> is 540 bytes");
+template <typename FeatureT> using FeatureCloud = std::vector<FeatureT>;
+template <typename FeatureT> inline const FeatureT *cloud_data(const FeatureCloud<FeatureT> &c) { return c.data(); }
+template <typename FeatureT> inline size_t cloud_size(const FeatureCloud<FeatureT> &c) { return c.size(); }
+template <typename FeatureT> inline int feature_dim() { return FeatureT::descriptorSize(); }
+#else
+template <typename FeatureT> using FeatureCloud = typename pcl::PointCloud<FeatureT>::ConstPtr;
+template <typename FeatureT> inline const FeatureT *cloud_data(const FeatureCloud<FeatureT> &c) { return c->points.data(); }
+template <typename FeatureT> inline size_t cloud_size(const FeatureCloud<FeatureT> &c) { return c->size(); }
+template <typename FeatureT> inline int feature_dim() {
+    return pcl::DefaultPointRepresentation<FeatureT>().getNumberOfDimensions();   // as include/matching.h:598-599
+}
+#endif
+
+// reference include/common.h:192-195 (pcl::Indices == std::vector<int>)
+struct MultivaluedCorrespondence {
+    std::vector<int> match_indices;
+    std::vector<float> distances;
+};
+
+// reference include/common.h:120-127; binary-identical to b200m_corr
+struct Correspondence {
+    int index_query = -1, index_match = -1;
+    float distance = std::numeric_limits<float>::max();
+    float threshold = 0.f;
+};
+static_assert(sizeof(Correspondence) == sizeof(b200m_corr), "Correspondence must stay 16 bytes");
+typedef std::vector<Correspondence> Correspondences;
+typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
+
+// The fields of AlignmentParameters (reference include/common.h:135-163) read on this path.
+struct AlignmentParameters {
+    bool use_bfmatcher = true;      // :144  either backend maps to the same exact GPU search
+    int bf_block_size = 10000;      // :145  accepted, unused
+    int ratio_k = 2;                // :146  MATCHING_RATIO_K
+    int randomness = 1;             // :147  k
+    float distance_thr = std::numeric_limits<float>::max();   // :139
+    std::string matching_id = "lr"; // :149  one_sided | lr | ratio
+    float ratio_thr = 1.1f;         // MATCHING_RATIO_THRESHOLD, include/common.h:50
+    int device = 0;
+    int precision = B200M_PREC_TC_F16;
+};
+
+class Context {   // RAII b200m_ctx; one per host thread
+public:
+    explicit Context(int device = 0) {
+        if (b200m_create(&ctx_, device) != 0) throw std::runtime_error(b200m_last_error(nullptr));
+    }
+    ~Context() { b200m_destroy(ctx_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    b200m_ctx *get() const { return ctx_; }
+    void check(int rc) const {
+        if (rc != 0) throw std::runtime_error(b200m_last_error(ctx_));
+    }
+    template <typename FeatureT>
+    void upload(int side, const FeatureCloud<FeatureT> &cloud) {
+        // &cloud.points[0] with stride sizeof(FeatureT): what pcl2cv reads (reference include/matching.h:556-558)
+        check(b200m_upload(ctx_, side, reinterpret_cast<const float *>(cloud_data<FeatureT>(cloud)), cloud_size<FeatureT>(cloud),
+                           sizeof(FeatureT), feature_dim<FeatureT>(), 0));
+    }
+
+private:
+    b200m_ctx *ctx_ = nullptr;
+};
+
+inline b200m_params make_params(const AlignmentParameters &p, int mode, int k) {
+    b200m_params q;
+    q.k = k;
+    q.mode = mode;
+    q.ratio_thr = p.ratio_thr;
+    q.distance_thr = p.distance_thr;
+    q.precision = p.precision;
+    q.cand_cap = 0;
+    return q;
+}
+
+// matchBF<FeatureT> (reference include/matching.h:594-634): one entry per query, <= k matches, ascending L2.
+template <typename FeatureT>
+std::vector<MultivaluedCorrespondence> matchBF(const FeatureCloud<FeatureT> &query_features,
+                                               const FeatureCloud<FeatureT> &train_features,
+                                               const AlignmentParameters &parameters) {
+    Context ctx(parameters.device);
+    ctx.upload<FeatureT>(0, query_features);
+    ctx.upload<FeatureT>(1, train_features);
+    const size_t nq = cloud_size<FeatureT>(query_features);
+    const int k = parameters.randomness;
+    std::vector<int32_t> idx(nq * k);
+    std::vector<float> dist(nq * k);
+    std::vector<int32_t> cnt(nq);
+    b200m_params p = make_params(parameters, B200M_MODE_KNN_ONLY, k);
+    ctx.check(b200m_knn(ctx.get(), &p, 0, 0, 0, idx.data(), dist.data(), cnt.data()));
+    std::vector<MultivaluedCorrespondence> out(nq);
+    for (size_t i = 0; i < nq; ++i) {
+        out[i].match_indices.assign(idx.begin() + i * k, idx.begin() + i * k + cnt[i]);
+        out[i].distances.assign(dist.begin() + i * k, dist.begin() + i * k + cnt[i]);
+    }
+    return out;
+}
+
+// matchFLANN<FeatureT> (reference include/matching.h:562-592): same exact result set.
+template <typename FeatureT>
+std::vector<MultivaluedCorrespondence> matchFLANN(const FeatureCloud<FeatureT> &query_features,
+                                                  const FeatureCloud<FeatureT> &train_features,
+                                                  const AlignmentParameters &parameters) {
+    return matchBF<FeatureT>(query_features, train_features, parameters);
+}
+
+// matchLocal<FeatureT> with match_search_radius = inf (reference include/matching.h:637-678 as called by
+// tests/flann_bf_matcher.h:66-72).  The spatially gated variant is a next-row item.
+template <typename FeatureT>
+std::vector<MultivaluedCorrespondence> matchLocal(const FeatureCloud<FeatureT> &query_features,
+                                                  const FeatureCloud<FeatureT> &train_features,
+                                                  const AlignmentParameters &parameters) {
+    return matchBF<FeatureT>(query_features, train_features, parameters);
+}
+
+// FeatureBasedMatcher (reference include/matching.h:25-42) at the descriptor seam.
+class FeatureBasedMatcher {
+public:
+    using Ptr = std::shared_ptr<FeatureBasedMatcher>;
+    virtual ~FeatureBasedMatcher() = default;
+    virtual CorrespondencesPtr match() = 0;
+    inline float getAverageDistance() const { return average_distance_; }
+    virtual std::string getClassName() = 0;
+
+protected:
+    float average_distance_ = std::numeric_limits<float>::max();
+};
+
+template <typename FeatureT>
+class FeatureBasedMatcherImpl : public FeatureBasedMatcher {
+public:
+    // thresholds_*: calculateSmoothedDensities outputs (may be empty); kps_indices_*: keypoint-local -> cloud-global
+    // index maps applied by finalize (reference include/matching.h:356-362); may be empty.
+    FeatureBasedMatcherImpl(FeatureCloud<FeatureT> src, FeatureCloud<FeatureT> tgt, AlignmentParameters parameters,
+                            std::vector<float> thresholds_src = {}, std::vector<float> thresholds_tgt = {},
+                            std::vector<int> kps_indices_src = {}, std::vector<int> kps_indices_tgt = {})
+        : src_(std::move(src)), tgt_(std::move(tgt)), parameters_(std::move(parameters)),
+          thr_src_(std::move(thresholds_src)), thr_tgt_(std::move(thresholds_tgt)),
+          kps_src_(std::move(kps_indices_src)), kps_tgt_(std::move(kps_indices_tgt)) {}
+
+    CorrespondencesPtr match() override {
+        Context ctx(parameters_.device);
+        ctx.upload<FeatureT>(0, src_);
+        ctx.upload<FeatureT>(1, tgt_);
+        const int k = mode() == B200M_MODE_RATIO ? (parameters_.ratio_k < 2 ? 2 : parameters_.ratio_k) : parameters_.randomness;
+        b200m_params p = make_params(parameters_, mode(), k);
+        const size_t nq = cloud_size<FeatureT>(src_);
+        auto out = std::make_shared<Correspondences>(nq * (mode() == B200M_MODE_MUTUAL ? k : 1));
+        size_t n = 0;
+        const bool thr = !thr_src_.empty() && !thr_tgt_.empty();
+        ctx.check(b200m_match(ctx.get(), &p, thr ? thr_src_.data() : nullptr, thr ? thr_tgt_.data() : nullptr,
+                              reinterpret_cast<b200m_corr *>(out->data()), out->size(), &n, &average_distance_));
+        out->resize(n);
+        for (auto &c : *out) {   // finalize
+            if (!kps_src_.empty()) c.index_query = kps_src_[c.index_query];
+            if (!kps_tgt_.empty()) c.index_match = kps_tgt_[c.index_match];
+        }
+        return out;
+    }
+
+protected:
+    virtual int mode() const = 0;
+    FeatureCloud<FeatureT> src_, tgt_;
+    AlignmentParameters parameters_;
+    std::vector<float> thr_src_, thr_tgt_;
+    std::vector<int> kps_src_, kps_tgt_;
+};
+
+template <typename FeatureT>
+class OneSidedMatcher : public FeatureBasedMatcherImpl<FeatureT> {   // reference include/matching.h:385-416
+public:
+    using FeatureBasedMatcherImpl<FeatureT>::FeatureBasedMatcherImpl;
+    std::string getClassName() override { return "OneSidedMatcher"; }
+protected:
+    int mode() const override { return B200M_MODE_ONE_SIDED; }
+};
+
+template <typename FeatureT>
+class LeftToRightMatcher : public FeatureBasedMatcherImpl<FeatureT> {   // reference include/matching.h:418-458
+public:
+    using FeatureBasedMatcherImpl<FeatureT>::FeatureBasedMatcherImpl;
+    std::string getClassName() override { return "LeftToRightMatcher"; }
+protected:
+    int mode() const override { return B200M_MODE_MUTUAL; }
+};
+
+template <typename FeatureT>
+class RatioMatcher : public FeatureBasedMatcherImpl<FeatureT> {   // reference include/matching.h:460-478 (stub there)
+public:
+    using FeatureBasedMatcherImpl<FeatureT>::FeatureBasedMatcherImpl;
+    std::string getClassName() override { return "RatioMatcher"; }
+protected:
+    int mode() const override { return B200M_MODE_RATIO; }
+};
+
+// getFeatureBasedMatcherFromParameters (reference src/matching.cpp:21-76) for one feature type.
+template <typename FeatureT, typename... Args>
+FeatureBasedMatcher::Ptr getFeatureBasedMatcherFromParameters(const FeatureCloud<FeatureT> &src, const FeatureCloud<FeatureT> &tgt,
+                                                              const AlignmentParameters &parameters, Args &&...rest) {
+    if (parameters.matching_id == "one_sided")
+        return std::make_shared<OneSidedMatcher<FeatureT>>(src, tgt, parameters, std::forward<Args>(rest)...);
+    if (parameters.matching_id == "lr")
+        return std::make_shared<LeftToRightMatcher<FeatureT>>(src, tgt, parameters, std::forward<Args>(rest)...);
+    if (parameters.matching_id == "ratio")
+        return std::make_shared<RatioMatcher<FeatureT>>(src, tgt, parameters, std::forward<Args>(rest)...);
+    throw std::runtime_error("Matching method " + parameters.matching_id + " isn't supported by the B200 matcher");
+}
+
+}  // namespace b200match

@@ -179,7 +179,7 @@ class ShardedMatcher:
         import torch.distributed as dist
         gathered = []
         for x in local:
-            out = torch.empty((self.world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+            out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
             dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
-            gathered.append(out)
+            gathered.append(out.view((self.world,) + tuple(x.shape)))
         return self.b.merge(k, gathered[0], gathered[1], gathered[2])

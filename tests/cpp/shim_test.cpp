@@ -1,0 +1,86 @@
+// C++ user of the shim, written like the reference's own tests/flann_bf_matcher.h:31-90: BF == FLANN == Local
+// indices in both directions, then the matcher classes.  Descriptors come from a raw float32 dump written by the
+// pytest driver (tests/test_cpp_shim.py), results go back as text so the driver can compare with the oracle.
+//   shim_test <fpfh|shot|rops> <src.bin> <n_src> <tgt.bin> <n_tgt> <k> <out.txt>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "b200match_shim.hpp"
+
+using namespace b200match;
+
+template <typename FeatureT>
+static std::vector<FeatureT> load(const char *path, size_t n) {
+    std::vector<FeatureT> v(n);
+    std::ifstream f(path, std::ios::binary);
+    f.read(reinterpret_cast<char *>(v.data()), (std::streamsize) (n * sizeof(FeatureT)));
+    if (!f) throw std::runtime_error(std::string("cannot read ") + path);
+    return v;
+}
+
+static void assertCorrespondencesEqual(int i, const MultivaluedCorrespondence &a, const MultivaluedCorrespondence &b) {
+    if (a.match_indices != b.match_indices) {   // tests/flann_bf_matcher.h:16-29
+        std::cerr << "[" << i << "] match indices differ\n";
+        abort();
+    }
+}
+
+template <typename FeatureT>
+static int run(char **argv) {
+    size_t ns = std::stoul(argv[3]), nt = std::stoul(argv[5]);
+    auto src = load<FeatureT>(argv[2], ns);
+    auto tgt = load<FeatureT>(argv[4], nt);
+    AlignmentParameters parameters;
+    parameters.randomness = std::stoi(argv[6]);
+    FILE *out = fopen(argv[7], "w");
+    for (int dir = 0; dir < 2; ++dir) {
+        const auto &q = dir ? tgt : src;
+        const auto &t = dir ? src : tgt;
+        auto bf = matchBF<FeatureT>(q, t, parameters);
+        auto flann = matchFLANN<FeatureT>(q, t, parameters);
+        auto local = matchLocal<FeatureT>(q, t, parameters);
+        if (bf.size() != q.size()) abort();   // rassert at include/matching.h:312
+        for (size_t i = 0; i < q.size(); ++i) {
+            assertCorrespondencesEqual((int) i, bf[i], flann[i]);
+            assertCorrespondencesEqual((int) i, bf[i], local[i]);
+            fprintf(out, "knn %d %zu %zu", dir, i, bf[i].match_indices.size());
+            for (size_t m = 0; m < bf[i].match_indices.size(); ++m)
+                fprintf(out, " %d %.9g", bf[i].match_indices[m], bf[i].distances[m]);
+            fprintf(out, "\n");
+        }
+    }
+    for (const char *id : {"one_sided", "lr", "ratio"}) {
+        if (!strcmp(id, "ratio") && parameters.randomness < 2) continue;
+        parameters.matching_id = id;
+        auto matcher = getFeatureBasedMatcherFromParameters<FeatureT>(src, tgt, parameters);
+        auto corrs = matcher->match();
+        fprintf(out, "matcher %s %s %zu %.9g\n", id, matcher->getClassName().c_str(), corrs->size(), matcher->getAverageDistance());
+        for (const auto &c : *corrs) fprintf(out, "corr %s %d %d %.9g\n", id, c.index_query, c.index_match, c.distance);
+    }
+    try {
+        parameters.matching_id = "cluster";
+        getFeatureBasedMatcherFromParameters<FeatureT>(src, tgt, parameters);
+        abort();
+    } catch (const std::runtime_error &) {
+    }
+    fclose(out);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc != 8) {
+        std::cerr << "usage: shim_test <fpfh|shot|rops> src.bin n_src tgt.bin n_tgt k out.txt\n";
+        return 2;
+    }
+    try {
+        if (!strcmp(argv[1], "fpfh")) return run<FPFHSignature33>(argv);
+        if (!strcmp(argv[1], "shot")) return run<SHOT352>(argv);
+        if (!strcmp(argv[1], "rops")) return run<Histogram135>(argv);
+    } catch (const std::exception &e) {
+        std::cerr << "error: " << e.what() << "\n";
+        return 1;
+    }
+    return 2;
+}

@@ -1,0 +1,71 @@
+"""The C++ host mirror (include/b200match_shim.hpp): compiles against the C-ABI on CPU; on the GPU box the
+reference-style C++ program (tests/cpp/shim_test.cpp) must reproduce the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lidar_global_registration_b200 import build as b200_build
+from lidar_global_registration_b200 import synth
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "shim_test")
+
+
+def _build_exe():
+    b200_build.build()
+    src = os.path.join(ROOT, "tests", "cpp", "shim_test.cpp")
+    deps = [src, os.path.join(ROOT, "include", "b200match_shim.hpp"), os.path.join(ROOT, "include", "b200match.h")]
+    if os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
+        return EXE
+    libdir = os.path.join(ROOT, "lidar_global_registration_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+                    "-L", libdir, "-l:libb200match.so", "-Wl,-rpath," + libdir], check=True)
+    return EXE
+
+
+def test_shim_compiles_and_links():
+    exe = _build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("desc,ns,nt,k", [("fpfh", 700, 900, 2), ("shot", 300, 420, 1), ("rops", 280, 300, 3)])
+def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
+    exe = _build_exe()
+    src, tgt, dim = synth.make_pair(desc, ns, nt, nan_frac=0.01)
+    sp, tp, op = tmp_path / "s.bin", tmp_path / "t.bin", tmp_path / "o.txt"
+    src.tofile(sp)
+    tgt.tofile(tp)
+    r = subprocess.run([exe, desc, str(sp), str(ns), str(tp), str(nt), str(k), str(op)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    s_d, t_d = src[:, :dim], tgt[:, :dim]
+    exp = {0: orc.knn(s_d, t_d, k), 1: orc.knn(t_d, s_d, k)}
+    got_corr = {"one_sided": [], "lr": [], "ratio": []}
+    heads = {}
+    n_knn = 0
+    for line in open(op):
+        w = line.split()
+        if w[0] == "knn":
+            d, i, c = int(w[1]), int(w[2]), int(w[3])
+            idx, dist, cnt = exp[d]
+            assert c == cnt[i]
+            assert [int(x) for x in w[4::2]] == idx[i, :c].tolist()
+            assert [np.float32(x) for x in w[5::2]] == dist[i, :c].tolist()
+            n_knn += 1
+        elif w[0] == "matcher":
+            heads[w[1]] = (w[2], int(w[3]), np.float32(w[4]))
+        elif w[0] == "corr":
+            got_corr[w[1]].append((int(w[2]), int(w[3]), np.float32(w[4])))
+    assert n_knn == ns + nt
+    fmax = np.float32(np.finfo(np.float32).max)
+    for mid, mode, cls in (("one_sided", "one_sided", "OneSidedMatcher"), ("lr", "mutual", "LeftToRightMatcher"),
+                           ("ratio", "ratio", "RatioMatcher")):
+        if mid == "ratio" and k < 2:
+            continue
+        e, eavg = orc.match(s_d, t_d, max(k, 2) if mid == "ratio" else k, mode, 1.1, fmax)
+        assert heads[mid][0] == cls and heads[mid][1] == len(e) and heads[mid][2] == np.float32(eavg)
+        assert got_corr[mid] == [(int(a), int(b), np.float32(c)) for a, b, c in zip(e["index_query"], e["index_match"], e["distance"])]
