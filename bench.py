@@ -97,6 +97,10 @@ class CpuReference:
         from lidar_global_registration_b200 import synth
         from oracle import oracle as orc
         self.orc, self.k, self.both = orc, k, mode == "mutual"
+        try:
+            orc.set_num_threads(len(os.sched_getaffinity(0)))   # all host cores, whatever OMP_NUM_THREADS torchrun exported
+        except AttributeError:
+            orc.set_num_threads(os.cpu_count() or 1)
         self.cores = orc.num_threads()
         self.n_src, self.n_tgt = n_src, n_tgt
         # numpy generation is slow at the named sizes: generate <= 200k rows and tile them with small

@@ -13,6 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200match.so")
 SOURCES = ["api.cu", "pack.cu", "exact.cu", "filter.cu", "candidates_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+LINK_VERSION = "cudart-shared-1"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wall",
          "-diag-suppress", "177"]
@@ -30,7 +31,7 @@ def _stale(target, deps):
 
 def source_hash():
     """Content hash of everything the library is built from (sources, headers, flags)."""
-    h = hashlib.sha256(" ".join(FLAGS).encode())
+    h = hashlib.sha256((" ".join(FLAGS) + LINK_VERSION).encode())
     files = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "internal.cuh"),
                                                        os.path.join(HERE, "..", "include", "b200match.h")]
     for f in files:
@@ -64,9 +65,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libb200match build failed")
-    if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-        subprocess.run(cmd, check=True)
+    # The stamp did not match, so always relink.  One CUDA runtime per process: bind to the shared libcudart.so.12
+    # (the one torch has already loaded when the library is used next to torch; /usr/local/cuda/lib64 for
+    # stand-alone C++ users) instead of a private static copy -- two runtimes in one process can disagree about
+    # the current device on multi-GPU ranks.
+    cmd = [NVCC, "-shared", "-cudart", "shared", "-o", LIB] + objs + [
+        "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+    subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:
         f.write(digest + "\n")
     return LIB

@@ -97,6 +97,15 @@ static inline void l2_norm_block(const float *q, const float *train, size_t t_st
     for (int u = 0; u < ORC_UNROLL; ++u) out[u] = sqrtf(s[u]);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the timed CPU baseline asks for all host cores explicitly. */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void) n;
+#endif
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -96,6 +96,12 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads.argtypes = [C.c_int]
+    lib().orc_set_num_threads.restype = None
+    lib().orc_set_num_threads(int(n))
+
+
 def knn(query, train, k, scalar=False):
     """Canonical exact kNN == matchLocal(radius=inf) == matchFLANN result set
     (include/matching.h:637-678, :562-592).  Returns (idx[nq,k] int32 -1 padded,
