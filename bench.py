@@ -31,6 +31,7 @@ WORKLOADS = {
     "c1": ("fpfh", 20000, 20000, 1, "mutual", "FPFH-33 20k x 20k k=1 mutual (BASELINE configs[0])"),
     "c2": ("fpfh", 200000, 200000, 2, "ratio", "FPFH-33 200k x 200k k=2 + ratio 1.1 (BASELINE configs[1])"),
     "c3": ("shot", 500000, 500000, 2, "mutual", "SHOT-352 500k x 500k k=2 + mutual (BASELINE configs[2])"),
+    "c3s": ("shot", 40000, 40000, 2, "mutual", "SHOT-352 40k x 40k k=2 + mutual (reduced copy of configs[2], for debugging)"),
     "c4": ("fpfh", 2000000, 2000000, 5, "mutual", "FPFH-33 2M x 2M k=5 mutual k-lists (BASELINE configs[3])"),
 }
 METRIC = "descriptor queries/sec (k=2 + mutual)"
@@ -184,6 +185,10 @@ def run_b200(args, wl):
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
+        if "B200M_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["B200M_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)   # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:

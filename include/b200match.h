@@ -86,7 +86,8 @@ typedef struct {
 B200M_API int b200m_create(b200m_ctx **ctx, int device);
 B200M_API void b200m_destroy(b200m_ctx *ctx);
 B200M_API const char *b200m_last_error(const b200m_ctx *ctx); /* ctx may be NULL: last create error */
-/* run on the caller's CUDA stream (a cudaStream_t passed as void*), e.g. torch's current stream; NULL = own stream */
+/* run on the caller's CUDA stream (a cudaStream_t passed as void*), e.g. torch's current stream; NULL = the
+ * context's own non-blocking stream.  To name the legacy default stream pass cudaStreamLegacy ((void*)0x1). */
 B200M_API int b200m_set_stream(b200m_ctx *ctx, void *cuda_stream);
 B200M_API int b200m_sync(b200m_ctx *ctx);
 B200M_API int b200m_set_profiling(b200m_ctx *ctx, int on);

@@ -34,7 +34,10 @@ class GpuBackend:
         self.use_torch_stream()
 
     def use_torch_stream(self):
-        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        """Queue the library's work on torch's current stream.  torch reports the legacy default stream as
+        handle 0, which the C-ABI reads as "use the context's own stream": pass cudaStreamLegacy (0x1) instead,
+        otherwise torch's ops (NCCL waits, .item(), events) would not be ordered with the library's kernels."""
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
 
     def close(self):
         self.ctx.close()
