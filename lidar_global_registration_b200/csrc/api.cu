@@ -117,7 +117,11 @@ int b200m_create(b200m_ctx **out, int device) {
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("B200M_TC_CLUSTER")) {
         int c = atoi(e);
-        if (c == 1 || c == 2 || c == 4) ctx->tc_cluster = c;
+        if (c == 1 || c == 2 || c == 4) { ctx->tc_cluster = c; ctx->tc_pair = 0; }
+    }
+    if (const char *e = getenv("B200M_TC_MODE")) {
+        if (!strcmp(e, "mcast")) ctx->tc_pair = 0;
+        if (!strcmp(e, "pair")) ctx->tc_pair = 1;
     }
     *out = ctx;
     return 0;
@@ -513,8 +517,8 @@ int b200m_debug_tc_tile(b200m_ctx *ctx, int direction, size_t q_row0, size_t t_t
     if (q_row0 >= q.n || t_tile * B200M_TILE_N >= t.n_pad) return b200m_fail_msg(ctx, "debug_tc_tile: tile out of range");
     if (!ctx->prep.ready || ctx->prep.ver[0] != ctx->side[0].version || ctx->prep.ver[1] != ctx->side[1].version)
         CK(launch_tc_prepare(ctx));
-    CK(ctx->ws_out.reserve(sizeof(float) * B200M_TILE_M * B200M_TILE_N));
-    CK(cudaMemsetAsync(ctx->ws_out.p, 0xff, sizeof(float) * B200M_TILE_M * B200M_TILE_N, ctx->stream));
+    CK(ctx->ws_out.reserve(sizeof(float) * 2 * B200M_TILE_M * B200M_TILE_N));   // pair mode dumps two query tiles
+    CK(cudaMemsetAsync(ctx->ws_out.p, 0xff, sizeof(float) * 2 * B200M_TILE_M * B200M_TILE_N, ctx->stream));
     int n_lists = 0, cap = 0;
     size_t n_rows = q.n - q_row0 < (size_t) B200M_TILE_M ? q.n - q_row0 : (size_t) B200M_TILE_M;
     if (tc_candidates(ctx, direction, q_row0, n_rows, 1, 0, &n_lists, &cap, ctx->ws_out.as<float>(), t_tile)) return 1;

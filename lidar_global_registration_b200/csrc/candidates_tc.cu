@@ -35,7 +35,7 @@ constexpr int kThreads = 192;            // warp 0: TMA producer, warp 1: MMA is
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
 constexpr long long kWaitLimitCycles = 4000000000LL;   // ~2 s: a wedged pipeline traps instead of hanging the GPU
@@ -45,6 +45,8 @@ struct TcParams {
     int ksteps;           // K=16 MMA steps actually needed: ceil((dim + 3) / 16)
     int stages;           // B ring depth
     int cluster;          // CTAs per cluster sharing every train tile by TMA multicast (1, 2 or 4)
+    int pair;             // 1: CTA-pair mode (cta_group::2, M=256 across two SMs, each CTA holds half of B); cluster == 2
+    int stage_bytes;      // bytes of one B stage in this CTA's shared memory (32 KB, or 16 KB in pair mode)
     int n_ttiles;         // 256-row train tiles
     int tiles_per_split;
     int q_row0;           // first query row of this call (row_begin)
@@ -109,6 +111,21 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *tmap, uint32_t leader_bar, int c0, int c1) {
+    // CTA-pair form: the bytes land in THIS CTA's shared memory, the transaction count goes to the leader's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -127,6 +144,22 @@ __device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask)
                  : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -166,6 +199,8 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D=F32 (bit 4), A=B=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t) (B200M_TILE_N >> 3) << 17) | ((uint32_t) (B200M_TILE_M >> 4) << 24);
+// CTA-pair form: M = 256 (128 rows from each CTA's A tile), N = 256 (128 train rows from each CTA's B stage)
+constexpr uint32_t kInstrDescPair = (1u << 4) | ((uint32_t) (B200M_TILE_N >> 3) << 17) | ((uint32_t) ((2 * B200M_TILE_M) >> 4) << 24);
 
 // ---- per-row selection state ------------------------------------------------------------------
 template <int KT>
@@ -252,7 +287,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + (size_t) p.ka * kATileBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t) p.stages * kStageBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t) p.stages * p.stage_bytes);
     // barrier map: [0..S) full, [S..2S) empty, 2S a_full, 2S+1.. tmem_full[2], 2S+3.. tmem_empty[2]
     const uint32_t bar_base = smem_u32(bars);
     auto bar_full = [&](int s) { return bar_base + 8u * (uint32_t) s; };
@@ -272,21 +307,29 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), (uint32_t) p.cluster);   // every CTA of the cluster must have read the stage
+            // multicast mode: every CTA of the cluster must have read the stage; pair mode: one commit frees it
+            mbar_init(bar_empty(s), p.pair ? 1u : (uint32_t) p.cluster);
         }
         mbar_init(bar_a, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), 128);
+            mbar_init(bar_tempty(b), p.pair ? 256u : 128u);   // pair mode: both CTAs' epilogues report to the leader
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (p.pair) {   // the same warp of both CTAs of the pair allocates
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
@@ -300,29 +343,49 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ===== TMA producer =====
         if (lane == 0) {
             const int q_row = p.q_row0 + qtile * B200M_TILE_M;
-            mbar_arrive_expect_tx(bar_a, (uint32_t) (p.ka * kATileBytes));
-            for (int a = 0; a < p.ka; ++a) tma_load_2d(smem_u32(sA + (size_t) a * kATileBytes), &tmap_q, bar_a, a * 64, q_row);
-            int it = 0;
-            for (int t = t0; t < t1; ++t) {
-                for (int a = 0; a < p.ka; ++a, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
-                    mbar_wait(bar_empty(s), ph ^ 1u);
-                    mbar_arrive_expect_tx(bar_full(s), (uint32_t) kStageBytes);
-                    if (p.cluster == 1) {
-                        tma_load_2d(smem_u32(sB + (size_t) s * kStageBytes), &tmap_t, bar_full(s), a * 64, t * B200M_TILE_N);
-                    } else {
-                        // this CTA fetches its 1/cluster slice of the tile and multicasts it into every peer
-                        const int slice = B200M_TILE_N / p.cluster;
-                        tma_load_2d_mcast(smem_u32(sB + (size_t) s * kStageBytes + (size_t) crank * slice * 128), &tmap_t,
-                                          bar_full(s), a * 64, t * B200M_TILE_N + (int) crank * slice, cmask);
+            if (p.pair) {
+                // CTA-pair mode: each CTA keeps its own 128 query rows and HALF of every train tile (its 128 rows);
+                // all transaction bytes are counted on the leader's barriers, which the leader's MMA thread waits on.
+                const uint32_t lead_a = map_to_cta(bar_a, 0);
+                if (crank == 0) mbar_arrive_expect_tx(bar_a, (uint32_t) (2 * p.ka * kATileBytes));
+                for (int a = 0; a < p.ka; ++a)
+                    tma_load_2d_2sm(smem_u32(sA + (size_t) a * kATileBytes), &tmap_q, lead_a, a * 64, q_row);
+                int it = 0;
+                for (int t = t0; t < t1; ++t) {
+                    for (int a = 0; a < p.ka; ++a, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
+                        mbar_wait(bar_empty(s), ph ^ 1u);
+                        if (crank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t) (2 * p.stage_bytes));
+                        tma_load_2d_2sm(smem_u32(sB + (size_t) s * p.stage_bytes), &tmap_t, map_to_cta(bar_full(s), 0), a * 64,
+                                        t * B200M_TILE_N + (int) crank * (B200M_TILE_N / 2));
+                    }
+                }
+            } else {
+                mbar_arrive_expect_tx(bar_a, (uint32_t) (p.ka * kATileBytes));
+                for (int a = 0; a < p.ka; ++a) tma_load_2d(smem_u32(sA + (size_t) a * kATileBytes), &tmap_q, bar_a, a * 64, q_row);
+                int it = 0;
+                for (int t = t0; t < t1; ++t) {
+                    for (int a = 0; a < p.ka; ++a, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
+                        mbar_wait(bar_empty(s), ph ^ 1u);
+                        mbar_arrive_expect_tx(bar_full(s), (uint32_t) kStageBytes);
+                        if (p.cluster == 1) {
+                            tma_load_2d(smem_u32(sB + (size_t) s * kStageBytes), &tmap_t, bar_full(s), a * 64, t * B200M_TILE_N);
+                        } else {
+                            // this CTA fetches its 1/cluster slice of the tile and multicasts it into every peer
+                            const int slice = B200M_TILE_N / p.cluster;
+                            tma_load_2d_mcast(smem_u32(sB + (size_t) s * kStageBytes + (size_t) crank * slice * 128), &tmap_t,
+                                              bar_full(s), a * 64, t * B200M_TILE_N + (int) crank * slice, cmask);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && (!p.pair || crank == 0)) {   // pair mode: the leader CTA issues for both SMs
             mbar_wait(bar_a, 0);
             tc_fence_after();
             int it = 0;
@@ -338,15 +401,23 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     mbar_wait(bar_full(s), ph);
                     tc_fence_after();
                     const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t) a * kATileBytes));
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t) s * kStageBytes));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t) s * p.stage_bytes));
                     const int nk = min(4, p.ksteps - 4 * a);
-                    for (int kk = 0; kk < nk; ++kk)   // +32 B per K=16 step inside the 128 B swizzle atom
-                        tc_mma_f16(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDesc,
-                                   (uint32_t) ((a | kk) != 0));
-                    if (p.cluster == 1) tc_commit(bar_empty(s));   // frees the B stage once these MMAs have read it
-                    else tc_commit_mcast(bar_empty(s), cmask);     // ... in every CTA that multicasts into it
+                    if (p.pair) {
+                        for (int kk = 0; kk < nk; ++kk)
+                            tc_mma_f16_2sm(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDescPair,
+                                           (uint32_t) ((a | kk) != 0));
+                        tc_commit_2sm_mcast(bar_empty(s), (uint16_t) 3);   // frees the stage in both CTAs
+                    } else {
+                        for (int kk = 0; kk < nk; ++kk)   // +32 B per K=16 step inside the 128 B swizzle atom
+                            tc_mma_f16(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDesc,
+                                       (uint32_t) ((a | kk) != 0));
+                        if (p.cluster == 1) tc_commit(bar_empty(s));   // frees the B stage once these MMAs have read it
+                        else tc_commit_mcast(bar_empty(s), cmask);     // ... in every CTA that multicasts into it
+                    }
                 }
-                tc_commit(bar_tfull(buf));            // accumulator complete
+                if (p.pair) tc_commit_2sm_mcast(bar_tfull(buf), (uint16_t) 3);   // accumulators complete in both CTAs
+                else tc_commit(bar_tfull(buf));
             }
         }
     } else {
@@ -385,7 +456,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tmem_ld_32x32b_x32(taddr + (uint32_t) (c * 32), ra);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) p.dump[row_in_tile * B200M_TILE_N + c * 32 + i] = __uint_as_float(ra[i]);
+                    for (int i = 0; i < 32; ++i)
+                        p.dump[((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + c * 32 + i] = __uint_as_float(ra[i]);
                 }
             }
             // two register buffers: the TMEM read of the next 32 columns is in flight while these are filtered;
@@ -401,7 +473,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
             }
             tc_fence_before();
-            mbar_arrive(bar_tempty(buf));
+            if (p.pair) mbar_arrive_cluster(map_to_cta(bar_tempty(buf), 0));   // the leader's MMA thread owns the accumulators
+            else mbar_arrive(bar_tempty(buf));
         }
         if (active && !p.dump) p.cand_cnt[list_row] = st.cnt;
     }
@@ -410,7 +483,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (p.pair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -501,21 +577,26 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
                   int *n_lists_out, int *cap_out, float *dump, size_t dump_t_tile) {
     Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
     const int n_qtiles = (int) ((n_rows + B200M_TILE_M - 1) / B200M_TILE_M);
-    // CTAs of a cluster walk the same train tiles, so each fetches 1/cluster of every tile from L2 and
-    // multicasts it to its peers: L2->SM traffic (the limiter of a 128-row tile) drops by the cluster size.
-    int cluster = ctx->tc_cluster > 0 ? ctx->tc_cluster : 2;
-    if (dump || n_qtiles < 2 * cluster) cluster = 1;
+    // Default = CTA-pair mode (cta_group::2): the two CTAs of a cluster form one M=256 MMA, each keeps its own 128
+    // query rows and HALF of every train tile, so per SM the B stream (TMA writes and MMA reads of shared memory, and
+    // L2->SM traffic) is halved -- a single-CTA M=128 x N=256 SS-mode MMA is shared-memory-bandwidth bound.
+    // B200M_TC_MODE=mcast / B200M_TC_CLUSTER select the cta_group::1 path with TMA multicast (kept for comparison).
+    int pair = ctx->tc_pair;
+    int cluster = pair ? 2 : (ctx->tc_cluster > 0 ? ctx->tc_cluster : 2);
+    if (!pair && (dump || n_qtiles < 2 * cluster)) cluster = 1;
     const CUtensorMap *mq = nullptr, *mt = nullptr;
     if (get_tmap(ctx, direction, true, 1, &mq)) return 1;
     if (get_tmap(ctx, 1 - direction, false, cluster, &mt)) return 1;
 
     TcParams p{};
     p.cluster = cluster;
+    p.pair = pair;
+    p.stage_bytes = pair ? kStageBytes / 2 : kStageBytes;
     p.ka = q.kp / 64;
     p.ksteps = (q.dim + B200M_AUG_COLS + 15) / 16;
     const size_t smem_limit = 227 * 1024;
     const size_t fixed = (size_t) p.ka * kATileBytes + 1024 /*alignment*/ + 256 /*barriers*/;
-    int stages = (int) ((smem_limit - fixed) / kStageBytes);
+    int stages = (int) ((smem_limit - fixed) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return b200m_fail_msg(ctx, "tc_candidates: descriptor too long for the shared-memory pipeline");
     p.stages = stages;
@@ -553,8 +634,8 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
     p.dump = dump;
     if (dump) p.tiles_per_split = (int) dump_t_tile;
-    const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * kStageBytes + 1024 + 256;
-    dim3 grid((unsigned) (dump ? 1 : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
+    const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + 256;
+    dim3 grid((unsigned) (dump ? cluster : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
     int kt = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : 16;
     int rc;
     switch (kt) {
