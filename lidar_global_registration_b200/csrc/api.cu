@@ -119,6 +119,7 @@ int b200m_create(b200m_ctx **out, int device) {
         int c = atoi(e);
         if (c == 1 || c == 2 || c == 4) { ctx->tc_cluster = c; ctx->tc_pair = 0; }
     }
+    if (const char *e = getenv("B200M_TC_DEBUG")) ctx->tc_debug = atoi(e);
     if (const char *e = getenv("B200M_TC_MODE")) {
         if (!strcmp(e, "mcast")) ctx->tc_pair = 0;
         if (!strcmp(e, "pair")) ctx->tc_pair = 1;

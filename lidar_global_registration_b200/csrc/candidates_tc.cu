@@ -31,10 +31,12 @@
 
 namespace {
 
-constexpr int kThreads = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kThreads = 320;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kEpiThreads = 256;         // two epilogue warps per scheduler: warp w drains TMEM lanes 32*(w%4).., columns 128*((w-2)/4)..
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
+constexpr int kTailBytes = 2048;         // barriers (<= 29 x 8 B) + TMEM slot + per-row shared state (3 x 128 x 4 B)
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
@@ -59,6 +61,8 @@ struct TcParams {
     int32_t *cand_idx;    // [n_lists][n_rows][cap]
     int32_t *cand_cnt;    // [n_lists][n_rows]
     float *dump;          // debug: raw accumulators of one tile [128][256]
+    int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
+                          // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -205,10 +209,13 @@ constexpr uint32_t kInstrDescPair = (1u << 4) | ((uint32_t) (B200M_TILE_N >> 3) 
 // ---- per-row selection state ------------------------------------------------------------------
 template <int KT>
 struct RowState {
-    float tk[KT];   // k smallest accumulator values so far, ascending
-    float thr;      // append threshold derived from tk[k-1]
-    int cnt;        // entries appended (may run past cap: overflow)
+    float tk[KT];   // k smallest accumulator values this thread has seen, ascending
+    float thr;      // effective append threshold: min(own threshold, the partner thread's published one)
+    float thr_own;  // threshold derived from this thread's tk[k-1]
     float na, eta, slop, gfac;
+    int *s_cnt;             // shared: entries appended to the row's list by both threads (may run past cap: overflow)
+    float *s_thr_own;       // shared: where this thread publishes thr_own
+    const float *s_thr_peer;   // shared: the partner thread's (other half of the columns, same row) published threshold
 };
 
 // Largest accumulator value an exact top-k member can have, given k accumulators <= T exist
@@ -248,8 +255,8 @@ __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, Ro
         const float s2a = (i & 2) ? s4[2] : s4[0], s2b = (i & 2) ? s4[3] : s4[1];
         float v = (i & 1) ? s2b : s2a;
         if (v < st.thr) {   // the threshold may have tightened since the mask was taken
-            if (st.cnt < cap) out[st.cnt] = col0 + i;
-            st.cnt++;
+            const int slot = atomicAdd(st.s_cnt, 1);
+            if (slot < cap) out[slot] = col0 + i;
 #pragma unroll
             for (int s = 0; s < KT; ++s) {
                 float lo = fminf(st.tk[s], v);
@@ -260,9 +267,11 @@ __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, Ro
 #pragma unroll
             for (int s = 0; s < KT - 1; ++s)
                 if (s == k - 1) T = st.tk[s];
-            st.thr = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
+            st.thr_own = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
+            st.thr = fminf(st.thr, st.thr_own);
         }
     }
+    *st.s_thr_own = st.thr_own;   // publish for the thread that filters the other half of this row's columns
 }
 
 template <int KT>
@@ -296,6 +305,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     auto bar_tfull = [&](int b) { return bar_base + 8u * (uint32_t) (2 * p.stages + 1 + b); };
     auto bar_tempty = [&](int b) { return bar_base + 8u * (uint32_t) (2 * p.stages + 3 + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 5);
+    int *s_cnt = reinterpret_cast<int *>(bars + 2 * p.stages + 6);        // [128] appended entries per row
+    float *s_thr = reinterpret_cast<float *>(s_cnt + B200M_TILE_M);       // [2][128] published thresholds per column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -313,7 +324,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_init(bar_a, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), p.pair ? 256u : 128u);   // pair mode: both CTAs' epilogues report to the leader
+            mbar_init(bar_tempty(b), p.pair ? 2u * kEpiThreads : (uint32_t) kEpiThreads);   // pair mode: both CTAs' epilogues report to the leader
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -356,6 +367,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         const int s = it % p.stages;
                         const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
                         mbar_wait(bar_empty(s), ph ^ 1u);
+                        if (p.debug_flags & 4) {   // timing experiment: no B traffic at all
+                            if (crank == 0) mbar_arrive(bar_full(s));
+                            continue;
+                        }
                         if (crank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t) (2 * p.stage_bytes));
                         tma_load_2d_2sm(smem_u32(sB + (size_t) s * p.stage_bytes), &tmap_t, map_to_cta(bar_full(s), 0), a * 64,
                                         t * B200M_TILE_N + (int) crank * (B200M_TILE_N / 2));
@@ -402,7 +417,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_after();
                     const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t) a * kATileBytes));
                     const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t) s * p.stage_bytes));
-                    const int nk = min(4, p.ksteps - 4 * a);
+                    const int nk = (p.debug_flags & 2) ? 0 : min(4, p.ksteps - 4 * a);
                     if (p.pair) {
                         for (int kk = 0; kk < nk; ++kk)
                             tc_mma_f16_2sm(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDescPair,
@@ -421,8 +436,11 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
         }
     } else {
-        // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4).. =====
+        // ===== epilogue: 8 warps.  Warp w owns TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of
+        // every tile, so each scheduler has two epilogue warps to hide each other's TMEM-load and dependency latency.
+        // The two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row_in_tile = quarter * 32 + lane;
         const int local = qtile * B200M_TILE_M + row_in_tile;
         const bool active = local < p.n_rows;
@@ -430,7 +448,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
         st.thr = active ? INFINITY : -INFINITY;
-        st.cnt = 0;
+        st.thr_own = st.thr;
+        st.s_cnt = s_cnt + row_in_tile;
+        st.s_thr_own = s_thr + half * B200M_TILE_M + row_in_tile;
+        st.s_thr_peer = s_thr + (half ^ 1) * B200M_TILE_M + row_in_tile;
+        if (half == 0) *st.s_cnt = 0;
+        *st.s_thr_own = st.thr;
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
             const float ab = sqrtf(na) + p.bmax;
@@ -439,6 +462,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             st.slop = ab * ab * 1.52587890625e-5f + 1e-6f;
             st.gfac = 1.f + 2.2f * (float) (p.dim + 4) * 5.9604644775390625e-8f;
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
         const size_t list_row = (size_t) split * p.n_rows + (active ? local : 0);
         int32_t *out = p.cand_idx + list_row * p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
@@ -448,35 +472,44 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t use = (uint32_t) (lt >> 1);
             mbar_wait(bar_tfull(buf), use & 1u);
             tc_fence_after();
-            const uint32_t taddr = lane_base + (uint32_t) (buf * B200M_TILE_N);
-            const int col_base = t * B200M_TILE_N;
+            const uint32_t taddr = lane_base + (uint32_t) (buf * B200M_TILE_N + half * (B200M_TILE_N / 2));
+            const int col_base = t * B200M_TILE_N + half * (B200M_TILE_N / 2);
+            if (p.debug_flags & 1) {
+                tc_fence_before();
+                if (p.pair) mbar_arrive_cluster(map_to_cta(bar_tempty(buf), 0));
+                else mbar_arrive(bar_tempty(buf));
+                continue;
+            }
             if (p.dump) {   // debug: raw accumulators of this tile
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     tmem_ld_32x32b_x32(taddr + (uint32_t) (c * 32), ra);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        p.dump[((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + c * 32 + i] = __uint_as_float(ra[i]);
+                        p.dump[((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * (B200M_TILE_N / 2) + c * 32 + i] =
+                            __uint_as_float(ra[i]);
                 }
             }
+            st.thr = fminf(st.thr, *st.s_thr_peer);   // pick up what the partner thread has learnt
             // two register buffers: the TMEM read of the next 32 columns is in flight while these are filtered;
             // the loop stays rolled so that its body (two copies of the chunk code) fits the instruction cache
             tmem_ld_32x32b_x32(taddr, ra);
 #pragma unroll 1
-            for (int c = 0; c < 8; c += 2) {
+            for (int c = 0; c < 4; c += 2) {
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
                 process_chunk<KT>(ra, col_base + c * 32, st, p.k, out, p.cap);
                 tmem_ld_wait();
-                if (c + 2 < 8) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
+                if (c + 2 < 4) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
                 process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
             }
             tc_fence_before();
             if (p.pair) mbar_arrive_cluster(map_to_cta(bar_tempty(buf), 0));   // the leader's MMA thread owns the accumulators
             else mbar_arrive(bar_tempty(buf));
         }
-        if (active && !p.dump) p.cand_cnt[list_row] = st.cnt;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // both threads of every row are done appending
+        if (half == 0 && active && !p.dump) p.cand_cnt[list_row] = *st.s_cnt;
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
@@ -556,7 +589,14 @@ int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT>, *mq, *mt, p));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT>, *mq, *mt, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // do not leave the launch error behind for the next call
+        return b200m_fail_msg(ctx, std::string("tc_candidates launch failed: ") + cudaGetErrorString(e) + " (grid " +
+                                       std::to_string(grid.x) + "x" + std::to_string(grid.y) + ", cluster " +
+                                       std::to_string(p.cluster) + ", pair " + std::to_string(p.pair) + ", smem " +
+                                       std::to_string(smem) + ", stages " + std::to_string(p.stages) + ")");
+    }
     return 0;
 }
 
@@ -583,7 +623,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // B200M_TC_MODE=mcast / B200M_TC_CLUSTER select the cta_group::1 path with TMA multicast (kept for comparison).
     int pair = ctx->tc_pair;
     int cluster = pair ? 2 : (ctx->tc_cluster > 0 ? ctx->tc_cluster : 2);
-    if (!pair && (dump || n_qtiles < 2 * cluster)) cluster = 1;
+    if (!pair && (cluster < 2 || dump)) cluster = 2;   // the kernel contains cta_group::2 code: clusters must be even-sized
     const CUtensorMap *mq = nullptr, *mt = nullptr;
     if (get_tmap(ctx, direction, true, 1, &mq)) return 1;
     if (get_tmap(ctx, 1 - direction, false, cluster, &mt)) return 1;
@@ -595,9 +635,11 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.ka = q.kp / 64;
     p.ksteps = (q.dim + B200M_AUG_COLS + 15) / 16;
     const size_t smem_limit = 227 * 1024;
-    const size_t fixed = (size_t) p.ka * kATileBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+    const size_t fixed = (size_t) p.ka * kATileBytes + 1024 /*alignment*/ + kTailBytes /*barriers + per-row shared state*/;
     int stages = (int) ((smem_limit - fixed) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
+    if ((ctx->tc_debug & 8) && stages > 4) stages = 4;     // timing experiment: shallow ring
+    if ((ctx->tc_debug & 16) && stages > 6) stages = 6;
     if (stages < 2) return b200m_fail_msg(ctx, "tc_candidates: descriptor too long for the shared-memory pipeline");
     p.stages = stages;
     p.n_ttiles = (int) (t.n_pad / B200M_TILE_N);
@@ -633,8 +675,9 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.cand_idx = ctx->ws_cand_idx.as<int32_t>();
     p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
     p.dump = dump;
+    p.debug_flags = ctx->tc_debug;
     if (dump) p.tiles_per_split = (int) dump_t_tile;
-    const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + 256;
+    const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + kTailBytes;
     dim3 grid((unsigned) (dump ? cluster : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
     int kt = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : 16;
     int rc;

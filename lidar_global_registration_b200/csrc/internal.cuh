@@ -62,6 +62,7 @@ struct b200m_ctx {
     bool totals_init = false;
     void *tmap_cache = nullptr;
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
+    int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
     int tc_pair = 1;       // 1 = CTA-pair (cta_group::2) candidate kernel; 0 = cta_group::1 + multicast (B200M_TC_MODE=mcast)
     bool profiling = false;
     b200m_stats stats{};

@@ -293,12 +293,15 @@ def test_properties_at_bench_scale():
     _same((idx[rows], dist[rows], cnt[rows]), eo)
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("mode", ["pair", "mcast2", "mcast4"])
 @pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 3000, 9000, 2), ("shot", 1100, 2600, 5)])
-def test_multicast_cluster_sizes(monkeypatch, cluster, desc, nq, nt, k):
-    """The train tile is shared across a thread-block cluster by TMA multicast; every cluster size gives the
-    same (oracle-exact) lists."""
-    monkeypatch.setenv("B200M_TC_CLUSTER", str(cluster))
+def test_candidate_kernel_modes(monkeypatch, mode, desc, nq, nt, k):
+    """The candidate kernel's two operand-sharing schemes -- CTA pair (tcgen05 cta_group::2, default) and
+    cta_group::1 with TMA multicast across a cluster of 2 or 4 -- give the same (oracle-exact) lists."""
+    if mode == "pair":
+        monkeypatch.setenv("B200M_TC_MODE", "pair")
+    else:
+        monkeypatch.setenv("B200M_TC_CLUSTER", mode[-1])
     src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
     with M.Context(0) as ctx:
         ctx.upload(0, src, dim)
