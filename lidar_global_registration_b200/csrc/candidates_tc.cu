@@ -31,8 +31,7 @@
 
 namespace {
 
-constexpr int kThreads = 320;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
-constexpr int kEpiThreads = 256;         // two epilogue warps per scheduler: warp w drains TMEM lanes 32*(w%4).., columns 128*((w-2)/4)..
+// threads per CTA = 64 + 128 * EH: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, then 4 * EH epilogue warps
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
@@ -62,7 +61,8 @@ struct TcParams {
     int32_t *cand_cnt;    // [n_lists][n_rows]
     float *dump;          // debug: raw accumulators of one tile [128][256]
     int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
-                          // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages
+                          // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages, 32 = epilogue only
+                          // drains TMEM (no filtering), 64 / 128 = force EH = 1 / 2
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -176,6 +176,23 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+template <bool PAIR>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (PAIR) tc_mma_f16_2sm(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else tc_mma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -214,8 +231,8 @@ struct RowState {
     float thr_own;  // threshold derived from this thread's tk[k-1]
     float na, eta, slop, gfac;
     int *s_cnt;             // shared: entries appended to the row's list by both threads (may run past cap: overflow)
-    float *s_thr_own;       // shared: where this thread publishes thr_own
-    const float *s_thr_peer;   // shared: the partner thread's (other half of the columns, same row) published threshold
+    float *s_thr_own;       // shared: where this thread publishes thr_own (EH = 2: read by the thread that filters
+                            // the other half of this row's columns)
 };
 
 // Largest accumulator value an exact top-k member can have, given k accumulators <= T exist
@@ -235,7 +252,7 @@ __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(
 // Rare path, kept compact (it is instantiated twice inside the tile loop and the loop has to stay in the
 // instruction cache): bit mask of the columns under the threshold, then one iteration per set bit with the
 // value fetched through a select tree (no dynamic register indexing, no local memory).
-template <int KT>
+template <int KT, int EH>
 __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
                                            int32_t *__restrict__ out, int cap) {
     const float thr0 = st.thr;
@@ -271,10 +288,10 @@ __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, Ro
             st.thr = fminf(st.thr, st.thr_own);
         }
     }
-    *st.s_thr_own = st.thr_own;   // publish for the thread that filters the other half of this row's columns
+    if (EH == 2) *st.s_thr_own = st.thr_own;   // publish for the thread that filters the other half of this row's columns
 }
 
-template <int KT>
+template <int KT, int EH>
 __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
                                               int32_t *__restrict__ out, int cap) {
     // fast path: 32 accumulators -> their minimum in 16 three-input min ops, one compare
@@ -284,53 +301,62 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0,
     const float a9 = min3(F(27), F(28), F(29)), a10 = fminf(F(30), F(31));
     const float b0 = min3(a0, a1, a2), b1 = min3(a3, a4, a5), b2 = min3(a6, a7, a8), b3 = min3(a9, a10, b0);
     const float m = min3(b1, b2, b3);
-    if (m < st.thr) slow_chunk<KT>(r, col0, st, k, out, cap);   // inactive rows carry thr = -inf
+    if (m < st.thr) slow_chunk<KT, EH>(r, col0, st, k, out, cap);   // inactive rows carry thr = -inf
 }
 #undef F
 
-template <int KT>
-__global__ void __launch_bounds__(kThreads, 1)
+// PAIR: CTA-pair mode (tcgen05.mma cta_group::2, M = 256 across two SMs, each CTA holds half of every train tile).
+// EH:   epilogue column halves.  1 = four epilogue warps, a thread owns a whole row; 2 = eight warps (two per
+//       scheduler), warp w drains TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of every tile.
+template <int KT, bool PAIR, int EH>
+__global__ void __launch_bounds__(64 + 128 * EH, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
                      const TcParams p) {
+    constexpr int kEpiWarps = 4 * EH;
+    constexpr int kEpiThreads = 128 * EH;
+    constexpr int kColsPerWarp = B200M_TILE_N / EH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + (size_t) p.ka * kATileBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t) p.stages * p.stage_bytes);
     // barrier map: [0..S) full, [S..2S) empty, 2S a_full, 2S+1.. tmem_full[2], 2S+3.. tmem_empty[2]
-    const uint32_t bar_base = smem_u32(bars);
-    auto bar_full = [&](int s) { return bar_base + 8u * (uint32_t) s; };
-    auto bar_empty = [&](int s) { return bar_base + 8u * (uint32_t) (p.stages + s); };
-    const uint32_t bar_a = bar_base + 8u * (uint32_t) (2 * p.stages);
-    auto bar_tfull = [&](int b) { return bar_base + 8u * (uint32_t) (2 * p.stages + 1 + b); };
-    auto bar_tempty = [&](int b) { return bar_base + 8u * (uint32_t) (2 * p.stages + 3 + b); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 5);
-    int *s_cnt = reinterpret_cast<int *>(bars + 2 * p.stages + 6);        // [128] appended entries per row
+    const int stages = p.stages;
+    const uint32_t bar_full0 = smem_u32(bars);
+    const uint32_t bar_empty0 = bar_full0 + 8u * (uint32_t) stages;
+    const uint32_t bar_a = bar_full0 + 8u * (uint32_t) (2 * stages);
+    const uint32_t bar_tfull0 = bar_a + 8u;
+    const uint32_t bar_tempty0 = bar_a + 24u;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * stages + 5);
+    int *s_cnt = reinterpret_cast<int *>(bars + 2 * stages + 6);          // [128] appended entries per row
     float *s_thr = reinterpret_cast<float *>(s_cnt + B200M_TILE_M);       // [2][128] published thresholds per column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
     const int t0 = p.dump ? p.tiles_per_split : split * p.tiles_per_split;   // dump mode: tiles_per_split holds the tile id
     const int t1 = p.dump ? t0 + 1 : min(p.n_ttiles, t0 + p.tiles_per_split);
+    const int ka = p.ka;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
-        for (int s = 0; s < p.stages; ++s) {
-            mbar_init(bar_full(s), 1);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(bar_full0 + 8u * s, 1);
             // multicast mode: every CTA of the cluster must have read the stage; pair mode: one commit frees it
-            mbar_init(bar_empty(s), p.pair ? 1u : (uint32_t) p.cluster);
+            mbar_init(bar_empty0 + 8u * s, PAIR ? 1u : (uint32_t) p.cluster);
         }
         mbar_init(bar_a, 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), p.pair ? 2u * kEpiThreads : (uint32_t) kEpiThreads);   // pair mode: both CTAs' epilogues report to the leader
+            mbar_init(bar_tfull0 + 8u * b, 1);
+            // one arrival per epilogue WARP (a per-thread count serialises hundreds of barrier updates per tile);
+            // pair mode: both CTAs' epilogue warps report to the leader, whose MMA thread owns the accumulators
+            mbar_init(bar_tempty0 + 8u * b, PAIR ? 2u * kEpiWarps : (uint32_t) kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        if (p.pair) {   // the same warp of both CTAs of the pair allocates
+        if (PAIR) {   // the same warp of both CTAs of the pair allocates
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                          "r"(kTmemCols)
                          : "memory");
@@ -351,94 +377,119 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint16_t cmask = (uint16_t) ((1u << p.cluster) - 1u);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            const int q_row = p.q_row0 + qtile * B200M_TILE_M;
-            if (p.pair) {
-                // CTA-pair mode: each CTA keeps its own 128 query rows and HALF of every train tile (its 128 rows);
-                // all transaction bytes are counted on the leader's barriers, which the leader's MMA thread waits on.
-                const uint32_t lead_a = map_to_cta(bar_a, 0);
-                if (crank == 0) mbar_arrive_expect_tx(bar_a, (uint32_t) (2 * p.ka * kATileBytes));
-                for (int a = 0; a < p.ka; ++a)
-                    tma_load_2d_2sm(smem_u32(sA + (size_t) a * kATileBytes), &tmap_q, lead_a, a * 64, q_row);
-                int it = 0;
-                for (int t = t0; t < t1; ++t) {
-                    for (int a = 0; a < p.ka; ++a, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
-                        mbar_wait(bar_empty(s), ph ^ 1u);
+        // ===== TMA producer: the whole warp walks the ring (warp-uniform control flow keeps addresses and barrier
+        // handles in uniform registers), one elected lane issues =====
+        const int q_row = p.q_row0 + qtile * B200M_TILE_M;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        if (PAIR) {
+            // CTA-pair mode: each CTA keeps its own 128 query rows and HALF of every train tile (its 128 rows);
+            // all transaction bytes are counted on the leader's barriers, which the leader's MMA thread waits on.
+            const uint32_t lead_a = map_to_cta(bar_a, 0);
+            const uint32_t lead_full0 = map_to_cta(bar_full0, 0);
+            const int row_off = (int) crank * (B200M_TILE_N / 2);
+            if (elect_one()) {
+                if (crank == 0) mbar_arrive_expect_tx(bar_a, (uint32_t) (2 * ka * kATileBytes));
+                for (int a = 0; a < ka; ++a) tma_load_2d_2sm(sA_u + (uint32_t) (a * kATileBytes), &tmap_q, lead_a, a * 64, q_row);
+            }
+            __syncwarp();
+            uint32_t s = 0, ph = 1;
+            for (int t = t0; t < t1; ++t) {
+                for (int a = 0; a < ka; ++a) {
+                    mbar_wait(bar_empty0 + 8u * s, ph);
+                    if (elect_one()) {
                         if (p.debug_flags & 4) {   // timing experiment: no B traffic at all
-                            if (crank == 0) mbar_arrive(bar_full(s));
-                            continue;
+                            if (crank == 0) mbar_arrive(bar_full0 + 8u * s);
+                        } else {
+                            if (crank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, (uint32_t) (2 * p.stage_bytes));
+                            tma_load_2d_2sm(sB_u + s * (uint32_t) p.stage_bytes, &tmap_t, lead_full0 + 8u * s, a * 64,
+                                            t * B200M_TILE_N + row_off);
                         }
-                        if (crank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t) (2 * p.stage_bytes));
-                        tma_load_2d_2sm(smem_u32(sB + (size_t) s * p.stage_bytes), &tmap_t, map_to_cta(bar_full(s), 0), a * 64,
-                                        t * B200M_TILE_N + (int) crank * (B200M_TILE_N / 2));
                     }
+                    __syncwarp();
+                    if (++s == (uint32_t) stages) { s = 0; ph ^= 1u; }
                 }
-            } else {
-                mbar_arrive_expect_tx(bar_a, (uint32_t) (p.ka * kATileBytes));
-                for (int a = 0; a < p.ka; ++a) tma_load_2d(smem_u32(sA + (size_t) a * kATileBytes), &tmap_q, bar_a, a * 64, q_row);
-                int it = 0;
-                for (int t = t0; t < t1; ++t) {
-                    for (int a = 0; a < p.ka; ++a, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
-                        mbar_wait(bar_empty(s), ph ^ 1u);
-                        mbar_arrive_expect_tx(bar_full(s), (uint32_t) kStageBytes);
+            }
+        } else {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_a, (uint32_t) (ka * kATileBytes));
+                for (int a = 0; a < ka; ++a) tma_load_2d(sA_u + (uint32_t) (a * kATileBytes), &tmap_q, bar_a, a * 64, q_row);
+            }
+            __syncwarp();
+            const int slice = B200M_TILE_N / p.cluster;
+            uint32_t s = 0, ph = 1;
+            for (int t = t0; t < t1; ++t) {
+                for (int a = 0; a < ka; ++a) {
+                    mbar_wait(bar_empty0 + 8u * s, ph);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_full0 + 8u * s, (uint32_t) kStageBytes);
                         if (p.cluster == 1) {
-                            tma_load_2d(smem_u32(sB + (size_t) s * kStageBytes), &tmap_t, bar_full(s), a * 64, t * B200M_TILE_N);
+                            tma_load_2d(sB_u + s * (uint32_t) kStageBytes, &tmap_t, bar_full0 + 8u * s, a * 64, t * B200M_TILE_N);
                         } else {
                             // this CTA fetches its 1/cluster slice of the tile and multicasts it into every peer
-                            const int slice = B200M_TILE_N / p.cluster;
-                            tma_load_2d_mcast(smem_u32(sB + (size_t) s * kStageBytes + (size_t) crank * slice * 128), &tmap_t,
-                                              bar_full(s), a * 64, t * B200M_TILE_N + (int) crank * slice, cmask);
+                            tma_load_2d_mcast(sB_u + s * (uint32_t) kStageBytes + crank * (uint32_t) (slice * 128), &tmap_t,
+                                              bar_full0 + 8u * s, a * 64, t * B200M_TILE_N + (int) crank * slice, cmask);
                         }
                     }
+                    __syncwarp();
+                    if (++s == (uint32_t) stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && (!p.pair || crank == 0)) {   // pair mode: the leader CTA issues for both SMs
+        // ===== MMA issuer.  One MMA (K = 16) is 128 tensor-pipe cycles, so the issue loop has to stay far below that
+        // per instruction: warp-uniform control flow, ring position kept as counters (no divisions), descriptors
+        // advanced by adding to their low word, the four K steps of an atom unrolled. =====
+        if (!PAIR || crank == 0) {   // pair mode: the leader CTA issues for both SMs
             mbar_wait(bar_a, 0);
             tc_fence_after();
-            int it = 0;
+            const uint64_t desc_a0 = make_kmajor_sw128_desc(smem_u32(sA));
+            const uint64_t desc_b0 = make_kmajor_sw128_desc(smem_u32(sB));
+            const uint32_t a_step = (uint32_t) (kATileBytes >> 4), b_step = (uint32_t) (p.stage_bytes >> 4);
+            const int nk_last = (p.debug_flags & 2) ? 0 : p.ksteps - 4 * (ka - 1);   // K steps of the last atom (1..4)
+            const bool no_mma = (p.debug_flags & 2) != 0;
+            constexpr uint32_t idesc = PAIR ? kInstrDescPair : kInstrDesc;
+            uint32_t s = 0, ph = 0;
             for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
-                const int buf = lt & 1;
-                const uint32_t use = (uint32_t) (lt >> 1);
-                mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u);
+                const uint32_t buf = (uint32_t) lt & 1u;
+                mbar_wait(bar_tempty0 + 8u * buf, (((uint32_t) lt >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t) (buf * B200M_TILE_N);
-                for (int a = 0; a < p.ka; ++a, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t) (it / p.stages) & 1u;
-                    mbar_wait(bar_full(s), ph);
+                const uint32_t tmem_d = tmem_base + buf * (uint32_t) B200M_TILE_N;
+                for (int a = 0; a < ka; ++a) {
+                    mbar_wait(bar_full0 + 8u * s, ph);
                     tc_fence_after();
-                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t) a * kATileBytes));
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t) s * p.stage_bytes));
-                    const int nk = (p.debug_flags & 2) ? 0 : min(4, p.ksteps - 4 * a);
-                    if (p.pair) {
-                        for (int kk = 0; kk < nk; ++kk)
-                            tc_mma_f16_2sm(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDescPair,
-                                           (uint32_t) ((a | kk) != 0));
-                        tc_commit_2sm_mcast(bar_empty(s), (uint16_t) 3);   // frees the stage in both CTAs
-                    } else {
-                        for (int kk = 0; kk < nk; ++kk)   // +32 B per K=16 step inside the 128 B swizzle atom
-                            tc_mma_f16(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), kInstrDesc,
-                                       (uint32_t) ((a | kk) != 0));
-                        if (p.cluster == 1) tc_commit(bar_empty(s));   // frees the B stage once these MMAs have read it
-                        else tc_commit_mcast(bar_empty(s), cmask);     // ... in every CTA that multicasts into it
+                    if (elect_one()) {
+                        const uint64_t da = desc_a0 + (uint64_t) ((uint32_t) a * a_step);
+                        const uint64_t db = desc_b0 + (uint64_t) (s * b_step);
+                        if (a + 1 < ka) {
+                            if (!no_mma) {
+                                // +32 B (2 descriptor units) per K = 16 step inside the 128 B swizzle atom
+                                tc_mma<PAIR>(tmem_d, da, db, idesc, (uint32_t) (a != 0));
+                                tc_mma<PAIR>(tmem_d, da + 2, db + 2, idesc, 1u);
+                                tc_mma<PAIR>(tmem_d, da + 4, db + 4, idesc, 1u);
+                                tc_mma<PAIR>(tmem_d, da + 6, db + 6, idesc, 1u);
+                            }
+                        } else {
+                            for (int kk = 0; kk < nk_last; ++kk)
+                                tc_mma<PAIR>(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), idesc, (uint32_t) ((a | kk) != 0));
+                        }
+                        // frees the B stage once these MMAs have read it (in every CTA that writes into it)
+                        if (PAIR) tc_commit_2sm_mcast(bar_empty0 + 8u * s, (uint16_t) 3);
+                        else if (p.cluster == 1) tc_commit(bar_empty0 + 8u * s);
+                        else tc_commit_mcast(bar_empty0 + 8u * s, cmask);
                     }
+                    __syncwarp();
+                    if (++s == (uint32_t) stages) { s = 0; ph ^= 1u; }
                 }
-                if (p.pair) tc_commit_2sm_mcast(bar_tfull(buf), (uint16_t) 3);   // accumulators complete in both CTAs
-                else tc_commit(bar_tfull(buf));
+                if (elect_one()) {   // accumulators of this tile complete (in both CTAs of a pair)
+                    if (PAIR) tc_commit_2sm_mcast(bar_tfull0 + 8u * buf, (uint16_t) 3);
+                    else tc_commit(bar_tfull0 + 8u * buf);
+                }
+                __syncwarp();
             }
         }
     } else {
-        // ===== epilogue: 8 warps.  Warp w owns TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of
-        // every tile, so each scheduler has two epilogue warps to hide each other's TMEM-load and dependency latency.
-        // The two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
+        // ===== epilogue: a thread owns one TMEM lane (query row) and kColsPerWarp columns of every tile.  With EH = 2
+        // the two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row_in_tile = quarter * 32 + lane;
@@ -451,7 +502,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         st.thr_own = st.thr;
         st.s_cnt = s_cnt + row_in_tile;
         st.s_thr_own = s_thr + half * B200M_TILE_M + row_in_tile;
-        st.s_thr_peer = s_thr + (half ^ 1) * B200M_TILE_M + row_in_tile;
+        const float *s_thr_peer = s_thr + (half ^ 1) * B200M_TILE_M + row_in_tile;
         if (half == 0) *st.s_cnt = 0;
         *st.s_thr_own = st.thr;
         {
@@ -465,48 +516,47 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
         const size_t list_row = (size_t) split * p.n_rows + (active ? local : 0);
         int32_t *out = p.cand_idx + list_row * p.cap;
-        const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
+        const uint32_t tempty_dst0 = PAIR ? map_to_cta(bar_tempty0, 0) : bar_tempty0;
         uint32_t ra[32], rb[32];
         for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
-            const int buf = lt & 1;
-            const uint32_t use = (uint32_t) (lt >> 1);
-            mbar_wait(bar_tfull(buf), use & 1u);
+            const uint32_t buf = (uint32_t) lt & 1u;
+            mbar_wait(bar_tfull0 + 8u * buf, ((uint32_t) lt >> 1) & 1u);
             tc_fence_after();
-            const uint32_t taddr = lane_base + (uint32_t) (buf * B200M_TILE_N + half * (B200M_TILE_N / 2));
-            const int col_base = t * B200M_TILE_N + half * (B200M_TILE_N / 2);
-            if (p.debug_flags & 1) {
-                tc_fence_before();
-                if (p.pair) mbar_arrive_cluster(map_to_cta(bar_tempty(buf), 0));
-                else mbar_arrive(bar_tempty(buf));
-                continue;
-            }
-            if (p.dump) {   // debug: raw accumulators of this tile
+            const uint32_t taddr = lane_base + buf * (uint32_t) B200M_TILE_N;
+            const int col_base = t * B200M_TILE_N + half * kColsPerWarp;
+            if (!(p.debug_flags & 1)) {
+                if (p.dump) {   // debug: raw accumulators of this tile
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld_32x32b_x32(taddr + (uint32_t) (c * 32), ra);
-                    tmem_ld_wait();
+                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                        tmem_ld_32x32b_x32(taddr + (uint32_t) (c * 32), ra);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        p.dump[((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * (B200M_TILE_N / 2) + c * 32 + i] =
-                            __uint_as_float(ra[i]);
+                        for (int i = 0; i < 32; ++i)
+                            p.dump[((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * kColsPerWarp + c * 32 + i] =
+                                __uint_as_float(ra[i]);
+                    }
+                }
+                if (EH == 2) st.thr = fminf(st.thr, *s_thr_peer);   // pick up what the partner thread has learnt
+                // two register buffers: the TMEM read of the next 32 columns is in flight while these are filtered;
+                // the loop stays rolled so that its body (two copies of the chunk code) fits the instruction cache
+                tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp / 32; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
+                    if (!(p.debug_flags & 32)) process_chunk<KT, EH>(ra, col_base + c * 32, st, p.k, out, p.cap);
+                    tmem_ld_wait();
+                    if (c + 2 < kColsPerWarp / 32) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
+                    if (!(p.debug_flags & 32)) process_chunk<KT, EH>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
                 }
             }
-            st.thr = fminf(st.thr, *st.s_thr_peer);   // pick up what the partner thread has learnt
-            // two register buffers: the TMEM read of the next 32 columns is in flight while these are filtered;
-            // the loop stays rolled so that its body (two copies of the chunk code) fits the instruction cache
-            tmem_ld_32x32b_x32(taddr, ra);
-#pragma unroll 1
-            for (int c = 0; c < 4; c += 2) {
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
-                process_chunk<KT>(ra, col_base + c * 32, st, p.k, out, p.cap);
-                tmem_ld_wait();
-                if (c + 2 < 4) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
-                process_chunk<KT>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
-            }
             tc_fence_before();
-            if (p.pair) mbar_arrive_cluster(map_to_cta(bar_tempty(buf), 0));   // the leader's MMA thread owns the accumulators
-            else mbar_arrive(bar_tempty(buf));
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(tempty_dst0 + 8u * buf);
+                else mbar_arrive(bar_tempty0 + 8u * buf);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // both threads of every row are done appending
         if (half == 0 && active && !p.dump) p.cand_cnt[list_row] = *st.s_cnt;
@@ -516,7 +566,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        if (p.pair)
+        if (PAIR)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -574,12 +624,12 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
     return 0;
 }
 
-template <int KT>
+template <int KT, bool PAIR, int EH>
 int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
-    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.blockDim = dim3(64 + 128 * EH, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -589,7 +639,7 @@ int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT>, *mq, *mt, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH>, *mq, *mt, p);
     if (e != cudaSuccess) {
         cudaGetLastError();   // do not leave the launch error behind for the next call
         return b200m_fail_msg(ctx, std::string("tc_candidates launch failed: ") + cudaGetErrorString(e) + " (grid " +
@@ -623,7 +673,6 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // B200M_TC_MODE=mcast / B200M_TC_CLUSTER select the cta_group::1 path with TMA multicast (kept for comparison).
     int pair = ctx->tc_pair;
     int cluster = pair ? 2 : (ctx->tc_cluster > 0 ? ctx->tc_cluster : 2);
-    if (!pair && (cluster < 2 || dump)) cluster = 2;   // the kernel contains cta_group::2 code: clusters must be even-sized
     const CUtensorMap *mq = nullptr, *mt = nullptr;
     if (get_tmap(ctx, direction, true, 1, &mq)) return 1;
     if (get_tmap(ctx, 1 - direction, false, cluster, &mt)) return 1;
@@ -680,14 +729,26 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + kTailBytes;
     dim3 grid((unsigned) (dump ? cluster : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
     int kt = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : 16;
+    // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
+    // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and a thread that owns its whole row
+    // keeps the tighter threshold (fewer candidates to re-rank).
+    int eh = p.ka <= 2 ? 2 : 1;
+    if (ctx->tc_debug & 64) eh = 1;
+    if (ctx->tc_debug & 128) eh = 2;
     int rc;
+#define B200M_TC_CASE(KT_)                                                                    \
+    rc = pair ? (eh == 2 ? launch_tc<KT_, true, 2>(ctx, mq, mt, p, grid, smem)                \
+                         : launch_tc<KT_, true, 1>(ctx, mq, mt, p, grid, smem))               \
+              : (eh == 2 ? launch_tc<KT_, false, 2>(ctx, mq, mt, p, grid, smem)               \
+                         : launch_tc<KT_, false, 1>(ctx, mq, mt, p, grid, smem))
     switch (kt) {
-        case 1: rc = launch_tc<1>(ctx, mq, mt, p, grid, smem); break;
-        case 2: rc = launch_tc<2>(ctx, mq, mt, p, grid, smem); break;
-        case 4: rc = launch_tc<4>(ctx, mq, mt, p, grid, smem); break;
-        case 8: rc = launch_tc<8>(ctx, mq, mt, p, grid, smem); break;
-        default: rc = launch_tc<16>(ctx, mq, mt, p, grid, smem); break;
+        case 1: B200M_TC_CASE(1); break;
+        case 2: B200M_TC_CASE(2); break;
+        case 4: B200M_TC_CASE(4); break;
+        case 8: B200M_TC_CASE(8); break;
+        default: B200M_TC_CASE(16); break;
     }
+#undef B200M_TC_CASE
     if (rc) return rc;
     ctx->stats.launches += 1;
     ctx->stats.candidate_launches += 1;

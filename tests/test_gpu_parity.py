@@ -293,15 +293,18 @@ def test_properties_at_bench_scale():
     _same((idx[rows], dist[rows], cnt[rows]), eo)
 
 
-@pytest.mark.parametrize("mode", ["pair", "mcast2", "mcast4"])
+@pytest.mark.parametrize("epi", ["eh1", "eh2"])
+@pytest.mark.parametrize("mode", ["pair", "mcast1", "mcast2", "mcast4"])
 @pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 3000, 9000, 2), ("shot", 1100, 2600, 5)])
-def test_candidate_kernel_modes(monkeypatch, mode, desc, nq, nt, k):
-    """The candidate kernel's two operand-sharing schemes -- CTA pair (tcgen05 cta_group::2, default) and
-    cta_group::1 with TMA multicast across a cluster of 2 or 4 -- give the same (oracle-exact) lists."""
+def test_candidate_kernel_modes(monkeypatch, mode, epi, desc, nq, nt, k):
+    """The candidate kernel's operand-sharing schemes -- CTA pair (tcgen05 cta_group::2, default) and cta_group::1
+    alone or with TMA multicast across a cluster of 2 or 4 -- and its two epilogue shapes (4 warps, a thread owns a
+    row; 8 warps, two threads share a row) all give the same (oracle-exact) lists."""
     if mode == "pair":
         monkeypatch.setenv("B200M_TC_MODE", "pair")
     else:
         monkeypatch.setenv("B200M_TC_CLUSTER", mode[-1])
+    monkeypatch.setenv("B200M_TC_DEBUG", "64" if epi == "eh1" else "128")   # 64 / 128 only force the epilogue shape
     src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
     with M.Context(0) as ctx:
         ctx.upload(0, src, dim)
