@@ -154,32 +154,37 @@ __device__ __forceinline__ void tc_commit_2sm_mcast(uint32_t bar, uint16_t cta_m
                  ::"r"(bar), "h"(cta_mask)
                  : "memory");
 }
+// One MMA, issued only when `enable` is set (a predicated instruction instead of a branch keeps the issue loop
+// straight-line); `accumulate` = 0 overwrites the accumulator.
 __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                               uint32_t accumulate) {
+                                               uint32_t accumulate, uint32_t enable) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
         : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                           uint32_t accumulate) {
+                                           uint32_t accumulate, uint32_t enable) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
         : "memory");
 }
 template <bool PAIR>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    if (PAIR) tc_mma_f16_2sm(tmem_d, desc_a, desc_b, idesc, accumulate);
-    else tc_mma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t enable) {
+    if (PAIR) tc_mma_f16_2sm(tmem_d, desc_a, desc_b, idesc, accumulate, enable);
+    else tc_mma_f16(tmem_d, desc_a, desc_b, idesc, accumulate, enable);
 }
 // true in exactly one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
@@ -224,15 +229,34 @@ constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t) (B200M_TILE_N >> 3) << 1
 constexpr uint32_t kInstrDescPair = (1u << 4) | ((uint32_t) (B200M_TILE_N >> 3) << 17) | ((uint32_t) ((2 * B200M_TILE_M) >> 4) << 24);
 
 // ---- per-row selection state ------------------------------------------------------------------
+// Shared-memory words are addressed through the shared window (32-bit addresses, ld/st/atom.shared) -- generic
+// pointers would cost an address conversion per access inside the tile loop.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+
 template <int KT>
 struct RowState {
-    float tk[KT];   // k smallest accumulator values this thread has seen, ascending
+    float tk[KT];   // k smallest accumulator values this thread has seen (of distinct columns), ascending
     float thr;      // effective append threshold: min(own threshold, the partner thread's published one)
-    float thr_own;  // threshold derived from this thread's tk[k-1]
     float na, eta, slop, gfac;
-    int *s_cnt;             // shared: entries appended to the row's list by both threads (may run past cap: overflow)
-    float *s_thr_own;       // shared: where this thread publishes thr_own (EH = 2: read by the thread that filters
-                            // the other half of this row's columns)
+    uint32_t s_cnt;       // shared: entries appended to the row's list by both threads (may run past cap: overflow)
+    uint32_t s_thr_own;   // shared: where this thread publishes its own threshold (EH = 2: read by the thread that
+                          // filters the other half of this row's columns)
 };
 
 // Largest accumulator value an exact top-k member can have, given k accumulators <= T exist
@@ -248,13 +272,38 @@ __device__ __forceinline__ float cand_threshold(float T, float na, float eta, fl
 
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }   // one FMNMX3
 
-#define F(i) __uint_as_float(r[i])
-// Rare path, kept compact (it is instantiated twice inside the tile loop and the loop has to stay in the
-// instruction cache): bit mask of the columns under the threshold, then one iteration per set bit with the
-// value fetched through a select tree (no dynamic register indexing, no local memory).
+template <int KT>
+__device__ __forceinline__ float kth_smallest(const RowState<KT> &st, int k) {
+    float T = st.tk[KT - 1];
+#pragma unroll
+    for (int s = 0; s < KT - 1; ++s)
+        if (s == k - 1) T = st.tk[s];
+    return T;
+}
+// branch-free sorted insertion of one value (2 * KT min/max ops)
+template <int KT>
+__device__ __forceinline__ void tk_insert(RowState<KT> &st, float v) {
+#pragma unroll
+    for (int s = 0; s < KT; ++s) {
+        const float lo = fminf(st.tk[s], v);
+        v = fmaxf(st.tk[s], v);
+        st.tk[s] = lo;
+    }
+}
 template <int KT, int EH>
-__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
-                                           int32_t *__restrict__ out, int cap) {
+__device__ __forceinline__ void retighten(RowState<KT> &st, int k) {
+    const float thr_own = cand_threshold(kth_smallest<KT>(st, k), st.na, st.eta, st.slop, st.gfac);
+    st.thr = fminf(st.thr, thr_own);
+    if (EH == 2) sts_f32(st.s_thr_own, thr_own);
+}
+
+#define F(i) __uint_as_float(r[i])
+// Warm-up path (a row that has not yet seen k columns, i.e. its first tile): every column under the running
+// threshold is appended and inserted one at a time, the threshold tightening as soon as k values are known.  The
+// value is fetched through a select tree (no dynamic register indexing, no local memory).
+template <int KT, int EH>
+__device__ __forceinline__ void warmup_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
+                                             int32_t *__restrict__ out, int cap) {
     const float thr0 = st.thr;
     uint32_t mask = 0;
 #pragma unroll
@@ -270,71 +319,110 @@ __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int col0, Ro
 #pragma unroll
         for (int j = 0; j < 4; ++j) s4[j] = (i & 4) ? s8[4 + j] : s8[j];
         const float s2a = (i & 2) ? s4[2] : s4[0], s2b = (i & 2) ? s4[3] : s4[1];
-        float v = (i & 1) ? s2b : s2a;
+        const float v = (i & 1) ? s2b : s2a;
         if (v < st.thr) {   // the threshold may have tightened since the mask was taken
-            const int slot = atomicAdd(st.s_cnt, 1);
+            const int slot = (int) atoms_add_u32(st.s_cnt, 1u);
             if (slot < cap) out[slot] = col0 + i;
-#pragma unroll
-            for (int s = 0; s < KT; ++s) {
-                float lo = fminf(st.tk[s], v);
-                v = fmaxf(st.tk[s], v);
-                st.tk[s] = lo;
-            }
-            float T = st.tk[KT - 1];
-#pragma unroll
-            for (int s = 0; s < KT - 1; ++s)
-                if (s == k - 1) T = st.tk[s];
-            st.thr_own = cand_threshold(T, st.na, st.eta, st.slop, st.gfac);
-            st.thr = fminf(st.thr, st.thr_own);
+            tk_insert<KT>(st, v);
+            retighten<KT, EH>(st, k);
         }
     }
-    if (EH == 2) *st.s_thr_own = st.thr_own;   // publish for the thread that filters the other half of this row's columns
 }
 
-template <int KT, int EH>
-__device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
-                                              int32_t *__restrict__ out, int cap) {
-    // fast path: 32 accumulators -> their minimum in 16 three-input min ops, one compare
-    const float a0 = min3(F(0), F(1), F(2)), a1 = min3(F(3), F(4), F(5)), a2 = min3(F(6), F(7), F(8));
-    const float a3 = min3(F(9), F(10), F(11)), a4 = min3(F(12), F(13), F(14)), a5 = min3(F(15), F(16), F(17));
-    const float a6 = min3(F(18), F(19), F(20)), a7 = min3(F(21), F(22), F(23)), a8 = min3(F(24), F(25), F(26));
-    const float a9 = min3(F(27), F(28), F(29)), a10 = fminf(F(30), F(31));
-    const float b0 = min3(a0, a1, a2), b1 = min3(a3, a4, a5), b2 = min3(a6, a7, a8), b3 = min3(a9, a10, b0);
-    const float m = min3(b1, b2, b3);
-    if (m < st.thr) slow_chunk<KT, EH>(r, col0, st, k, out, cap);   // inactive rows carry thr = -inf
+// Steady-state append: every column of the chunk under the (already re-tightened) threshold goes to the list.
+__device__ __forceinline__ void append_chunk(const uint32_t (&r)[32], int col0, float thr, uint32_t s_cnt,
+                                             int32_t *__restrict__ out, int cap) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mask |= (F(i) < thr) ? (1u << i) : 0u;
+    while (mask) {
+        const int i = __ffs((int) mask) - 1;
+        mask &= mask - 1;
+        const int slot = (int) atoms_add_u32(s_cnt, 1u);
+        if (slot < cap) out[slot] = col0 + i;
+    }
+}
+
+// minimum of 32 accumulators: one dependent chain of 16 three-input min ops (one live temporary; the four chains of a
+// 128-column batch are independent, which is all the instruction-level parallelism the half-rate min pipe can use)
+__device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
+    float m = min3(F(0), F(1), F(2));
+#pragma unroll
+    for (int i = 3; i < 31; i += 2) m = min3(m, F(i), F(i + 1));
+    return fminf(m, F(31));
 }
 #undef F
+
+// 128 accumulators of one row, already in registers (the TMEM buffer has been handed back to the MMA issuer).
+// Fast path: their minimum against the row threshold -- 66 min ops, one compare, one branch per 128 columns.
+// Rare path: the four chunk minima (four distinct columns) go into the row's k-smallest list, the threshold is
+// re-derived, and the columns under it are appended.  Tracking only chunk minima keeps the list an upper bound of the
+// true k smallest -- all the certificate needs -- and misses a tightening only when two of the k smallest fall into
+// one 32-column chunk.
+template <int KT, int EH>
+__device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const uint32_t (&r2)[32],
+                                           const uint32_t (&r3)[32], int col0, RowState<KT> &st, int k,
+                                           int32_t *__restrict__ out, int cap) {
+    const float m0 = min32(r0), m1 = min32(r1), m2 = min32(r2), m3 = min32(r3);
+    if (fminf(min3(m0, m1, m2), m3) < st.thr) {   // inactive rows carry thr = -inf
+        if (kth_smallest<KT>(st, k) == INFINITY) {
+            if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, cap);
+            if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, cap);
+            if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + 64, st, k, out, cap);
+            if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + 96, st, k, out, cap);
+        } else {
+            tk_insert<KT>(st, m0);
+            tk_insert<KT>(st, m1);
+            tk_insert<KT>(st, m2);
+            tk_insert<KT>(st, m3);
+            retighten<KT, EH>(st, k);
+            const float thr = st.thr;
+            if (m0 < thr) append_chunk(r0, col0, thr, st.s_cnt, out, cap);
+            if (m1 < thr) append_chunk(r1, col0 + 32, thr, st.s_cnt, out, cap);
+            if (m2 < thr) append_chunk(r2, col0 + 64, thr, st.s_cnt, out, cap);
+            if (m3 < thr) append_chunk(r3, col0 + 96, thr, st.s_cnt, out, cap);
+        }
+    }
+}
 
 // PAIR: CTA-pair mode (tcgen05.mma cta_group::2, M = 256 across two SMs, each CTA holds half of every train tile).
 // EH:   epilogue column halves.  1 = four epilogue warps, a thread owns a whole row; 2 = eight warps (two per
 //       scheduler), warp w drains TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of every tile.
-template <int KT, bool PAIR, int EH>
+// DBG:  compiles the timing experiments (TcParams::debug_flags) and the accumulator dump in; the production
+//       instantiation carries none of it in its loops.
+template <int KT, bool PAIR, int EH, bool DBG>
 __global__ void __launch_bounds__(64 + 128 * EH, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
                      const TcParams p) {
+    const int dflags = DBG ? p.debug_flags : 0;
+    float *const dump = DBG ? p.dump : nullptr;
     constexpr int kEpiWarps = 4 * EH;
     constexpr int kEpiThreads = 128 * EH;
     constexpr int kColsPerWarp = B200M_TILE_N / EH;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-    uint8_t *sA = smem;
-    uint8_t *sB = sA + (size_t) p.ka * kATileBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t) p.stages * p.stage_bytes);
+    // Everything in shared memory is addressed through the shared window (32-bit addresses).  The operand tiles need
+    // 1024-byte alignment (128B-swizzle atoms of 8 rows); the dynamic segment starts at a 1024-aligned window offset as
+    // long as the kernel has no static shared memory, and the round-up below keeps it correct if that ever changes
+    // (the launch reserves the slack).
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_u = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA_u = smem_u;
+    const uint32_t sB_u = sA_u + (uint32_t) (p.ka * kATileBytes);
+    const uint32_t bars_u = sB_u + (uint32_t) (p.stages * p.stage_bytes);
     // barrier map: [0..S) full, [S..2S) empty, 2S a_full, 2S+1.. tmem_full[2], 2S+3.. tmem_empty[2]
     const int stages = p.stages;
-    const uint32_t bar_full0 = smem_u32(bars);
+    const uint32_t bar_full0 = bars_u;
     const uint32_t bar_empty0 = bar_full0 + 8u * (uint32_t) stages;
     const uint32_t bar_a = bar_full0 + 8u * (uint32_t) (2 * stages);
     const uint32_t bar_tfull0 = bar_a + 8u;
     const uint32_t bar_tempty0 = bar_a + 24u;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * stages + 5);
-    int *s_cnt = reinterpret_cast<int *>(bars + 2 * stages + 6);          // [128] appended entries per row
-    float *s_thr = reinterpret_cast<float *>(s_cnt + B200M_TILE_M);       // [2][128] published thresholds per column half
+    const uint32_t tmem_slot = bars_u + 8u * (uint32_t) (2 * stages + 5);
+    const uint32_t s_cnt = bars_u + 8u * (uint32_t) (2 * stages + 6);     // [128] u32: appended entries per row
+    const uint32_t s_thr = s_cnt + 4u * B200M_TILE_M;                     // [2][128] f32: published thresholds per column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
-    const int t0 = p.dump ? p.tiles_per_split : split * p.tiles_per_split;   // dump mode: tiles_per_split holds the tile id
-    const int t1 = p.dump ? t0 + 1 : min(p.n_ttiles, t0 + p.tiles_per_split);
+    const int t0 = dump ? p.tiles_per_split : split * p.tiles_per_split;   // dump mode: tiles_per_split holds the tile id
+    const int t1 = dump ? t0 + 1 : min(p.n_ttiles, t0 + p.tiles_per_split);
     const int ka = p.ka;
 
     if (threadIdx.x == 0) {
@@ -357,12 +445,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     if (warp == 1) {
         if (PAIR) {   // the same warp of both CTAs of the pair allocates
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                          "r"(kTmemCols)
                          : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                          "r"(kTmemCols)
                          : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -372,7 +460,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
     else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = lds_u32(tmem_slot);
     const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t) ((1u << p.cluster) - 1u);
 
@@ -380,7 +468,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ===== TMA producer: the whole warp walks the ring (warp-uniform control flow keeps addresses and barrier
         // handles in uniform registers), one elected lane issues =====
         const int q_row = p.q_row0 + qtile * B200M_TILE_M;
-        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
         if (PAIR) {
             // CTA-pair mode: each CTA keeps its own 128 query rows and HALF of every train tile (its 128 rows);
             // all transaction bytes are counted on the leader's barriers, which the leader's MMA thread waits on.
@@ -397,7 +484,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 for (int a = 0; a < ka; ++a) {
                     mbar_wait(bar_empty0 + 8u * s, ph);
                     if (elect_one()) {
-                        if (p.debug_flags & 4) {   // timing experiment: no B traffic at all
+                        if (dflags & 4) {   // timing experiment: no B traffic at all
                             if (crank == 0) mbar_arrive(bar_full0 + 8u * s);
                         } else {
                             if (crank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, (uint32_t) (2 * p.stage_bytes));
@@ -442,11 +529,11 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (!PAIR || crank == 0) {   // pair mode: the leader CTA issues for both SMs
             mbar_wait(bar_a, 0);
             tc_fence_after();
-            const uint64_t desc_a0 = make_kmajor_sw128_desc(smem_u32(sA));
-            const uint64_t desc_b0 = make_kmajor_sw128_desc(smem_u32(sB));
+            const uint64_t desc_a0 = make_kmajor_sw128_desc(sA_u);
+            const uint64_t desc_b0 = make_kmajor_sw128_desc(sB_u);
             const uint32_t a_step = (uint32_t) (kATileBytes >> 4), b_step = (uint32_t) (p.stage_bytes >> 4);
-            const int nk_last = (p.debug_flags & 2) ? 0 : p.ksteps - 4 * (ka - 1);   // K steps of the last atom (1..4)
-            const bool no_mma = (p.debug_flags & 2) != 0;
+            const uint32_t nk_full = (dflags & 2) ? 0u : 4u;
+            const uint32_t nk_last = (dflags & 2) ? 0u : (uint32_t) (p.ksteps - 4 * (ka - 1));   // K steps of the last atom (1..4)
             constexpr uint32_t idesc = PAIR ? kInstrDescPair : kInstrDesc;
             uint32_t s = 0, ph = 0;
             for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
@@ -460,18 +547,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (elect_one()) {
                         const uint64_t da = desc_a0 + (uint64_t) ((uint32_t) a * a_step);
                         const uint64_t db = desc_b0 + (uint64_t) (s * b_step);
-                        if (a + 1 < ka) {
-                            if (!no_mma) {
-                                // +32 B (2 descriptor units) per K = 16 step inside the 128 B swizzle atom
-                                tc_mma<PAIR>(tmem_d, da, db, idesc, (uint32_t) (a != 0));
-                                tc_mma<PAIR>(tmem_d, da + 2, db + 2, idesc, 1u);
-                                tc_mma<PAIR>(tmem_d, da + 4, db + 4, idesc, 1u);
-                                tc_mma<PAIR>(tmem_d, da + 6, db + 6, idesc, 1u);
-                            }
-                        } else {
-                            for (int kk = 0; kk < nk_last; ++kk)
-                                tc_mma<PAIR>(tmem_d, da + (uint64_t) (2 * kk), db + (uint64_t) (2 * kk), idesc, (uint32_t) ((a | kk) != 0));
-                        }
+                        // K steps of this atom: 4, or what is left of the row in the last one; +32 B (2 descriptor
+                        // units) per K = 16 step inside the 128 B swizzle atom
+                        const uint32_t nk = a + 1 < ka ? nk_full : nk_last;
+                        tc_mma<PAIR>(tmem_d, da, db, idesc, (uint32_t) (a != 0), (uint32_t) (nk > 0));
+                        tc_mma<PAIR>(tmem_d, da + 2, db + 2, idesc, 1u, (uint32_t) (nk > 1));
+                        tc_mma<PAIR>(tmem_d, da + 4, db + 4, idesc, 1u, (uint32_t) (nk > 2));
+                        tc_mma<PAIR>(tmem_d, da + 6, db + 6, idesc, 1u, (uint32_t) (nk > 3));
                         // frees the B stage once these MMAs have read it (in every CTA that writes into it)
                         if (PAIR) tc_commit_2sm_mcast(bar_empty0 + 8u * s, (uint16_t) 3);
                         else if (p.cluster == 1) tc_commit(bar_empty0 + 8u * s);
@@ -499,12 +581,11 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
         st.thr = active ? INFINITY : -INFINITY;
-        st.thr_own = st.thr;
-        st.s_cnt = s_cnt + row_in_tile;
-        st.s_thr_own = s_thr + half * B200M_TILE_M + row_in_tile;
-        const float *s_thr_peer = s_thr + (half ^ 1) * B200M_TILE_M + row_in_tile;
-        if (half == 0) *st.s_cnt = 0;
-        *st.s_thr_own = st.thr;
+        st.s_cnt = s_cnt + 4u * (uint32_t) row_in_tile;
+        st.s_thr_own = s_thr + 4u * (uint32_t) (half * B200M_TILE_M + row_in_tile);
+        const uint32_t s_thr_peer = s_thr + 4u * (uint32_t) ((half ^ 1) * B200M_TILE_M + row_in_tile);
+        if (half == 0) sts_u32(st.s_cnt, 0u);
+        sts_f32(st.s_thr_own, st.thr);
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
             const float ab = sqrtf(na) + p.bmax;
@@ -515,51 +596,75 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
         const size_t list_row = (size_t) split * p.n_rows + (active ? local : 0);
-        int32_t *out = p.cand_idx + list_row * p.cap;
+        int32_t *const out = p.cand_idx + list_row * p.cap;
+        const int k = p.k, cap = p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(bar_tempty0, 0) : bar_tempty0;
-        uint32_t ra[32], rb[32];
-        for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        long long c_wait = 0, c_ld = 0, c_fast = 0, c_slow = 0;   // B200M_TC_DEBUG & 512: where this warp's cycles go
+        int n_slow = 0;
+        const bool prof = (dflags & 512) != 0;
+        int col_base = t0 * B200M_TILE_N + half * kColsPerWarp;
+        for (int lt = 0; lt < t1 - t0; ++lt, col_base += B200M_TILE_N) {
             const uint32_t buf = (uint32_t) lt & 1u;
+            long long c0 = prof ? clock64() : 0;
             mbar_wait(bar_tfull0 + 8u * buf, ((uint32_t) lt >> 1) & 1u);
             tc_fence_after();
+            if (prof) { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const uint32_t taddr = lane_base + buf * (uint32_t) B200M_TILE_N;
-            const int col_base = t * B200M_TILE_N + half * kColsPerWarp;
-            if (!(p.debug_flags & 1)) {
-                if (p.dump) {   // debug: raw accumulators of this tile
+            if (EH == 2) st.thr = fminf(st.thr, lds_f32(s_thr_peer));   // pick up what the partner thread has learnt
+            // 128 columns at a time: four TMEM loads in flight, one wait.  The accumulator buffer goes back to the MMA
+            // issuer as soon as this warp's last load has landed in registers -- the filtering below then overlaps the
+            // MMAs of the tile after next instead of sitting on their critical path.
 #pragma unroll 1
-                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
-                        tmem_ld_32x32b_x32(taddr + (uint32_t) (c * 32), ra);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            p.dump[((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * kColsPerWarp + c * 32 + i] =
-                                __uint_as_float(ra[i]);
+            for (int h = 0; h < kColsPerWarp / 128; ++h) {
+                if (!(dflags & 1)) {
+                    tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128), r0);
+                    tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 32), r1);
+                    tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 64), r2);
+                    tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 96), r3);
+                    tmem_ld_wait();
+                }
+                if (prof) { long long c1 = clock64(); c_ld += c1 - c0; c0 = c1; }
+                if (h == kColsPerWarp / 128 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(tempty_dst0 + 8u * buf);
+                        else mbar_arrive(bar_tempty0 + 8u * buf);
                     }
                 }
-                if (EH == 2) st.thr = fminf(st.thr, *s_thr_peer);   // pick up what the partner thread has learnt
-                // two register buffers: the TMEM read of the next 32 columns is in flight while these are filtered;
-                // the loop stays rolled so that its body (two copies of the chunk code) fits the instruction cache
-                tmem_ld_32x32b_x32(taddr, ra);
-#pragma unroll 1
-                for (int c = 0; c < kColsPerWarp / 32; c += 2) {
-                    tmem_ld_wait();
-                    tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 1) * 32), rb);
-                    if (!(p.debug_flags & 32)) process_chunk<KT, EH>(ra, col_base + c * 32, st, p.k, out, p.cap);
-                    tmem_ld_wait();
-                    if (c + 2 < kColsPerWarp / 32) tmem_ld_32x32b_x32(taddr + (uint32_t) ((c + 2) * 32), ra);
-                    if (!(p.debug_flags & 32)) process_chunk<KT, EH>(rb, col_base + (c + 1) * 32, st, p.k, out, p.cap);
+                if (dflags & (1 | 32)) continue;
+                if (dump) {   // debug: raw accumulators of this tile
+                    float *d = dump + ((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * kColsPerWarp + h * 128;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        d[i] = __uint_as_float(r0[i]);
+                        d[32 + i] = __uint_as_float(r1[i]);
+                        d[64 + i] = __uint_as_float(r2[i]);
+                        d[96 + i] = __uint_as_float(r3[i]);
+                    }
+                }
+                if (dflags & 256) {   // timing experiment: fast path only
+                    if (fminf(fminf(min32(r0), min32(r1)), fminf(min32(r2), min32(r3))) < st.thr) st.na += 1.f;
+                    continue;
+                }
+                const float thr_before = st.thr;
+                process128<KT, EH>(r0, r1, r2, r3, col_base + h * 128, st, k, out, cap);
+                if (prof) {
+                    long long c1 = clock64();
+                    const bool slow = __any_sync(0xffffffffu, st.thr != thr_before);
+                    if (slow) { c_slow += c1 - c0; ++n_slow; } else c_fast += c1 - c0;
+                    c0 = c1;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (PAIR) mbar_arrive_cluster(tempty_dst0 + 8u * buf);
-                else mbar_arrive(bar_tempty0 + 8u * buf);
-            }
         }
+        if (prof && lane == 0 && blockIdx.x < 2 && blockIdx.y == 0)
+            printf("b200match epi-prof cta %d warp %d tiles %d: wait %lld ld %lld fast %lld slow %lld (entries that tightened: %d)\n",
+                   blockIdx.x, warp, t1 - t0, c_wait, c_ld, c_fast, c_slow, n_slow);
+        if ((dflags & 256) && st.na == -1.f) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // both threads of every row are done appending
-        if (half == 0 && active && !p.dump) p.cand_cnt[list_row] = *st.s_cnt;
+        if (half == 0 && active && !dump) p.cand_cnt[list_row] = (int32_t) lds_u32(st.s_cnt);
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
@@ -624,9 +729,9 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
     return 0;
 }
 
-template <int KT, bool PAIR, int EH>
+template <int KT, bool PAIR, int EH, bool DBG>
 int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
-    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(64 + 128 * EH, 1, 1);
@@ -639,7 +744,7 @@ int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH>, *mq, *mt, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, DBG>, *mq, *mt, p);
     if (e != cudaSuccess) {
         cudaGetLastError();   // do not leave the launch error behind for the next call
         return b200m_fail_msg(ctx, std::string("tc_candidates launch failed: ") + cudaGetErrorString(e) + " (grid " +
@@ -736,11 +841,15 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     if (ctx->tc_debug & 64) eh = 1;
     if (ctx->tc_debug & 128) eh = 2;
     int rc;
-#define B200M_TC_CASE(KT_)                                                                    \
-    rc = pair ? (eh == 2 ? launch_tc<KT_, true, 2>(ctx, mq, mt, p, grid, smem)                \
-                         : launch_tc<KT_, true, 1>(ctx, mq, mt, p, grid, smem))               \
-              : (eh == 2 ? launch_tc<KT_, false, 2>(ctx, mq, mt, p, grid, smem)               \
-                         : launch_tc<KT_, false, 1>(ctx, mq, mt, p, grid, smem))
+    const bool dbg = dump != nullptr || ctx->tc_debug != 0;
+#define B200M_TC_CASE2(KT_, DBG_)                                                             \
+    rc = pair ? (eh == 2 ? launch_tc<KT_, true, 2, DBG_>(ctx, mq, mt, p, grid, smem)          \
+                         : launch_tc<KT_, true, 1, DBG_>(ctx, mq, mt, p, grid, smem))         \
+              : (eh == 2 ? launch_tc<KT_, false, 2, DBG_>(ctx, mq, mt, p, grid, smem)         \
+                         : launch_tc<KT_, false, 1, DBG_>(ctx, mq, mt, p, grid, smem))
+#define B200M_TC_CASE(KT_)               \
+    if (dbg) { B200M_TC_CASE2(KT_, true); } \
+    else { B200M_TC_CASE2(KT_, false); }
     switch (kt) {
         case 1: B200M_TC_CASE(1); break;
         case 2: B200M_TC_CASE(2); break;
@@ -749,6 +858,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
         default: B200M_TC_CASE(16); break;
     }
 #undef B200M_TC_CASE
+#undef B200M_TC_CASE2
     if (rc) return rc;
     ctx->stats.launches += 1;
     ctx->stats.candidate_launches += 1;
