@@ -141,7 +141,8 @@ void b200m_destroy(b200m_ctx *ctx) {
     ctx->prep.mean.release(); ctx->prep.red.release();
     DevBuf *ws[] = {&ctx->ws_cand_idx, &ctx->ws_cand_cnt, &ctx->ws_flag_rows, &ctx->ws_counters, &ctx->ws_scan,
                     &ctx->ws_out, &ctx->ws_misc, &ctx->ws_fidx, &ctx->ws_fdist, &ctx->ws_fcnt, &ctx->ws_ridx,
-                    &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr, &ctx->ws_totals};
+                    &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr, &ctx->ws_totals, &ctx->ws_part_i, &ctx->ws_part_d,
+                    &ctx->ws_done, &ctx->ws_cand_val, &ctx->ws_cand_thr};
     for (DevBuf *b : ws) b->release();
     tc_release(ctx);
     if (ctx->pool) {
@@ -310,16 +311,16 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
         StatTimer tf(ctx, &ctx->stats.ms_fallback);
         CK(launch_exact_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(),
                              t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_rows, nullptr, nullptr, k, d_idx,
-                             d_dist, d_count, 1 << 30, st));
+                             d_dist, d_count, 1 << 30, 0, nullptr, nullptr, nullptr, st));
         ctx->stats.launches += 1;
         tf.stop();
         return 0;
     }
     // 1. tensor-core candidate pass: per row a certified superset of the exact top-k
-    int n_lists = 0, cap = 0;
+    int n_lists = 0, cap = 0, has_values = 0;
     {
         StatTimer tc(ctx, &ctx->stats.ms_candidates);
-        if (tc_candidates(ctx, direction, row_begin, n_rows, k, p->cand_cap, &n_lists, &cap, nullptr, 0)) return 1;
+        if (tc_candidates(ctx, direction, row_begin, n_rows, k, p->cand_cap, &n_lists, &cap, &has_values, nullptr, 0)) return 1;
         tc.stop();
     }
     // 2. exact FP32 re-rank of the candidates (bit-identical arithmetic to the reference)
@@ -330,8 +331,10 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
         StatTimer tr(ctx, &ctx->stats.ms_rerank);
         CK(launch_rerank(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(), t.valid.as<uint8_t>(),
                          t.n, t.index_offset, row_begin, n_rows, k, ctx->ws_cand_idx.as<int32_t>(),
-                         ctx->ws_cand_cnt.as<int32_t>(), n_lists, cap, d_idx, d_dist, d_count,
-                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), st));
+                         ctx->ws_cand_cnt.as<int32_t>(), n_lists, cap,
+                         has_values ? ctx->ws_cand_val.as<float>() : nullptr,
+                         has_values ? ctx->ws_cand_thr.as<float>() : nullptr, d_idx, d_dist, d_count,
+                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), ctx->sm_count, st));
         ctx->stats.launches += 1;
         tr.stop();
     }
@@ -339,11 +342,21 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
     {
         StatTimer tf(ctx, &ctx->stats.ms_fallback);
         size_t max_blocks = (size_t) ctx->sm_count * 8;
+        const int split_blocks = ctx->sm_count * 2;
+        const size_t part = exact_split_ws_entries(split_blocks, k);
+        CK(ctx->ws_part_i.reserve(sizeof(int32_t) * part));
+        CK(ctx->ws_part_d.reserve(sizeof(float) * part));
+        CK(ctx->ws_done.reserve(sizeof(unsigned int) * (size_t) exact_split_max_rows()));
+        if (!ctx->done_init) {   // the merging CTA leaves every counter at zero again
+            CK(cudaMemsetAsync(ctx->ws_done.p, 0, sizeof(unsigned int) * (size_t) exact_split_max_rows(), st));
+            ctx->done_init = true;
+        }
         CK(launch_exact_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(),
                              t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_rows,
                              ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), k, d_idx, d_dist, d_count,
-                             (int) (n_rows < max_blocks ? n_rows : max_blocks), st));
-        ctx->stats.launches += 1;
+                             (int) (n_rows < max_blocks ? n_rows : max_blocks), split_blocks, ctx->ws_part_i.as<int32_t>(),
+                             ctx->ws_part_d.as<float>(), ctx->ws_done.as<unsigned int>(), st));
+        ctx->stats.launches += 2;
         tf.stop();
     }
     if (ctx->profiling) {   // fold this call's counters into the running totals on the device (read at get_stats)
@@ -520,9 +533,9 @@ int b200m_debug_tc_tile(b200m_ctx *ctx, int direction, size_t q_row0, size_t t_t
         CK(launch_tc_prepare(ctx));
     CK(ctx->ws_out.reserve(sizeof(float) * 2 * B200M_TILE_M * B200M_TILE_N));   // pair mode dumps two query tiles
     CK(cudaMemsetAsync(ctx->ws_out.p, 0xff, sizeof(float) * 2 * B200M_TILE_M * B200M_TILE_N, ctx->stream));
-    int n_lists = 0, cap = 0;
+    int n_lists = 0, cap = 0, has_values = 0;
     size_t n_rows = q.n - q_row0 < (size_t) B200M_TILE_M ? q.n - q_row0 : (size_t) B200M_TILE_M;
-    if (tc_candidates(ctx, direction, q_row0, n_rows, 1, 0, &n_lists, &cap, ctx->ws_out.as<float>(), t_tile)) return 1;
+    if (tc_candidates(ctx, direction, q_row0, n_rows, 1, 0, &n_lists, &cap, &has_values, ctx->ws_out.as<float>(), t_tile)) return 1;
     CK(cudaMemcpyAsync(host_out, ctx->ws_out.p, sizeof(float) * B200M_TILE_M * B200M_TILE_N, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -59,6 +59,8 @@ struct TcParams {
     const float *q_norm16;
     int32_t *cand_idx;    // [n_lists][n_rows][cap]
     int32_t *cand_cnt;    // [n_lists][n_rows]
+    float *cand_val;      // [n_lists][n_rows][cap] accumulator value of every entry, or null (EH = 1 kernels only)
+    float *cand_thr;      // [n_lists][n_rows] the row's final append threshold (written when cand_val is)
     float *dump;          // debug: raw accumulators of one tile [128][256]
     int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
                           // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages, 32 = epilogue only
@@ -298,12 +300,24 @@ __device__ __forceinline__ void retighten(RowState<KT> &st, int k) {
 }
 
 #define F(i) __uint_as_float(r[i])
+// element i (runtime index) of 32 registers through a select tree: no dynamic register indexing, no local memory
+__device__ __forceinline__ float select32(const uint32_t (&r)[32], int i) {
+    float s16[16], s8[8], s4[4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s16[j] = (i & 16) ? F(16 + j) : F(j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s8[j] = (i & 8) ? s16[8 + j] : s16[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s4[j] = (i & 4) ? s8[4 + j] : s8[j];
+    const float s2a = (i & 2) ? s4[2] : s4[0], s2b = (i & 2) ? s4[3] : s4[1];
+    return (i & 1) ? s2b : s2a;
+}
 // Warm-up path (a row that has not yet seen k columns, i.e. its first tile): every column under the running
 // threshold is appended and inserted one at a time, the threshold tightening as soon as k values are known.  The
 // value is fetched through a select tree (no dynamic register indexing, no local memory).
 template <int KT, int EH>
 __device__ __forceinline__ void warmup_chunk(const uint32_t (&r)[32], int col0, RowState<KT> &st, int k,
-                                             int32_t *__restrict__ out, int cap) {
+                                             int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
     const float thr0 = st.thr;
     uint32_t mask = 0;
 #pragma unroll
@@ -311,18 +325,13 @@ __device__ __forceinline__ void warmup_chunk(const uint32_t (&r)[32], int col0, 
     while (mask) {
         const int i = __ffs((int) mask) - 1;
         mask &= mask - 1;
-        float s16[16], s8[8], s4[4];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s16[j] = (i & 16) ? F(16 + j) : F(j);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s8[j] = (i & 8) ? s16[8 + j] : s16[j];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) s4[j] = (i & 4) ? s8[4 + j] : s8[j];
-        const float s2a = (i & 2) ? s4[2] : s4[0], s2b = (i & 2) ? s4[3] : s4[1];
-        const float v = (i & 1) ? s2b : s2a;
+        const float v = select32(r, i);
         if (v < st.thr) {   // the threshold may have tightened since the mask was taken
             const int slot = (int) atoms_add_u32(st.s_cnt, 1u);
-            if (slot < cap) out[slot] = col0 + i;
+            if (slot < cap) {
+                out[slot] = col0 + i;
+                if (EH == 1) out_v[slot] = v;
+            }
             tk_insert<KT>(st, v);
             retighten<KT, EH>(st, k);
         }
@@ -330,8 +339,11 @@ __device__ __forceinline__ void warmup_chunk(const uint32_t (&r)[32], int col0, 
 }
 
 // Steady-state append: every column of the chunk under the (already re-tightened) threshold goes to the list.
+// EH = 1 kernels (long descriptors: the epilogue has slack, the re-rank gather is what costs) also record the
+// accumulator value, so that the re-rank can drop every entry that the row's FINAL threshold no longer admits.
+template <int EH>
 __device__ __forceinline__ void append_chunk(const uint32_t (&r)[32], int col0, float thr, uint32_t s_cnt,
-                                             int32_t *__restrict__ out, int cap) {
+                                             int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
     uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) mask |= (F(i) < thr) ? (1u << i) : 0u;
@@ -339,7 +351,10 @@ __device__ __forceinline__ void append_chunk(const uint32_t (&r)[32], int col0, 
         const int i = __ffs((int) mask) - 1;
         mask &= mask - 1;
         const int slot = (int) atoms_add_u32(s_cnt, 1u);
-        if (slot < cap) out[slot] = col0 + i;
+        if (slot < cap) {
+            out[slot] = col0 + i;
+            if (EH == 1) out_v[slot] = select32(r, i);
+        }
     }
 }
 
@@ -362,14 +377,14 @@ __device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
 template <int KT, int EH>
 __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const uint32_t (&r2)[32],
                                            const uint32_t (&r3)[32], int col0, RowState<KT> &st, int k,
-                                           int32_t *__restrict__ out, int cap) {
+                                           int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
     const float m0 = min32(r0), m1 = min32(r1), m2 = min32(r2), m3 = min32(r3);
     if (fminf(min3(m0, m1, m2), m3) < st.thr) {   // inactive rows carry thr = -inf
         if (kth_smallest<KT>(st, k) == INFINITY) {
-            if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, cap);
-            if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, cap);
-            if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + 64, st, k, out, cap);
-            if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + 96, st, k, out, cap);
+            if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, out_v, cap);
+            if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, out_v, cap);
+            if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + 64, st, k, out, out_v, cap);
+            if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + 96, st, k, out, out_v, cap);
         } else {
             tk_insert<KT>(st, m0);
             tk_insert<KT>(st, m1);
@@ -377,10 +392,10 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
             tk_insert<KT>(st, m3);
             retighten<KT, EH>(st, k);
             const float thr = st.thr;
-            if (m0 < thr) append_chunk(r0, col0, thr, st.s_cnt, out, cap);
-            if (m1 < thr) append_chunk(r1, col0 + 32, thr, st.s_cnt, out, cap);
-            if (m2 < thr) append_chunk(r2, col0 + 64, thr, st.s_cnt, out, cap);
-            if (m3 < thr) append_chunk(r3, col0 + 96, thr, st.s_cnt, out, cap);
+            if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.s_cnt, out, out_v, cap);
+            if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.s_cnt, out, out_v, cap);
+            if (m2 < thr) append_chunk<EH>(r2, col0 + 64, thr, st.s_cnt, out, out_v, cap);
+            if (m3 < thr) append_chunk<EH>(r3, col0 + 96, thr, st.s_cnt, out, out_v, cap);
         }
     }
 }
@@ -597,6 +612,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
         const size_t list_row = (size_t) split * p.n_rows + (active ? local : 0);
         int32_t *const out = p.cand_idx + list_row * p.cap;
+        float *const out_v = EH == 1 ? p.cand_val + list_row * p.cap : nullptr;
         const int k = p.k, cap = p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(bar_tempty0, 0) : bar_tempty0;
@@ -650,7 +666,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     continue;
                 }
                 const float thr_before = st.thr;
-                process128<KT, EH>(r0, r1, r2, r3, col_base + h * 128, st, k, out, cap);
+                process128<KT, EH>(r0, r1, r2, r3, col_base + h * 128, st, k, out, out_v, cap);
                 if (prof) {
                     long long c1 = clock64();
                     const bool slow = __any_sync(0xffffffffu, st.thr != thr_before);
@@ -664,7 +680,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                    blockIdx.x, warp, t1 - t0, c_wait, c_ld, c_fast, c_slow, n_slow);
         if ((dflags & 256) && st.na == -1.f) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // both threads of every row are done appending
-        if (half == 0 && active && !dump) p.cand_cnt[list_row] = (int32_t) lds_u32(st.s_cnt);
+        if (half == 0 && active && !dump) {
+            p.cand_cnt[list_row] = (int32_t) lds_u32(st.s_cnt);
+            if (EH == 1) p.cand_thr[list_row] = st.thr;
+        }
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
@@ -769,7 +788,7 @@ void tc_release(b200m_ctx *ctx) {
 }
 
 int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
-                  int *n_lists_out, int *cap_out, float *dump, size_t dump_t_tile) {
+                  int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile) {
     Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
     const int n_qtiles = (int) ((n_rows + B200M_TILE_M - 1) / B200M_TILE_M);
     // Default = CTA-pair mode (cta_group::2): the two CTAs of a cluster form one M=256 MMA, each keeps its own 128
@@ -828,18 +847,27 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     CK(ctx->ws_cand_cnt.reserve(sizeof(int32_t) * (size_t) n_splits * n_rows));
     p.cand_idx = ctx->ws_cand_idx.as<int32_t>();
     p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
+    // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
+    // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and there a thread that owns its whole row
+    // also records the accumulator values so that the re-rank can prune by the row's final threshold.
+    int eh = p.ka <= 2 ? 2 : 1;
+    if (ctx->tc_debug & 64) eh = 1;
+    if (ctx->tc_debug & 128) eh = 2;
+    p.cand_val = nullptr;
+    p.cand_thr = nullptr;
+    if (eh == 1) {
+        CK(ctx->ws_cand_val.reserve(sizeof(float) * (size_t) n_splits * n_rows * (size_t) cap));
+        CK(ctx->ws_cand_thr.reserve(sizeof(float) * (size_t) n_splits * n_rows));
+        p.cand_val = ctx->ws_cand_val.as<float>();
+        p.cand_thr = ctx->ws_cand_thr.as<float>();
+    }
+    *has_values_out = eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
     if (dump) p.tiles_per_split = (int) dump_t_tile;
     const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + kTailBytes;
     dim3 grid((unsigned) (dump ? cluster : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
     int kt = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : 16;
-    // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
-    // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and a thread that owns its whole row
-    // keeps the tighter threshold (fewer candidates to re-rank).
-    int eh = p.ka <= 2 ? 2 : 1;
-    if (ctx->tc_debug & 64) eh = 1;
-    if (ctx->tc_debug & 128) eh = 2;
     int rc;
     const bool dbg = dump != nullptr || ctx->tc_debug != 0;
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \

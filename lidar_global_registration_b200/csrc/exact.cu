@@ -53,7 +53,7 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
                   const float *__restrict__ t_f32, const uint8_t *__restrict__ t_valid, size_t nt,
                   long long t_off, size_t row_begin, size_t n_rows, const int32_t *__restrict__ row_list,
                   const int32_t *__restrict__ row_list_count, int k, int32_t *__restrict__ idx,
-                  float *__restrict__ dist, int32_t *__restrict__ count) {
+                  float *__restrict__ dist, int32_t *__restrict__ count, int split_max) {
     extern __shared__ float smem[];
     float *sq = smem;                                   // [dp] query row
     float *red_d = smem + dp;                           // [warps]
@@ -63,6 +63,7 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
     __shared__ int win_i, win_t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t total = row_list ? (size_t) *row_list_count : n_rows;
+    if (row_list && split_max > 0 && total <= (size_t) split_max) return;   // few flagged rows: exact_rows_split_kernel has them
 
     for (size_t r = blockIdx.x; r < total; r += gridDim.x) {
         const size_t local = row_list ? (size_t) row_list[r] : r;
@@ -136,95 +137,370 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
     }
 }
 
-// ---- re-rank -----------------------------------------------------------------
-// One warp per query row.  The candidate lists of the tensor-core pass are walked 32 at a
-// time: candidate c belongs to lane c, which runs the reference's sequential FP32 chain for
-// it.  Train rows are fetched 128 B at a time by the whole warp (coalesced, each line read
-// once) into a 32x33 shared tile, then every lane consumes its own row of the tile.
-constexpr int kRerankWarps = 8;
-constexpr int kMaxLists = 16;
+// ---- exact rows, split over the whole grid (a FEW flagged rows) -------------------------------
+// The one-CTA-per-row kernel above streams the entire train set through a single SM per row -- 700 MB at 15 GB/s for
+// SHOT-352 x 500k, tens of milliseconds for one overflowed row.  Here every CTA scans its slice of the train set for
+// every flagged row and leaves a sorted partial k-list; the CTA that finishes a row last merges the partials.
+constexpr int kSplitMaxRows = 256;
 
 template <int KMAX>
-__global__ void __launch_bounds__(kRerankWarps * 32)
+__device__ __forceinline__ void block_select(float (&ld)[KMAX], int (&li)[KMAX], int k, float *red_d, int *red_i, int *red_w,
+                                             float *win_d, int *win_i, int *win_t, float *out_d, int *out_i, int *found_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int head = 0, found = 0;
+    for (int round = 0; round < k; ++round) {
+        float hd = INFINITY;
+        int hi = INT_MAX;
+#pragma unroll
+        for (int m = 0; m < KMAX; ++m)
+            if (m == head) { hd = ld[m]; hi = li[m]; }
+        float bd = hd;
+        int bi = hi, bt = tid;
+        for (int o = 16; o > 0; o >>= 1) {
+            float od2 = __shfl_xor_sync(0xffffffffu, bd, o);
+            int oi2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            int ot2 = __shfl_xor_sync(0xffffffffu, bt, o);
+            if (lex_less(od2, oi2, bd, bi)) { bd = od2; bi = oi2; bt = ot2; }
+        }
+        if (lane == 0) { red_d[warp] = bd; red_i[warp] = bi; red_w[warp] = bt; }
+        __syncthreads();
+        if (tid == 0) {
+            float wd = red_d[0];
+            int wi = red_i[0], wt = red_w[0];
+            for (int w = 1; w < kExactThreads / 32; ++w)
+                if (lex_less(red_d[w], red_i[w], wd, wi)) { wd = red_d[w]; wi = red_i[w]; wt = red_w[w]; }
+            *win_d = wd; *win_i = wi; *win_t = wt;
+        }
+        __syncthreads();
+        if (*win_i == INT_MAX) break;
+        if (tid == *win_t) head++;
+        if (tid == 0) { out_i[round] = *win_i; out_d[round] = *win_d; }
+        found = round + 1;
+        __syncthreads();
+    }
+    *found_out = found;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kExactThreads)
+exact_rows_split_kernel(const float *__restrict__ q_f32, int dp, const float *__restrict__ t_f32,
+                        const uint8_t *__restrict__ t_valid, size_t nt, long long t_off, size_t row_begin,
+                        const int32_t *__restrict__ row_list, const int32_t *__restrict__ row_list_count, int k,
+                        int32_t *__restrict__ part_i, float *__restrict__ part_d, unsigned int *__restrict__ done,
+                        int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count) {
+    extern __shared__ float smem[];
+    float *sq = smem;
+    float *red_d = smem + dp;
+    int *red_i = reinterpret_cast<int *>(red_d + kExactThreads / 32);
+    int *red_w = red_i + kExactThreads / 32;
+    __shared__ float win_d;
+    __shared__ int win_i, win_t, is_last;
+    const int total = *row_list_count;
+    if (total <= 0 || total > kSplitMaxRows) return;   // many flagged rows: the one-CTA-per-row kernel takes them
+    const int tid = threadIdx.x;
+    const int S = (int) gridDim.x;
+    const size_t chunk = (nt + S - 1) / S;
+    const size_t j0 = (size_t) blockIdx.x * chunk, j1 = j0 + chunk < nt ? j0 + chunk : nt;
+    for (int r = 0; r < total; ++r) {
+        const size_t local = (size_t) row_list[r];
+        const size_t qi = row_begin + local;
+        __syncthreads();
+        for (int d = tid; d < dp; d += kExactThreads) sq[d] = q_f32[qi * (size_t) dp + d];
+        __syncthreads();
+        float ld[KMAX];
+        int li[KMAX];
+#pragma unroll
+        for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; li[m] = INT_MAX; }
+        for (size_t j = j0 + tid; j < j1; j += kExactThreads) {
+            if (!t_valid[j]) continue;
+            float d = __fsqrt_rn(seq_sqdist(sq, t_f32 + j * (size_t) dp, dp));
+            if (lex_less(d, (int) j, ld[KMAX - 1], li[KMAX - 1])) {
+                float cd = d;
+                int ci = (int) j;
+#pragma unroll
+                for (int m = 0; m < KMAX; ++m) {
+                    if (lex_less(cd, ci, ld[m], li[m])) {
+                        float td = ld[m]; int ti = li[m];
+                        ld[m] = cd; li[m] = ci;
+                        cd = td; ci = ti;
+                    }
+                }
+            }
+        }
+        int32_t *pi = part_i + ((size_t) r * S + blockIdx.x) * k;
+        float *pd = part_d + ((size_t) r * S + blockIdx.x) * k;
+        int found = 0;
+        block_select<KMAX>(ld, li, k, red_d, red_i, red_w, &win_d, &win_i, &win_t, pd, pi, &found);
+        if (tid >= found && tid < k) { pi[tid] = INT_MAX; pd[tid] = INFINITY; }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = atomicAdd(&done[r], 1u) == (unsigned) (S - 1);
+        __syncthreads();
+        if (!is_last) continue;
+        __threadfence();
+        // merge: S sorted partial lists of k entries; every thread folds a strided share into its own sorted list
+#pragma unroll
+        for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; li[m] = INT_MAX; }
+        const int n_part = S * k;
+        const volatile int32_t *vi = part_i + (size_t) r * S * k;
+        const volatile float *vd = part_d + (size_t) r * S * k;
+        for (int e = tid; e < n_part; e += kExactThreads) {
+            float cd = vd[e];
+            int ci = vi[e];
+            if (ci == INT_MAX) continue;
+            if (lex_less(cd, ci, ld[KMAX - 1], li[KMAX - 1])) {
+#pragma unroll
+                for (int m = 0; m < KMAX; ++m) {
+                    if (lex_less(cd, ci, ld[m], li[m])) {
+                        float td = ld[m]; int ti = li[m];
+                        ld[m] = cd; li[m] = ci;
+                        cd = td; ci = ti;
+                    }
+                }
+            }
+        }
+        __shared__ float fin_d[B200M_MAX_K];
+        __shared__ int fin_i[B200M_MAX_K];
+        block_select<KMAX>(ld, li, k, red_d, red_i, red_w, &win_d, &win_i, &win_t, fin_d, fin_i, &found);
+        __syncthreads();
+        int32_t *oi = idx + local * k;
+        float *od = dist + local * k;
+        if (tid < k) {
+            oi[tid] = tid < found ? (int32_t) (fin_i[tid] + t_off) : -1;
+            od[tid] = tid < found ? fin_d[tid] : 0.f;
+        }
+        if (tid == 0) { count[local] = found; done[r] = 0u; }   // counter ready for the next call
+    }
+}
+
+// ---- re-rank -----------------------------------------------------------------
+// One warp per query row (persistent warps, grid-stride over rows).  The row's candidates are taken 32 at a time:
+// lane c owns candidate c.  Every lane issues ONE bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form)
+// of its candidate's whole FP32 row from HBM into the warp's shared-memory slab, all of them -- and the query row
+// -- completing on the warp's mbarrier, so a warp has its entire gather (up to 32 rows, 45 KB for SHOT-352) in
+// flight at once instead of a load/store round trip per 128 bytes.  Each lane then runs the reference's sequential
+// FP32 chain over its own slab row with 128-bit shared loads; the slab pitch is an odd number of 16-byte units, so
+// the 32 lanes' loads are bank-conflict free.
+constexpr int kMaxLists = 16;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// bytes between consecutive slab rows: the row itself, padded so that (pitch / 16) is odd
+__host__ __device__ inline int rerank_pitch_bytes(int dp) { return (dp / 4) % 2 ? dp * 4 : dp * 4 + 16; }
+// Slab rows per warp.  Short rows: one per lane.  Long rows (RoPS, SHOT): 8 -- the live candidates of a row (after
+// pruning, typically k plus a few) are compacted into the slab, a full slab of 32 x 1.4 KB would leave room for only four
+// warps per SM, and this kernel lives on the number of gathers in flight, not on lanes.
+__host__ __device__ inline int rerank_slots(int dp) { return rerank_pitch_bytes(dp) <= 256 ? 32 : 8; }
+__host__ __device__ inline size_t rerank_warp_bytes(int dp) { return (size_t) (rerank_slots(dp) + 1) * rerank_pitch_bytes(dp); }   // + the query
+
+// Row metadata travels through a three-deep software pipeline so that no warp ever waits on a dependent chain of
+// global loads: the list lengths of row r+2 and the candidate indices of row r+1 are in flight while row r's slab is
+// being filled and consumed.
+struct RerankLens {   // stage 1: issued two rows ahead
+    int len;          // lanes 0..n_lists-1: appended entries of list `lane` (may exceed cap: overflow)
+    int qv;           // q_valid of the row
+    float thr;        // lanes 0..n_lists-1: final append threshold of list `lane` (+inf when values were not recorded)
+};
+struct RerankRow {    // stage 2: issued one row ahead
+    int total;        // candidates over all lists (capped lists)
+    int my_len;       // capped length of list `lane`
+    int j0;           // candidate of this lane in the first group of 32 (-1: none or pruned); range-checked, validity not yet
+    float thr;        // pruning threshold of the row
+    bool overflow, qv;
+};
+
+__device__ __forceinline__ RerankLens rerank_fetch_lens(size_t local, size_t n_rows, size_t row_begin,
+                                                        const int32_t *__restrict__ cand_cnt,
+                                                        const float *__restrict__ cand_thr,
+                                                        const uint8_t *__restrict__ q_valid, int n_lists, int lane) {
+    RerankLens m;
+    m.len = 0;
+    m.qv = 0;
+    m.thr = INFINITY;
+    if (local < n_rows) {
+        if (lane < n_lists) {
+            m.len = __ldg(cand_cnt + (size_t) lane * n_rows + local);
+            if (cand_thr) m.thr = __ldg(cand_thr + (size_t) lane * n_rows + local);
+        }
+        m.qv = q_valid[row_begin + local];
+    }
+    return m;
+}
+
+// position `c` of the concatenated (capped) lists -> (list, offset); warp-uniform walk, every lane takes part
+__device__ __forceinline__ void rerank_locate(int c, int my_len, int n_lists, int &l_sel, int &c_sel) {
+    bool placed = false;
+    l_sel = 0;
+    c_sel = c;
+    for (int l = 0; l < n_lists; ++l) {
+        const int cl = __shfl_sync(0xffffffffu, my_len, l);
+        if (!placed) {
+            if (c_sel < cl) { placed = true; l_sel = l; }
+            else c_sel -= cl;
+        }
+    }
+}
+
+// Every list's final threshold bounds the accumulator of every exact top-k member (DESIGN.md "Certified
+// candidates"), so an entry whose recorded value is not under the smallest of them cannot be one.
+__device__ __forceinline__ float rerank_row_thr(const RerankLens &m) {
+    float t = m.thr;
+    for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
+
+__device__ __forceinline__ RerankRow rerank_fetch_row(const RerankLens &m, size_t local, size_t n_rows,
+                                                      const int32_t *__restrict__ cand_idx,
+                                                      const float *__restrict__ cand_val, int n_lists, int cap, size_t nt,
+                                                      int lane) {
+    RerankRow r;
+    r.qv = m.qv != 0;
+    r.overflow = __any_sync(0xffffffffu, m.len > cap);
+    r.my_len = m.len > cap ? cap : m.len;
+    int t = r.my_len;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    r.total = t;
+    int l_sel, c_sel;
+    rerank_locate(lane, r.my_len, n_lists, l_sel, c_sel);
+    r.j0 = -1;
+    r.thr = rerank_row_thr(m);
+    if (local < n_rows && r.qv && !r.overflow && lane < r.total) {
+        const size_t e = ((size_t) l_sel * n_rows + local) * cap + c_sel;
+        const int j = __ldg(cand_idx + e);
+        const bool keep = cand_val ? __ldg(cand_val + e) < r.thr : true;
+        r.j0 = (j < 0 || (size_t) j >= nt || !keep) ? -1 : j;
+    }
+    return r;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(512)
 rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_valid, int dp, int dim,
               const float *__restrict__ t_f32, const uint8_t *__restrict__ t_valid, size_t nt, long long t_off,
               size_t row_begin, size_t n_rows, int k,
               const int32_t *__restrict__ cand_idx, const int32_t *__restrict__ cand_cnt, int n_lists, int cap,
+              const float *__restrict__ cand_val, const float *__restrict__ cand_thr,
               int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count,
               int32_t *__restrict__ flag_rows, int32_t *__restrict__ counters) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(128) uint8_t rr_smem[];
     __shared__ unsigned long long blk_cands;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *sq = smem + (size_t) warp * (dp + 32 * 33);
-    float *tile = sq + dp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int pitch = rerank_pitch_bytes(dp);
+    const uint32_t row_bytes = (uint32_t) dp * 4u;
+    // per-warp slab: [32 candidate rows][pitch] then the query row; the warps' mbarriers sit behind all slabs
+    uint8_t *slab = rr_smem + (size_t) warp * rerank_warp_bytes(dp);
+    const uint32_t slab_u = smem_addr(slab);
+    const int G = rerank_slots(dp);
+    const uint32_t sq_u = slab_u + (uint32_t) G * (uint32_t) pitch;
+    const float4 *sq4 = reinterpret_cast<const float4 *>(slab + (size_t) G * pitch);
+    const uint32_t bar = smem_addr(rr_smem + (size_t) n_warps * rerank_warp_bytes(dp)) + 8u * (uint32_t) warp;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (threadIdx.x == 0) blk_cands = 0ull;
     __syncthreads();
-    const size_t local = (size_t) blockIdx.x * kRerankWarps + warp;
+    uint32_t phase = 0;
     unsigned long long my_cands = 0ull;
-    if (local < n_rows) {
+    const size_t stride = (size_t) gridDim.x * n_warps;
+    size_t local = (size_t) blockIdx.x * n_warps + warp;
+    // pipeline prologue
+    RerankRow cur = rerank_fetch_row(rerank_fetch_lens(local, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane), local,
+                                     n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+    RerankLens nxt_lens = rerank_fetch_lens(local + stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+    for (; local < n_rows; local += stride) {
         const size_t qi = row_begin + local;
         int32_t *oi = idx + local * k;
         float *od = dist + local * k;
-        if (!q_valid[qi]) {   // non-finite query -> empty entry (reference include/matching.h:576)
-            for (int m = lane; m < k; m += 32) { oi[m] = -1; od[m] = 0.f; }
-            if (lane == 0) count[local] = 0;
-        } else {
-            for (int d = lane; d < dp; d += 32) sq[d] = q_f32[qi * (size_t) dp + d];
-            // list sizes (warp-uniform)
-            int total = 0;
-            bool overflow = false;
-            for (int l = 0; l < n_lists; ++l) {
-                int c = cand_cnt[(size_t) l * n_rows + local];
-                if (c > cap) { overflow = true; c = cap; }
-                total += c;
-            }
-            float ld[KMAX];
-            int li[KMAX];
+        const bool work = cur.qv && !cur.overflow;
+        float ld[KMAX];
+        int li[KMAX];
 #pragma unroll
-            for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; li[m] = INT_MAX; }
-            __syncwarp();
-            if (!overflow) {
-                my_cands = (unsigned long long) total;
-                for (int base = 0; base < total; base += 32) {
-                    int c = base + lane;
-                    int j = -1;
-                    if (c < total) {
-                        int l = 0;
-                        for (; l < n_lists; ++l) {
-                            int cl = min(cand_cnt[(size_t) l * n_rows + local], cap);
-                            if (c < cl) break;
-                            c -= cl;
-                        }
-                        j = cand_idx[((size_t) l * n_rows + local) * cap + c];
-                        if (j < 0 || (size_t) j >= nt || !t_valid[j]) j = -1;   // padding / invalid train rows (:661)
+        for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; li[m] = INT_MAX; }
+        bool first = true;   // the query row rides with the first pass that gathers anything
+        RerankRow nxt;
+        if (!work || cur.total == 0) {
+            nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+            nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+        } else {
+            my_cands += (unsigned long long) cur.total;
+            for (int base = 0; base < cur.total; base += 32) {
+                int j = cur.j0;
+                if (base > 0) {   // list positions beyond the first 32 (rare): fetched on the spot
+                    int l_sel, c_sel;
+                    rerank_locate(base + lane, cur.my_len, n_lists, l_sel, c_sel);
+                    j = -1;
+                    if (base + lane < cur.total) {
+                        const size_t e = ((size_t) l_sel * n_rows + local) * cap + c_sel;
+                        j = cand_idx[e];
+                        if (j < 0 || (size_t) j >= nt || (cand_val && !(cand_val[e] < cur.thr))) j = -1;
                     }
-                    const unsigned live = __ballot_sync(0xffffffffu, j >= 0);
-                    float s = 0.f;
-                    for (int d0 = 0; d0 < dp; d0 += 32) {
-                        const bool in = d0 + lane < dp;
-#pragma unroll 8
-                        for (int cc = 0; cc < 32; ++cc) {
-                            int jj = __shfl_sync(0xffffffffu, j, cc);
-                            if ((live >> cc) & 1u) {
-                                float v = in ? __ldg(t_f32 + (size_t) jj * dp + d0 + lane) : 0.f;
-                                tile[cc * 33 + lane] = v;
-                            }
-                        }
-                        __syncwarp();
-                        if (j >= 0) {
-                            const int ne = min(32, dp - d0);
-                            const float *tr = tile + lane * 33;
-                            for (int e = 0; e < ne; ++e) {
-                                float df = __fsub_rn(sq[d0 + e], tr[e]);
-                                s = __fadd_rn(s, __fmul_rn(df, df));
-                            }
-                        }
-                        __syncwarp();
+                }
+                // live candidates, compacted: the n-th live lane uses slab row n (mod G), G at a time
+                const unsigned live = __ballot_sync(0xffffffffu, j >= 0);
+                const int n_live = __popc(live);
+                const int slot = __popc(live & ((1u << lane) - 1u));
+                for (int p0 = 0; p0 < n_live; p0 += G) {
+                    const bool mine = j >= 0 && slot >= p0 && slot < p0 + G;
+                    // earlier (generic-proxy) reads of the slab are ordered before the asynchronous writes that follow
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (lane == 0) {
+                        const int n_pass = n_live - p0 < G ? n_live - p0 : G;
+                        const uint32_t tx = (uint32_t) (n_pass + (first ? 1 : 0)) * row_bytes;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+                        if (first) bulk_g2s(sq_u, q_f32 + qi * (size_t) dp, row_bytes, bar);
                     }
-                    if (j >= 0) {
+                    __syncwarp();   // the expectation is posted before any copy can complete
+                    const float4 *my4 = reinterpret_cast<const float4 *>(slab + (size_t) (slot - p0) * pitch);
+                    if (mine) bulk_g2s(slab_u + (uint32_t) (slot - p0) * (uint32_t) pitch, t_f32 + (size_t) j * dp, row_bytes, bar);
+                    if (first) {
+                        // metadata of the rows behind this one: their loads land while this row's slab fills
+                        nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+                        nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+                        first = false;
+                    }
+                    bar_wait_parity(bar, phase);
+                    phase ^= 1u;
+                    if (mine) {
+                        float s = 0.f;
+#pragma unroll 4
+                        for (int d4 = 0; d4 < dp / 4; ++d4) {
+                            const float4 a = sq4[d4], b = my4[d4];
+                            float df = __fsub_rn(a.x, b.x);
+                            s = __fadd_rn(s, __fmul_rn(df, df));
+                            df = __fsub_rn(a.y, b.y);
+                            s = __fadd_rn(s, __fmul_rn(df, df));
+                            df = __fsub_rn(a.z, b.z);
+                            s = __fadd_rn(s, __fmul_rn(df, df));
+                            df = __fsub_rn(a.w, b.w);
+                            s = __fadd_rn(s, __fmul_rn(df, df));
+                        }
                         float cd = __fsqrt_rn(s);
                         int ci = j;
-                        if (lex_less(cd, ci, ld[KMAX - 1], li[KMAX - 1])) {
+                        // invalid (non-finite) train rows are never candidates (reference :661); only such a row -- or an
+                        // overflowing sum -- can give a non-finite distance, so validity is looked up on that path alone
+                        const bool ok = cd < INFINITY || t_valid[j] != 0;
+                        if (ok && lex_less(cd, ci, ld[KMAX - 1], li[KMAX - 1])) {
 #pragma unroll
                             for (int m = 0; m < KMAX; ++m) {
                                 if (lex_less(cd, ci, ld[m], li[m])) {
@@ -235,10 +511,17 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
-            // k rounds of warp arg-min over the per-lane list heads
-            int head = 0, found = 0;
+            if (first) {   // every candidate was pruned or invalid: nothing was gathered
+                nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+                nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+            }
+        }
+        // k rounds of warp arg-min over the per-lane list heads
+        int head = 0, found = 0;
+        if (work) {
             for (int round = 0; round < k; ++round) {
                 float hd = INFINITY;
                 int hi = INT_MAX;
@@ -257,15 +540,17 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
                 if (lane == 0) { oi[round] = (int32_t) (wi + t_off); od[round] = wd; }
                 found = round + 1;
             }
-            for (int m = found + lane; m < k; m += 32) { oi[m] = -1; od[m] = 0.f; }
-            if (lane == 0) {
-                count[local] = found;
-                if (overflow) {
-                    int pos = atomicAdd(counters, 1);
-                    flag_rows[pos] = (int32_t) local;
-                }
+        }
+        // a non-finite query has an empty entry (reference include/matching.h:576); overflowed rows are redone exactly
+        for (int m = found + lane; m < k; m += 32) { oi[m] = -1; od[m] = 0.f; }
+        if (lane == 0) {
+            count[local] = found;
+            if (cur.qv && cur.overflow) {
+                int pos = atomicAdd(counters, 1);
+                flag_rows[pos] = (int32_t) local;
             }
         }
+        cur = nxt;
     }
     if (lane == 0 && my_cands) atomicAdd(&blk_cands, my_cands);
     __syncthreads();
@@ -277,11 +562,21 @@ template <int KMAX>
 cudaError_t launch_exact_t(const float *q_f32, const uint8_t *q_valid, int dp, int dim, const float *t_f32,
                            const uint8_t *t_valid, size_t nt, int64_t t_off, size_t row_begin, size_t n_rows,
                            const int32_t *row_list, const int32_t *row_list_count, int k, int32_t *idx, float *dist,
-                           int32_t *count, int blocks, cudaStream_t st) {
+                           int32_t *count, int blocks, int split_blocks, int32_t *part_i, float *part_d,
+                           unsigned int *done, cudaStream_t st) {
     size_t smem = sizeof(float) * dp + (sizeof(float) + 2 * sizeof(int)) * (kExactThreads / 32);
+    const bool split = row_list && split_blocks > 0 && part_i && part_d && done;
+    if (split) {
+        exact_rows_split_kernel<KMAX><<<split_blocks, kExactThreads, smem, st>>>(
+            q_f32, dp, t_f32, t_valid, nt, (long long) t_off, row_begin, row_list, row_list_count, k, part_i, part_d, done,
+            idx, dist, count);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     exact_rows_kernel<KMAX><<<blocks, kExactThreads, smem, st>>>(q_f32, q_valid, dp, dim, t_f32, t_valid, nt,
                                                                  (long long) t_off, row_begin, n_rows, row_list,
-                                                                 row_list_count, k, idx, dist, count);
+                                                                 row_list_count, k, idx, dist, count,
+                                                                 split ? kSplitMaxRows : 0);
     return cudaGetLastError();
 }
 
@@ -290,12 +585,14 @@ cudaError_t launch_exact_t(const float *q_f32, const uint8_t *q_valid, int dp, i
 cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp, int dim,
                               const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
                               size_t row_begin, size_t n_rows, const int32_t *row_list, const int32_t *row_list_count,
-                              int k, int32_t *idx, float *dist, int32_t *count, int max_blocks, cudaStream_t st) {
+                              int k, int32_t *idx, float *dist, int32_t *count, int max_blocks, int split_blocks,
+                              int32_t *part_i, float *part_d, unsigned int *done, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     int blocks = (int) (n_rows < (size_t) max_blocks ? n_rows : (size_t) max_blocks);
 #define B200M_EXACT_CASE(K)                                                                                   \
     return launch_exact_t<K>(q_f32, q_valid, dp, dim, t_f32, t_valid, nt, t_index_offset, row_begin, n_rows,  \
-                             row_list, row_list_count, k, idx, dist, count, blocks, st)
+                             row_list, row_list_count, k, idx, dist, count, blocks, split_blocks, part_i, part_d, \
+                             done, st)
     if (k <= 1) B200M_EXACT_CASE(1);
     if (k <= 2) B200M_EXACT_CASE(2);
     if (k <= 4) B200M_EXACT_CASE(4);
@@ -305,26 +602,36 @@ cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp
 #undef B200M_EXACT_CASE
 }
 
+size_t exact_split_ws_entries(int split_blocks, int k) { return (size_t) kSplitMaxRows * (size_t) split_blocks * (size_t) k; }
+int exact_split_max_rows() { return kSplitMaxRows; }
+
 cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, int dim,
                           const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
                           size_t row_begin, size_t n_rows, int k,
                           const int32_t *cand_idx, const int32_t *cand_cnt, int n_lists, int cap,
+                          const float *cand_val, const float *cand_thr,
                           int32_t *idx, float *dist, int32_t *count,
-                          int32_t *flag_rows, int32_t *counters, cudaStream_t st) {
+                          int32_t *flag_rows, int32_t *counters, int sm_count, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     if (n_lists > kMaxLists) return cudaErrorInvalidValue;
-    unsigned blocks = (unsigned) ((n_rows + kRerankWarps - 1) / kRerankWarps);
-    size_t smem = sizeof(float) * (size_t) (dp + 32 * 33) * kRerankWarps;
+    // one CTA per SM holding as many warps (each with its own gather slab) as shared memory allows
+    const size_t per_warp = rerank_warp_bytes(dp) + 8;
+    int warps = (int) ((220 * 1024) / per_warp);
+    if (warps > 16) warps = 16;
+    if (warps < 1) return cudaErrorInvalidValue;   // dp <= 1024 needs at most 136 KB per warp
+    const size_t smem = (size_t) warps * per_warp;
+    size_t want = (n_rows + warps - 1) / warps;
+    // small descriptors leave room for two CTAs per SM
+    const size_t max_blocks = (size_t) sm_count * (smem <= 100 * 1024 ? 2 : 1);
+    unsigned blocks = (unsigned) (want < max_blocks ? want : max_blocks);
 #define B200M_RERANK_CASE(K)                                                                                    \
     do {                                                                                                        \
-        if (smem > 48 * 1024) {                                                                                 \
-            cudaError_t e = cudaFuncSetAttribute(rerank_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 (int) smem);                                                   \
-            if (e != cudaSuccess) return e;                                                                     \
-        }                                                                                                       \
-        rerank_kernel<K><<<blocks, kRerankWarps * 32, smem, st>>>(                                              \
+        cudaError_t e = cudaFuncSetAttribute(rerank_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                             (int) smem);                                                       \
+        if (e != cudaSuccess) return e;                                                                         \
+        rerank_kernel<K><<<blocks, warps * 32, smem, st>>>(                                                     \
             q_f32, q_valid, dp, dim, t_f32, t_valid, nt, (long long) t_index_offset, row_begin, n_rows, k,      \
-            cand_idx, cand_cnt, n_lists, cap, idx, dist, count, flag_rows, counters);                           \
+            cand_idx, cand_cnt, n_lists, cap, cand_val, cand_thr, idx, dist, count, flag_rows, counters);       \
         return cudaGetLastError();                                                                              \
     } while (0)
     if (k <= 1) B200M_RERANK_CASE(1);

@@ -58,6 +58,8 @@ struct b200m_ctx {
     Side side[2];
     TcPrep prep;
     DevBuf ws_cand_idx, ws_cand_cnt, ws_flag_rows, ws_counters, ws_scan, ws_out, ws_misc;
+    DevBuf ws_part_i, ws_part_d, ws_done, ws_cand_val, ws_cand_thr;
+    bool done_init = false;
     DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr, ws_totals;
     bool totals_init = false;
     void *tmap_cache = nullptr;
@@ -108,14 +110,20 @@ cudaError_t launch_tc_prepare(b200m_ctx *ctx);   // centre/scale + FP16 operand 
 cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp, int dim,
                               const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
                               size_t row_begin, size_t n_rows, const int32_t *row_list, const int32_t *row_list_count,
-                              int k, int32_t *idx, float *dist, int32_t *count, int max_blocks, cudaStream_t st);
+                              int k, int32_t *idx, float *dist, int32_t *count, int max_blocks,
+                              // few flagged rows (row_list given): split_blocks CTAs share every row; workspace of
+                              // exact_split_ws_entries() int32 + float entries and exact_split_max_rows() zeroed counters
+                              int split_blocks, int32_t *part_i, float *part_d, unsigned int *done, cudaStream_t st);
+size_t exact_split_ws_entries(int split_blocks, int k);
+int exact_split_max_rows();
 cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, int dim,
                           const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
                           size_t row_begin, size_t n_rows, int k,
                           const int32_t *cand_idx, const int32_t *cand_cnt, int n_lists, int cap,
+                          const float *cand_val, const float *cand_thr /* both null: no pruning */,
                           int32_t *idx, float *dist, int32_t *count,
                           int32_t *flag_rows, int32_t *counters /*[0]=flagged rows, [1..2]=candidate pairs (u64)*/,
-                          cudaStream_t st);
+                          int sm_count, cudaStream_t st);
 
 // filter.cu
 cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, size_t row_begin, size_t n_rows,
@@ -133,7 +141,8 @@ cudaError_t launch_merge(int k, int n_lists, size_t nq, const int32_t *idx_in, c
 // candidates_tc.cu
 // Fills ws_cand_idx [n_lists][n_rows][cap] and ws_cand_cnt [n_lists][n_rows] (entries appended per list; a
 // count above cap marks an overflowed list).  dump != nullptr: single tile, raw accumulators to dump[128][256].
+// *has_values_out = 1: ws_cand_val [n_lists][n_rows][cap] and ws_cand_thr [n_lists][n_rows] are filled too.
 int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
-                  int *n_lists_out, int *cap_out, float *dump, size_t dump_t_tile);
+                  int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile);
 bool tc_supported(const b200m_ctx *ctx, int dim, int k);
 void tc_release(b200m_ctx *ctx);

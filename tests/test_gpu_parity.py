@@ -311,3 +311,21 @@ def test_candidate_kernel_modes(monkeypatch, mode, epi, desc, nq, nt, k):
         ctx.upload(1, tgt, dim)
         _same(ctx.knn(k, 0), orc.knn(_dense(src, dim), _dense(tgt, dim), k))
         _same(ctx.knn(k, 1), orc.knn(_dense(tgt, dim), _dense(src, dim), k))
+
+
+@pytest.mark.parametrize("desc,nq,nt,k,regime", [("fpfh", 200, 5000, 2, "few"), ("shot", 150, 3000, 5, "few"),
+                                                 ("fpfh", 2000, 5000, 2, "many"), ("rops", 700, 2500, 3, "many")])
+def test_overflowed_candidate_lists_fall_back_exactly(desc, nq, nt, k, regime):
+    """A candidate list that overflows its slots sends the row to the exact CUDA-core path: split over the whole grid
+    when few rows overflow (<= 256), one CTA per row when many do.  cand_cap = k makes every row overflow."""
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    with M.Context(0) as ctx:
+        ctx.set_profiling(True)
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        ctx.reset_stats()
+        got = ctx.knn(k, 0, cand_cap=k)
+        flagged = ctx.stats()["rows_flagged"]
+        assert (0 < flagged <= 256) if regime == "few" else flagged > 256
+        _same(got, orc.knn(_dense(src, dim), _dense(tgt, dim), k))
+        _same(ctx.knn(k, 0, cand_cap=k), got)   # the split kernel's completion counters are reusable

@@ -1,6 +1,6 @@
-for cl in 1 2; do
-for d in 0 1 32 256; do
-    B200M_TC_CLUSTER=$cl B200M_TC_DEBUG=$d timeout 300 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_c2_cl${cl}_dbg$d.json 2> gpurun_out/n_c2_cl${cl}_dbg$d.err; echo c2 cl$cl dbg$d rc=$?
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; echo tests rc=$?
+tail -15 gpurun_out/t_all.log
+for w in c2 c3; do
+  timeout 300 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_$w.json 2> gpurun_out/n_$w.err; echo $w rc=$?
 done
-done
-python tools/bench_summary.py gpurun_out/n_*.json | grep -v "^  "
+python tools/bench_summary.py gpurun_out/n_*.json
