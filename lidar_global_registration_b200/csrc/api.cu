@@ -120,6 +120,7 @@ int b200m_create(b200m_ctx **out, int device) {
         if (c == 1 || c == 2 || c == 4) { ctx->tc_cluster = c; ctx->tc_pair = 0; }
     }
     if (const char *e = getenv("B200M_TC_DEBUG")) ctx->tc_debug = atoi(e);
+    if (const char *e = getenv("B200M_TC_SPLITS")) ctx->tc_splits = atoi(e);
     if (const char *e = getenv("B200M_TC_MODE")) {
         if (!strcmp(e, "mcast")) ctx->tc_pair = 0;
         if (!strcmp(e, "pair")) ctx->tc_pair = 1;
@@ -134,7 +135,7 @@ void b200m_destroy(b200m_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < 2; ++s) {
         Side &sd = ctx->side[s];
-        sd.staging.release(); sd.f32.release(); sd.valid.release();
+        sd.staging.release(); sd.f32.release(); sd.valid.release(); sd.stats.release();
         sd.op_query.release(); sd.op_train.release(); sd.norm16.release();
         ctx->ws_thr[s].release();
     }
@@ -215,8 +216,10 @@ static int upload_common(b200m_ctx *ctx, int side, const float *device_aos, size
     if (n == 0) return 0;
     CK(sd.f32.reserve(sizeof(float) * n * (size_t) sd.dp));
     CK(sd.valid.reserve(n));
+    CK(sd.stats.reserve(pack_stats_bytes(ctx->sm_count, sd.dp)));
     StatTimer t(ctx, &ctx->stats.ms_pack);
-    CK(launch_pack_f32(device_aos, n, stride_bytes, dim, sd.dp, sd.f32.as<float>(), sd.valid.as<uint8_t>(), ctx->stream));
+    CK(launch_pack_f32(device_aos, n, stride_bytes, dim, sd.dp, sd.f32.as<float>(), sd.valid.as<uint8_t>(),
+                       sd.stats.as<float>(), ctx->sm_count, ctx->stream));
     ctx->stats.launches += 1;
     t.stop();
     return 0;

@@ -818,12 +818,20 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.n_ttiles = (int) (t.n_pad / B200M_TILE_N);
     int n_splits = 1;
     if (!dump) {
-        // aim for >= 3 waves of CTAs; every split keeps at least 8 train tiles
-        int want = (3 * ctx->sm_count + n_qtiles - 1) / n_qtiles;
-        int max_by_tiles = p.n_ttiles / 8 > 0 ? p.n_ttiles / 8 : 1;
-        n_splits = want < 1 ? 1 : want;
-        if (n_splits > max_by_tiles) n_splits = max_by_tiles;
-        if (n_splits > kMaxLists) n_splits = kMaxLists;
+        // Train splits balance the waves of CTAs: a (cluster of) query tile(s) is a work unit that occupies its SMs for
+        // the whole sweep, so e.g. 245 units on 74 cluster slots run 4 waves at 83 % -- three splits run 10 waves at 99 %.
+        // Each split costs a CTA prologue (about 4 tiles' worth) and a candidate list of its own (about 2 % more work
+        // downstream), and keeps at least 8 train tiles.
+        const long long units = (n_qtiles + cluster - 1) / cluster, slots = ctx->sm_count / cluster > 0 ? ctx->sm_count / cluster : 1;
+        int max_splits = p.n_ttiles / 8 > 0 ? p.n_ttiles / 8 : 1;
+        if (max_splits > kMaxLists) max_splits = kMaxLists;
+        double best = 0;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const long long waves = (units * sp + slots - 1) / slots;
+            const double cost = (double) waves * ((p.n_ttiles + sp - 1) / sp + 4) * (1.0 + 0.02 * (sp - 1));
+            if (sp == 1 || cost < best) { best = cost; n_splits = sp; }
+        }
+        if (ctx->tc_splits > 0) n_splits = ctx->tc_splits < max_splits ? ctx->tc_splits : max_splits;   // B200M_TC_SPLITS: tuning override
     }
     p.tiles_per_split = (p.n_ttiles + n_splits - 1) / n_splits;
     n_splits = (p.n_ttiles + p.tiles_per_split - 1) / p.tiles_per_split;

@@ -34,6 +34,7 @@ struct Side {
     DevBuf staging;        // raw AoS as uploaded from the host
     DevBuf f32;            // [n][dp] dense FP32, zero padded columns
     DevBuf valid;          // [n] uint8
+    DevBuf stats;          // per-CTA column statistics of the pack kernel (see pack.cu)
     DevBuf op_query;       // [n_pad][kp] fp16: -2*x16, 1,1,1, 0...
     DevBuf op_train;       // [n_pad][kp] fp16:  x16, nb_hi, nb_mid, nb_lo, 0...
     DevBuf norm16;         // [n_pad] float: |x16|^2 in scaled units
@@ -64,6 +65,7 @@ struct b200m_ctx {
     bool totals_init = false;
     void *tmap_cache = nullptr;
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
+    int tc_splits = 0;     // B200M_TC_SPLITS: 0 = chosen per launch (wave balance); > 0 forces the number of train splits
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
     int tc_pair = 1;       // 1 = CTA-pair (cta_group::2) candidate kernel; 0 = cta_group::1 + multicast (B200M_TC_MODE=mcast)
     bool profiling = false;
@@ -102,8 +104,11 @@ struct StatTimer {
 
 // ---- kernel launchers (one translation unit each) ---------------------------
 // pack.cu
+// dense FP32 copy + validity + per-CTA column statistics (sum, min, max over valid rows) into `stats`
+// (pack_stats_bytes() bytes), which launch_tc_prepare turns into the common centre and FP16 scale
 cudaError_t launch_pack_f32(const float *aos, size_t n, size_t stride_bytes, int dim, int dp,
-                            float *f32, uint8_t *valid, cudaStream_t st);
+                            float *f32, uint8_t *valid, float *stats, int sm_count, cudaStream_t st);
+size_t pack_stats_bytes(int sm_count, int dp);
 cudaError_t launch_tc_prepare(b200m_ctx *ctx);   // centre/scale + FP16 operand tiles for both sides
 
 // exact.cu

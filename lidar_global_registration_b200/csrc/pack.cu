@@ -21,110 +21,198 @@
 
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kPackWarps = 16;       // warps per CTA of the persistent pack kernel
+constexpr int kWarpsPerBlock = 8;    // operand pack: one warp per row
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// column statistics of one CTA: [sum | min | max][dp] then the number of valid rows
+__host__ __device__ inline size_t stats_floats(int dp) { return (size_t) 3 * dp + 1; }
+
+// One warp per row, persistent over the rows.  NI = ceil(dp / 32) values per lane stay in registers: the row is dense-
+// copied, its validity decided (every value finite), and -- for valid rows only -- folded into the lane's running
+// column sum / min / max, from which tc_prepare derives the common centre and the FP16 scale without reading the data
+// again.
+template <int NI>
+__global__ void __launch_bounds__(kPackWarps * 32)
 pack_f32_kernel(const float *__restrict__ aos, size_t n, size_t stride_floats, int dim, int dp,
-                float *__restrict__ f32, uint8_t *__restrict__ valid) {
-    const int lane = threadIdx.x & 31;
-    size_t row = (size_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= n) return;
-    const float *src = aos + row * stride_floats;
-    float *dst = f32 + row * (size_t) dp;
-    bool ok = true;
-    for (int d = lane; d < dp; d += 32) {
-        float v = 0.f;
-        if (d < dim) {
-            v = __ldg(src + d);
-            ok = ok && isfinite(v);
+                float *__restrict__ f32, uint8_t *__restrict__ valid, float *__restrict__ stats) {
+    extern __shared__ float sh[];   // [3][dp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float sum[NI], mn[NI], mx[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { sum[i] = 0.f; mn[i] = INFINITY; mx[i] = -INFINITY; }
+    float cnt = 0.f;
+    for (size_t row = (size_t) blockIdx.x * kPackWarps + warp; row < n; row += (size_t) gridDim.x * kPackWarps) {
+        const float *src = aos + row * stride_floats;
+        float *dst = f32 + row * (size_t) dp;
+        float v[NI];
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int d = lane + 32 * i;
+            v[i] = d < dim ? __ldg(src + d) : 0.f;
+            ok = ok && isfinite(v[i]);
         }
-        dst[d] = v;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int d = lane + 32 * i;
+            if (d < dp) dst[d] = v[i];
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) valid[row] = ok ? 1 : 0;
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                sum[i] += v[i];
+                mn[i] = fminf(mn[i], v[i]);
+                mx[i] = fmaxf(mx[i], v[i]);
+            }
+            cnt += 1.f;
+        }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) valid[row] = ok ? 1 : 0;
+    // fold the warps of the CTA, one after the other
+    for (int d = threadIdx.x; d < dp; d += blockDim.x) { sh[d] = 0.f; sh[dp + d] = INFINITY; sh[2 * dp + d] = -INFINITY; }
+    __shared__ float sh_cnt;
+    if (threadIdx.x == 0) sh_cnt = 0.f;
+    __syncthreads();
+    for (int w = 0; w < kPackWarps; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int d = lane + 32 * i;
+                if (d < dp) {
+                    sh[d] += sum[i];
+                    sh[dp + d] = fminf(sh[dp + d], mn[i]);
+                    sh[2 * dp + d] = fmaxf(sh[2 * dp + d], mx[i]);
+                }
+            }
+            if (lane == 0) sh_cnt += cnt;
+        }
+        __syncthreads();
+    }
+    float *out = stats + (size_t) blockIdx.x * stats_floats(dp);
+    for (int d = threadIdx.x; d < 3 * dp; d += blockDim.x) out[d] = sh[d];
+    if (threadIdx.x == 0) out[3 * dp] = sh_cnt;
 }
 
-// ---- column sums over valid rows (for the common centre) --------------------
-// grid.x blocks stride over rows; thread t owns columns t, t+256, ... (<= 4 of them).
+// device-resident results of the statistics pass (read by the operand pack; copied to the host once, afterwards)
+struct PrepDev {
+    int maxabs_bits;        // max |x - mean| over the valid rows of both sides, as the bits of a non-negative float
+    int max_norm_bits[2];   // max |x16| per side, likewise (atomicMax)
+    int pad;
+};
+
+// power of two s with maxabs*s in (0.5, 1]; all-equal data (maxabs == 0) keeps s = 1
+__host__ __device__ inline float scale_for(float maxabs) {
+    float scale = 1.f;
+    if (maxabs > 0.f && isfinite(maxabs)) {
+        int ex;
+        float fr = frexpf(maxabs, &ex);   // maxabs = fr * 2^ex, fr in [0.5, 1)
+        if (fr == 0.5f) ex -= 1;          // exactly a power of two -> map to 1.0
+        scale = ldexpf(1.f, -ex);
+    }
+    return scale;
+}
+
+// Combine the per-CTA column statistics of both sides: CTA b owns columns 32b..32b+31, its eight warps each fold
+// every eighth partial; -> mean[dp] and (atomicMax) the largest centred magnitude.
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float *__restrict__ f32, const uint8_t *__restrict__ valid, size_t n, int dp,
-              double *__restrict__ partial /*[grid][dp+1]*/) {
-    double acc[4] = {0, 0, 0, 0};
-    double cnt = 0;
-    for (size_t r = blockIdx.x; r < n; r += gridDim.x) {
-        if (!valid[r]) continue;
-        const float *row = f32 + r * (size_t) dp;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int d = threadIdx.x + 256 * c;
-            if (d < dp) acc[c] += (double) row[d];
-        }
-        cnt += 1.0;
-    }
-    double *out = partial + (size_t) blockIdx.x * (dp + 1);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        int d = threadIdx.x + 256 * c;
-        if (d < dp) out[d] = acc[c];
-    }
-    if (threadIdx.x == 0) out[dp] = cnt;
-}
-
-__global__ void mean_kernel(const double *__restrict__ pa, int ga, const double *__restrict__ pb, int gb,
-                            int dp, float *__restrict__ mean) {
-    int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= dp) return;
+prep_finalize_kernel(const float *__restrict__ sa, int ga, const float *__restrict__ sb, int gb, int dp, int dim,
+                     float *__restrict__ mean, PrepDev *__restrict__ out) {
+    __shared__ double sh_s[8][32], sh_c[8];
+    __shared__ float sh_lo[8][32], sh_hi[8][32];
+    const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + col;
+    const size_t sf = stats_floats(dp);
     double s = 0, c = 0;
-    for (int g = 0; g < ga; ++g) { s += pa[(size_t) g * (dp + 1) + d]; c += pa[(size_t) g * (dp + 1) + dp]; }
-    for (int g = 0; g < gb; ++g) { s += pb[(size_t) g * (dp + 1) + d]; c += pb[(size_t) g * (dp + 1) + dp]; }
-    mean[d] = c > 0 ? (float) (s / c) : 0.f;
-}
-
-// max |x - mean| over valid rows -> bits of a non-negative float, atomicMax as int
-__global__ void __launch_bounds__(256)
-maxabs_kernel(const float *__restrict__ f32, const uint8_t *__restrict__ valid, size_t n, int dp, int dim,
-              const float *__restrict__ mean, int *__restrict__ out_bits) {
-    float m = 0.f;
-    for (size_t r = blockIdx.x; r < n; r += gridDim.x) {
-        if (!valid[r]) continue;
-        const float *row = f32 + r * (size_t) dp;
-        for (int d = threadIdx.x; d < dim; d += 256) m = fmaxf(m, fabsf(row[d] - mean[d]));
+    float lo = INFINITY, hi = -INFINITY;
+    for (int side = 0; side < 2; ++side) {
+        const float *st = side ? sb : sa;
+        const int g_n = side ? gb : ga;
+        for (int g = slice; g < g_n; g += 8) {
+            const float *row = st + (size_t) g * sf;
+            c += (double) row[3 * dp];
+            if (d < dp) {
+                s += (double) row[d];
+                lo = fminf(lo, row[dp + d]);
+                hi = fmaxf(hi, row[2 * dp + d]);
+            }
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_int(m));
+    sh_s[slice][col] = s;
+    sh_lo[slice][col] = lo;
+    sh_hi[slice][col] = hi;
+    if (col == 0) sh_c[slice] = c;
+    __syncthreads();
+    if (slice == 0 && d < dp) {
+        for (int w = 1; w < 8; ++w) {
+            s += sh_s[w][col];
+            lo = fminf(lo, sh_lo[w][col]);
+            hi = fmaxf(hi, sh_hi[w][col]);
+        }
+        double cc = 0;
+        for (int w = 0; w < 8; ++w) cc += sh_c[w];
+        const float mu = cc > 0 ? (float) (s / cc) : 0.f;
+        mean[d] = mu;
+        if (d < dim && cc > 0) {
+            const float e = fabsf(fmaxf(hi - mu, mu - lo));   // NaN keeps its (positive) bit pattern: larger than +inf as an int
+            atomicMax(&out->maxabs_bits, __float_as_int(e));
+        }
+    }
 }
 
-// One warp per (padded) row: FP16 operand rows + |x16|^2.
+// One warp per (padded) row: FP16 operand rows + |x16|^2.  A lane converts four consecutive values at a time
+// (128-bit loads, 64-bit stores).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pack_operands_kernel(const float *__restrict__ f32, const uint8_t *__restrict__ valid, size_t n, size_t n_pad,
-                     int dim, int dp, int kp, const float *__restrict__ mean, float scale,
-                     __half *__restrict__ op_query, __half *__restrict__ op_train, float *__restrict__ norm16,
-                     int *__restrict__ max_norm_bits) {
+                     int dim, int dp, int kp, const float *__restrict__ mean, PrepDev *__restrict__ prep, int side,
+                     __half *__restrict__ op_query, __half *__restrict__ op_train, float *__restrict__ norm16) {
     const int lane = threadIdx.x & 31;
     size_t row = (size_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= n_pad) return;
+    const float scale = scale_for(__int_as_float(prep->maxabs_bits));
     const bool ok = row < n && valid[row];
     __half *oq = op_query + row * (size_t) kp;
     __half *ot = op_train + row * (size_t) kp;
+    const float *src = f32 + row * (size_t) dp;
     double nrm = 0.0;
-    for (int d = lane; d < kp; d += 32) {
-        __half hq = __float2half_rn(0.f), ht = hq;
-        if (d < dim) {
-            if (ok) {
-                float x = (f32[row * (size_t) dp + d] - mean[d]) * scale;
-                ht = __float2half_rn(x);
-                float xf = __half2float(ht);
-                hq = __float2half_rn(-2.f * xf);   // exact: |x| <= 1, power-of-two factor
-                nrm += (double) xf * (double) xf;
-            }
-        } else if (d < dim + B200M_AUG_COLS) {
-            hq = __float2half_rn(1.f);             // picks up the three norm pieces of the train row
+    // the descriptor columns (dp is a multiple of 4, kp of 64; columns dim..dp-1 of f32 are zero): every load of the
+    // row is issued before the first conversion (kp <= 640: at most five 128-column sweeps)
+    float4 v[5], mu[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int d0 = 4 * lane + 128 * i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mu[i] = v[i];
+        if (ok && d0 < dp) {
+            v[i] = __ldg(reinterpret_cast<const float4 *>(src + d0));
+            mu[i] = __ldg(reinterpret_cast<const float4 *>(mean + d0));
         }
-        oq[d] = hq;
-        if (d < dim) ot[d] = ht;
-        else if (d >= dim + B200M_AUG_COLS) ot[d] = __float2half_rn(0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int d0 = 4 * lane + 128 * i;
+        if (d0 >= kp) break;
+        const float x[4] = {(v[i].x - mu[i].x) * scale, (v[i].y - mu[i].y) * scale, (v[i].z - mu[i].z) * scale,
+                            (v[i].w - mu[i].w) * scale};
+        __half ht[4], hq[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int d = d0 + e;
+            if (d < dim) {
+                ht[e] = __float2half_rn(x[e]);
+                const float xf = __half2float(ht[e]);
+                hq[e] = __float2half_rn(-2.f * xf);   // exact: |x| <= 1, power-of-two factor
+                nrm += (double) xf * (double) xf;
+            } else {
+                ht[e] = __float2half_rn(0.f);   // the three norm columns are filled in below
+                hq[e] = __float2half_rn(d < dim + B200M_AUG_COLS ? 1.f : 0.f);   // 1s pick up the norm pieces of the train row
+            }
+        }
+        *reinterpret_cast<uint2 *>(oq + d0) = *reinterpret_cast<const uint2 *>(hq);
+        *reinterpret_cast<uint2 *>(ot + d0) = *reinterpret_cast<const uint2 *>(ht);
     }
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    __syncwarp();
     if (lane == 0) {
         float nf = ok ? (float) nrm : 0.f;
         norm16[row] = nf;
@@ -137,17 +225,29 @@ pack_operands_kernel(const float *__restrict__ f32, const uint8_t *__restrict__ 
         ot[dim + 0] = hi;
         ot[dim + 1] = mid;
         ot[dim + 2] = lo;
-        if (ok) atomicMax(max_norm_bits, __float_as_int(sqrtf(nf)));
+        if (ok) atomicMax(&prep->max_norm_bits[side], __float_as_int(sqrtf(nf)));
     }
 }
 
 }  // namespace
 
+int pack_stats_blocks(int sm_count) { return sm_count * 2; }
+size_t pack_stats_bytes(int sm_count, int dp) { return sizeof(float) * (size_t) pack_stats_blocks(sm_count) * stats_floats(dp); }
+
 cudaError_t launch_pack_f32(const float *aos, size_t n, size_t stride_bytes, int dim, int dp,
-                            float *f32, uint8_t *valid, cudaStream_t st) {
+                            float *f32, uint8_t *valid, float *stats, int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    unsigned blocks = (unsigned) ((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    pack_f32_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(aos, n, stride_bytes / 4, dim, dp, f32, valid);
+    const unsigned blocks = (unsigned) pack_stats_blocks(sm_count);
+    const size_t smem = sizeof(float) * 3 * (size_t) dp;
+    const int ni = (dp + 31) / 32;
+#define B200M_PACK_CASE(NI)                                                                                          \
+    pack_f32_kernel<NI><<<blocks, kPackWarps * 32, smem, st>>>(aos, n, stride_bytes / 4, dim, dp, f32, valid, stats)
+    if (ni <= 2) B200M_PACK_CASE(2);
+    else if (ni <= 5) B200M_PACK_CASE(5);
+    else if (ni <= 11) B200M_PACK_CASE(11);
+    else if (ni <= 16) B200M_PACK_CASE(16);
+    else B200M_PACK_CASE(32);
+#undef B200M_PACK_CASE
     return cudaGetLastError();
 }
 
@@ -156,39 +256,15 @@ cudaError_t launch_tc_prepare(b200m_ctx *ctx) {
     TcPrep &pr = ctx->prep;
     cudaStream_t st = ctx->stream;
     const int dp = a.dp, dim = a.dim;
-    const int grid = ctx->sm_count * 4;
     cudaError_t e;
-    size_t part_bytes = sizeof(double) * (size_t) grid * (dp + 1);
-    if ((e = pr.red.reserve(2 * part_bytes + 64)) != cudaSuccess) return e;
+    if ((e = pr.red.reserve(sizeof(PrepDev))) != cudaSuccess) return e;
     if ((e = pr.mean.reserve(sizeof(float) * dp)) != cudaSuccess) return e;
-    double *pa = pr.red.as<double>();
-    double *pb = (double *) ((char *) pr.red.p + part_bytes);
-    int *scal = (int *) ((char *) pr.red.p + 2 * part_bytes);   // [0]=maxabs bits, [1],[2]=max norm bits per side
-    if ((e = cudaMemsetAsync(scal, 0, 64, st)) != cudaSuccess) return e;
-    int ga = a.n ? grid : 0, gb = b.n ? grid : 0;
-    if (ga) colsum_kernel<<<ga, 256, 0, st>>>(a.f32.as<float>(), a.valid.as<uint8_t>(), a.n, dp, pa);
-    if (gb) colsum_kernel<<<gb, 256, 0, st>>>(b.f32.as<float>(), b.valid.as<uint8_t>(), b.n, dp, pb);
-    mean_kernel<<<(dp + 127) / 128, 128, 0, st>>>(pa, ga, pb, gb, dp, pr.mean.as<float>());
-    if (ga) maxabs_kernel<<<ga, 256, 0, st>>>(a.f32.as<float>(), a.valid.as<uint8_t>(), a.n, dp, dim, pr.mean.as<float>(), scal);
-    if (gb) maxabs_kernel<<<gb, 256, 0, st>>>(b.f32.as<float>(), b.valid.as<uint8_t>(), b.n, dp, dim, pr.mean.as<float>(), scal);
-    ctx->stats.launches += (ga ? 2 : 0) + (gb ? 2 : 0) + 1;
-    int h[4] = {0, 0, 0, 0};
-    if ((e = cudaMemcpyAsync(h, scal, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    float maxabs;
-    memcpy(&maxabs, &h[0], 4);
-    // power of two s with maxabs*s in (0.5, 1]; all-equal data (maxabs == 0) keeps s = 1
-    float scale = 1.f;
-    if (maxabs > 0.f && isfinite(maxabs)) {
-        int ex;
-        float fr = frexpf(maxabs, &ex);   // maxabs = fr * 2^ex, fr in [0.5, 1)
-        if (fr == 0.5f) ex -= 1;          // exactly a power of two -> map to 1.0
-        scale = ldexpf(1.f, -ex);
-    }
-    pr.scale = scale;
-    // data whose spread cannot be brought into FP16 range (non-finite after centring, or a
-    // spread so small/large that the power-of-two scale leaves float range) stays on the exact path
-    pr.usable = isfinite(maxabs) && isfinite(scale) && scale > 0.f && maxabs < 1e30f && (maxabs == 0.f || maxabs > 1e-30f);
+    PrepDev *dev = pr.red.as<PrepDev>();
+    const int ga = a.n ? pack_stats_blocks(ctx->sm_count) : 0, gb = b.n ? pack_stats_blocks(ctx->sm_count) : 0;
+    if ((e = cudaMemsetAsync(dev, 0, sizeof(PrepDev), st)) != cudaSuccess) return e;
+    prep_finalize_kernel<<<(dp + 31) / 32, 256, 0, st>>>(a.stats.as<float>(), ga, b.stats.as<float>(), gb, dp, dim,
+                                                         pr.mean.as<float>(), dev);
+    ctx->stats.launches += 1;
     for (int s = 0; s < 2; ++s) {
         Side &sd = ctx->side[s];
         if (sd.n_pad == 0) continue;
@@ -198,15 +274,24 @@ cudaError_t launch_tc_prepare(b200m_ctx *ctx) {
         if ((e = sd.norm16.reserve(sizeof(float) * sd.n_pad)) != cudaSuccess) return e;
         unsigned blocks = (unsigned) ((sd.n_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
         pack_operands_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(
-            sd.f32.as<float>(), sd.valid.as<uint8_t>(), sd.n, sd.n_pad, dim, dp, sd.kp, pr.mean.as<float>(), scale,
-            sd.op_query.as<__half>(), sd.op_train.as<__half>(), sd.norm16.as<float>(), scal + 1 + s);
+            sd.f32.as<float>(), sd.valid.as<uint8_t>(), sd.n, sd.n_pad, dim, dp, sd.kp, pr.mean.as<float>(), dev, s,
+            sd.op_query.as<__half>(), sd.op_train.as<__half>(), sd.norm16.as<float>());
         ctx->stats.launches += 1;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(h, scal, 12, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    // the one host round trip of the prepare step: scale, usability and the per-side norm bounds
+    PrepDev h;
+    if ((e = cudaMemcpyAsync(&h, dev, sizeof(h), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    memcpy(&pr.max_norm[0], &h[1], 4);
-    memcpy(&pr.max_norm[1], &h[2], 4);
+    float maxabs;
+    memcpy(&maxabs, &h.maxabs_bits, 4);
+    const float scale = scale_for(maxabs);
+    pr.scale = scale;
+    // data whose spread cannot be brought into FP16 range (non-finite after centring, or a spread so small/large that
+    // the power-of-two scale leaves float range) stays on the exact path
+    pr.usable = isfinite(maxabs) && isfinite(scale) && scale > 0.f && maxabs < 1e30f && (maxabs == 0.f || maxabs > 1e-30f);
+    memcpy(&pr.max_norm[0], &h.max_norm_bits[0], 4);
+    memcpy(&pr.max_norm[1], &h.max_norm_bits[1], 4);
     pr.ver[0] = a.version;
     pr.ver[1] = b.version;
     pr.ready = true;
