@@ -33,6 +33,10 @@ WORKLOADS = {
     "c3": ("shot", 500000, 500000, 2, "mutual", "SHOT-352 500k x 500k k=2 + mutual (BASELINE configs[2])"),
     "c3s": ("shot", 40000, 40000, 2, "mutual", "SHOT-352 40k x 40k k=2 + mutual (reduced copy of configs[2], for debugging)"),
     "c4": ("fpfh", 2000000, 2000000, 5, "mutual", "FPFH-33 2M x 2M k=5 mutual k-lists (BASELINE configs[3])"),
+    # configs[4]: the target set is sharded 1M rows per GPU (8M at 8 GPUs) and every rank holds all queries; per-rank exact
+    # top-k with global indices, one NCCL all-gather of the k-lists, merge kernel.  n_tgt here is PER RANK (weak scaling).
+    "c5": ("shot", 500000, 1000000, 2, "knn_target_sharded",
+           "SHOT-352 kNN k=2, 500k queries x (1M target rows per GPU), target-sharded + NCCL top-k merge (BASELINE configs[4])"),
 }
 METRIC = "descriptor queries/sec (k=2 + mutual)"
 
@@ -175,7 +179,9 @@ def run_b200(args, wl):
     from lidar_global_registration_b200 import synth
 
     desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
-    mode = {"mutual": M.MODE_MUTUAL, "ratio": M.MODE_RATIO, "one_sided": M.MODE_ONE_SIDED}[mode_name]
+    tsharded = mode_name == "knn_target_sharded"
+    mode = {"mutual": M.MODE_MUTUAL, "ratio": M.MODE_RATIO, "one_sided": M.MODE_ONE_SIDED,
+            "knn_target_sharded": M.MODE_KNN_ONLY}[mode_name]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,13 +204,20 @@ def run_b200(args, wl):
     be = D.GpuBackend(local_rank)
     sm = D.ShardedMatcher(be, rank, world, group)
 
+    # target-sharded: every rank generates its own shard of n_tgt rows (seeded by rank), global row offset rank * n_tgt
     src, tgt, dim = synth.make_pair_torch(desc, n_src, n_tgt, dev)
+    if tsharded and rank > 0:   # a different shard per rank: the common recipe, rows rotated and slightly rescaled
+        tgt = (torch.roll(tgt, shifts=1237 * rank, dims=0) * (1.0 + 2e-3 * rank)).contiguous()
     stride_b = src.stride(0) * 4
+    t_off = rank * n_tgt if tsharded else 0
     torch.cuda.synchronize()
 
     def step_device():
         be.upload_device(0, src, dim)
-        be.upload_device(1, tgt, dim)
+        be.upload_device(1, tgt, dim, index_offset=t_off)
+        if tsharded:
+            idx, dst, cnt = sm.knn_target_sharded(k)
+            return idx, cnt.sum(), dst
         return sm.match_query_sharded(k, mode)
 
     def barrier():
@@ -246,11 +259,23 @@ def run_b200(args, wl):
     kk = k if mode == M.MODE_MUTUAL else 1
     q0, q1 = D.shard_bounds(n_src, rank, world)
     out_h = torch.empty((max((q1 - q0) * kk, 1), 4), dtype=torch.int32).pin_memory()
+    lists_h = None
+    if tsharded:
+        lists_h = [torch.empty((n_src, k), dtype=torch.int32).pin_memory(), torch.empty((n_src, k), dtype=torch.float32).pin_memory(),
+                   torch.empty((n_src,), dtype=torch.int32).pin_memory()]
     d2h = [0]
 
     def step_e2e():
         be.upload_host(0, src_h, dim)
-        be.upload_host(1, tgt_h, dim)
+        be.upload_host(1, tgt_h, dim, index_offset=t_off)
+        if tsharded:
+            idx, dst, cnt = sm.knn_target_sharded(k)
+            lists_h[0].copy_(idx, non_blocking=True)
+            lists_h[1].copy_(dst, non_blocking=True)
+            lists_h[2].copy_(cnt, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            d2h[0] = (lists_h[0].numel() + lists_h[1].numel() + lists_h[2].numel()) * 4 if rank == 0 else 0
+            return idx, cnt, None
         rec, n_out, _ = sm.match_query_sharded(k, mode)
         n = int(n_out.item())                       # 8-byte D2H + sync: the count the caller needs
         out_h[:n].copy_(rec[:n], non_blocking=True)
@@ -272,6 +297,8 @@ def run_b200(args, wl):
     both = mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL)
     t0, t1 = D.shard_bounds(n_tgt, rank, world)
     flops_per_step = 2.0 * dim * ((q1 - q0) * n_tgt + ((t1 - t0) * n_src if both else 0))
+    if tsharded:   # every rank: all queries against its own target shard
+        flops_per_step = 2.0 * dim * n_src * n_tgt
     cand_ms_per_step = st["ms_candidates"] / args.steps
     pk = peaks()
     achieved = flops_per_step / (cand_ms_per_step * 1e-3) / 1e12 if cand_ms_per_step > 0 else 0.0
@@ -288,17 +315,20 @@ def run_b200(args, wl):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r, cores, sample, secs = CpuReference(desc, n_src, n_tgt, k, mode_name).rate(12.0)
+        r, cores, sample, secs = CpuReference(desc, n_src, n_tgt, k, "one_sided" if tsharded else mode_name).rate(12.0)
         cpu = {"value": r, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample, "seconds": secs}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32 (FP16 tensor-core candidates, exact FP32 re-rank)",
+                "scaling": "weak" if tsharded else "strong", "vs_baseline": None,
+                "dtype": "f32 (FP16 tensor-core candidates, exact FP32 re-rank)",
                 "data": "synthetic",
                 "config": {"workload": cfg, "descriptor": desc, "dim": dim, "n_src": n_src, "n_tgt": n_tgt, "k": k,
                            "filter": mode_name, "row_stride_bytes": stride_b, "correspondences": n_corr,
-                           "sharding": "query-sharded, target replicated" if world > 1 else "single GPU",
+                           "sharding": ("target-sharded (n_tgt rows per rank, %d in total), queries replicated, NCCL all-gather + merge"
+                                        % (n_tgt * world)) if tsharded else
+                                       ("query-sharded, target replicated" if world > 1 else "single GPU"),
                            "l2": "inputs larger than L2 (no flush needed)" if n_tgt * dim * 2 > 126e6 else
                                  "inputs smaller than L2; the step rewrites >126 MB of operands/candidates between kNN passes"},
                 "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d) * world,

@@ -256,7 +256,7 @@ struct RowState {
     float tk[KT];   // k smallest accumulator values this thread has seen (of distinct columns), ascending
     float thr;      // effective append threshold: min(own threshold, the partner thread's published one)
     float na, eta, slop, gfac;
-    uint32_t s_cnt;       // shared: entries appended to the row's list by both threads (may run past cap: overflow)
+    int cnt;              // entries appended to this thread's own list (may run past cap: overflow)
     uint32_t s_thr_own;   // shared: where this thread publishes its own threshold (EH = 2: read by the thread that
                           // filters the other half of this row's columns)
 };
@@ -327,7 +327,7 @@ __device__ __forceinline__ void warmup_chunk(const uint32_t (&r)[32], int col0, 
         mask &= mask - 1;
         const float v = select32(r, i);
         if (v < st.thr) {   // the threshold may have tightened since the mask was taken
-            const int slot = (int) atoms_add_u32(st.s_cnt, 1u);
+            const int slot = st.cnt++;
             if (slot < cap) {
                 out[slot] = col0 + i;
                 if (EH == 1) out_v[slot] = v;
@@ -342,7 +342,7 @@ __device__ __forceinline__ void warmup_chunk(const uint32_t (&r)[32], int col0, 
 // EH = 1 kernels (long descriptors: the epilogue has slack, the re-rank gather is what costs) also record the
 // accumulator value, so that the re-rank can drop every entry that the row's FINAL threshold no longer admits.
 template <int EH>
-__device__ __forceinline__ void append_chunk(const uint32_t (&r)[32], int col0, float thr, uint32_t s_cnt,
+__device__ __forceinline__ void append_chunk(const uint32_t (&r)[32], int col0, float thr, int &cnt,
                                              int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
     uint32_t mask = 0;
 #pragma unroll
@@ -350,7 +350,7 @@ __device__ __forceinline__ void append_chunk(const uint32_t (&r)[32], int col0, 
     while (mask) {
         const int i = __ffs((int) mask) - 1;
         mask &= mask - 1;
-        const int slot = (int) atoms_add_u32(s_cnt, 1u);
+        const int slot = cnt++;
         if (slot < cap) {
             out[slot] = col0 + i;
             if (EH == 1) out_v[slot] = select32(r, i);
@@ -392,10 +392,10 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
             tk_insert<KT>(st, m3);
             retighten<KT, EH>(st, k);
             const float thr = st.thr;
-            if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.s_cnt, out, out_v, cap);
-            if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.s_cnt, out, out_v, cap);
-            if (m2 < thr) append_chunk<EH>(r2, col0 + 64, thr, st.s_cnt, out, out_v, cap);
-            if (m3 < thr) append_chunk<EH>(r3, col0 + 96, thr, st.s_cnt, out, out_v, cap);
+            if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
+            if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
+            if (m2 < thr) append_chunk<EH>(r2, col0 + 64, thr, st.cnt, out, out_v, cap);
+            if (m3 < thr) append_chunk<EH>(r3, col0 + 96, thr, st.cnt, out, out_v, cap);
         }
     }
 }
@@ -431,8 +431,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t bar_tfull0 = bar_a + 8u;
     const uint32_t bar_tempty0 = bar_a + 24u;
     const uint32_t tmem_slot = bars_u + 8u * (uint32_t) (2 * stages + 5);
-    const uint32_t s_cnt = bars_u + 8u * (uint32_t) (2 * stages + 6);     // [128] u32: appended entries per row
-    const uint32_t s_thr = s_cnt + 4u * B200M_TILE_M;                     // [2][128] f32: published thresholds per column half
+    const uint32_t s_thr = bars_u + 8u * (uint32_t) (2 * stages + 6);     // [2][128] f32: published thresholds per column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -596,10 +595,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
         st.thr = active ? INFINITY : -INFINITY;
-        st.s_cnt = s_cnt + 4u * (uint32_t) row_in_tile;
+        st.cnt = 0;
         st.s_thr_own = s_thr + 4u * (uint32_t) (half * B200M_TILE_M + row_in_tile);
         const uint32_t s_thr_peer = s_thr + 4u * (uint32_t) ((half ^ 1) * B200M_TILE_M + row_in_tile);
-        if (half == 0) sts_u32(st.s_cnt, 0u);
         sts_f32(st.s_thr_own, st.thr);
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
@@ -610,7 +608,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             st.gfac = 1.f + 2.2f * (float) (p.dim + 4) * 5.9604644775390625e-8f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
-        const size_t list_row = (size_t) split * p.n_rows + (active ? local : 0);
+        // every epilogue thread owns a private candidate list: [split][column half][row][cap]
+        const size_t list_row = (size_t) (split * EH + half) * p.n_rows + (active ? local : 0);
         int32_t *const out = p.cand_idx + list_row * p.cap;
         float *const out_v = EH == 1 ? p.cand_val + list_row * p.cap : nullptr;
         const int k = p.k, cap = p.cap;
@@ -679,9 +678,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             printf("b200match epi-prof cta %d warp %d tiles %d: wait %lld ld %lld fast %lld slow %lld (entries that tightened: %d)\n",
                    blockIdx.x, warp, t1 - t0, c_wait, c_ld, c_fast, c_slow, n_slow);
         if ((dflags & 256) && st.na == -1.f) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // both threads of every row are done appending
-        if (half == 0 && active && !dump) {
-            p.cand_cnt[list_row] = (int32_t) lds_u32(st.s_cnt);
+        if (active && !dump) {
+            p.cand_cnt[list_row] = st.cnt;
             if (EH == 1) p.cand_thr[list_row] = st.thr;
         }
     }
@@ -841,26 +839,30 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.dim = q.dim;
     p.bmax = ctx->prep.max_norm[1 - direction];
     p.q_norm16 = q.norm16.as<float>();
-    // expected appends per list ~ k*(ln(n/k)+1); leave generous head room, overflow is handled exactly
-    int cap = cap_request;
-    if (cap <= 0) {
-        double n_split = (double) p.tiles_per_split * B200M_TILE_N;
-        double expect = k * (log(fmax(n_split / k, 2.0)) + 1.0);
-        cap = (int) (1.6 * expect + 24.0);
-        cap = (cap + 7) / 8 * 8;
-    }
-    if (cap < k) cap = k;
-    p.cap = cap;
-    CK(ctx->ws_cand_idx.reserve(sizeof(int32_t) * (size_t) n_splits * n_rows * (size_t) cap));
-    CK(ctx->ws_cand_cnt.reserve(sizeof(int32_t) * (size_t) n_splits * n_rows));
-    p.cand_idx = ctx->ws_cand_idx.as<int32_t>();
-    p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
     // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
     // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and there a thread that owns its whole row
     // also records the accumulator values so that the re-rank can prune by the row's final threshold.
     int eh = p.ka <= 2 ? 2 : 1;
     if (ctx->tc_debug & 64) eh = 1;
     if (ctx->tc_debug & 128) eh = 2;
+    // A list receives a column whenever it is under the running threshold: for columns in random order that is a
+    // record process, E = k (ln(n / k) + 1) appends with variance about E, n = the columns the list's thread sees.
+    // cap = E + 8 sqrt(E) + 16 puts an overflow beyond 8 sigma; overflowed rows (adversarial column orders) are
+    // still answered exactly, by the CUDA-core fallback.
+    int cap = cap_request;
+    if (cap <= 0) {
+        const double n_list = (double) p.tiles_per_split * B200M_TILE_N / eh;
+        const double expect = k * (log(fmax(n_list / k, 2.0)) + 1.0);
+        cap = (int) (expect + 8.0 * sqrt(expect) + 16.0);
+        cap = (cap + 7) / 8 * 8;
+    }
+    if (cap < k) cap = k;
+    p.cap = cap;
+    const int n_lists = n_splits * eh;
+    CK(ctx->ws_cand_idx.reserve(sizeof(int32_t) * (size_t) n_lists * n_rows * (size_t) cap));
+    CK(ctx->ws_cand_cnt.reserve(sizeof(int32_t) * (size_t) n_lists * n_rows));
+    p.cand_idx = ctx->ws_cand_idx.as<int32_t>();
+    p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
     p.cand_val = nullptr;
     p.cand_thr = nullptr;
     if (eh == 1) {
@@ -898,7 +900,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     if (rc) return rc;
     ctx->stats.launches += 1;
     ctx->stats.candidate_launches += 1;
-    *n_lists_out = n_splits;
+    *n_lists_out = n_lists;
     *cap_out = cap;
     return 0;
 }

@@ -281,7 +281,7 @@ exact_rows_split_kernel(const float *__restrict__ q_f32, int dp, const float *__
 // flight at once instead of a load/store round trip per 128 bytes.  Each lane then runs the reference's sequential
 // FP32 chain over its own slab row with 128-bit shared loads; the slab pitch is an odd number of 16-byte units, so
 // the 32 lanes' loads are bank-conflict free.
-constexpr int kMaxLists = 16;
+constexpr int kMaxLists = 32;   // train splits x epilogue column halves
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 

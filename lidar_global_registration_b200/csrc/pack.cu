@@ -160,73 +160,79 @@ prep_finalize_kernel(const float *__restrict__ sa, int ga, const float *__restri
     }
 }
 
-// One warp per (padded) row: FP16 operand rows + |x16|^2.  A lane converts four consecutive values at a time
-// (128-bit loads, 64-bit stores).
+// One warp per (padded) row, persistent over the rows: FP16 operand rows + |x16|^2.  A lane converts four consecutive
+// values at a time (128-bit loads, 64-bit stores); the scale word is read once per warp and the side's largest norm
+// leaves through ONE atomic per warp (a per-row atomic on the line that also holds the scale serialises the kernel
+// in a single L2 slice: 0.9 ms instead of 0.25 ms for 500k SHOT rows).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pack_operands_kernel(const float *__restrict__ f32, const uint8_t *__restrict__ valid, size_t n, size_t n_pad,
                      int dim, int dp, int kp, const float *__restrict__ mean, PrepDev *__restrict__ prep, int side,
                      __half *__restrict__ op_query, __half *__restrict__ op_train, float *__restrict__ norm16) {
     const int lane = threadIdx.x & 31;
-    size_t row = (size_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= n_pad) return;
     const float scale = scale_for(__int_as_float(prep->maxabs_bits));
-    const bool ok = row < n && valid[row];
-    __half *oq = op_query + row * (size_t) kp;
-    __half *ot = op_train + row * (size_t) kp;
-    const float *src = f32 + row * (size_t) dp;
-    double nrm = 0.0;
-    // the descriptor columns (dp is a multiple of 4, kp of 64; columns dim..dp-1 of f32 are zero): every load of the
-    // row is issued before the first conversion (kp <= 640: at most five 128-column sweeps)
-    float4 v[5], mu[5];
+    float4 mu[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int d0 = 4 * lane + 128 * i;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mu[i] = v[i];
-        if (ok && d0 < dp) {
-            v[i] = __ldg(reinterpret_cast<const float4 *>(src + d0));
-            mu[i] = __ldg(reinterpret_cast<const float4 *>(mean + d0));
-        }
+        mu[i] = d0 < dp ? __ldg(reinterpret_cast<const float4 *>(mean + d0)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    float max_nf = 0.f;
+    const size_t stride = (size_t) gridDim.x * kWarpsPerBlock;
+    for (size_t row = (size_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < n_pad; row += stride) {
+        const bool ok = row < n && valid[row];
+        __half *oq = op_query + row * (size_t) kp;
+        __half *ot = op_train + row * (size_t) kp;
+        const float *src = f32 + row * (size_t) dp;
+        double nrm = 0.0;
+        // the descriptor columns (dp is a multiple of 4, kp of 64; columns dim..dp-1 of f32 are zero): every load of
+        // the row is issued before the first conversion (kp <= 640: at most five 128-column sweeps)
+        float4 v[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int d0 = 4 * lane + 128 * i;
-        if (d0 >= kp) break;
-        const float x[4] = {(v[i].x - mu[i].x) * scale, (v[i].y - mu[i].y) * scale, (v[i].z - mu[i].z) * scale,
-                            (v[i].w - mu[i].w) * scale};
-        __half ht[4], hq[4];
+        for (int i = 0; i < 5; ++i) {
+            const int d0 = 4 * lane + 128 * i;
+            v[i] = (row < n && d0 < dp) ? __ldg(reinterpret_cast<const float4 *>(src + d0)) : mu[i];   // x - mu = 0 beyond the row
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int d = d0 + e;
-            if (d < dim) {
-                ht[e] = __float2half_rn(x[e]);
-                const float xf = __half2float(ht[e]);
-                hq[e] = __float2half_rn(-2.f * xf);   // exact: |x| <= 1, power-of-two factor
-                nrm += (double) xf * (double) xf;
-            } else {
-                ht[e] = __float2half_rn(0.f);   // the three norm columns are filled in below
-                hq[e] = __float2half_rn(d < dim + B200M_AUG_COLS ? 1.f : 0.f);   // 1s pick up the norm pieces of the train row
+        for (int i = 0; i < 5; ++i) {
+            const int d0 = 4 * lane + 128 * i;
+            if (d0 >= kp) break;
+            const float x[4] = {(v[i].x - mu[i].x) * scale, (v[i].y - mu[i].y) * scale, (v[i].z - mu[i].z) * scale,
+                                (v[i].w - mu[i].w) * scale};
+            __half ht[4], hq[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d = d0 + e;
+                if (d < dim) {
+                    ht[e] = __float2half_rn(ok ? x[e] : 0.f);
+                    const float xf = __half2float(ht[e]);
+                    hq[e] = __float2half_rn(-2.f * xf);   // exact: |x| <= 1, power-of-two factor
+                    nrm += (double) xf * (double) xf;
+                } else {
+                    ht[e] = __float2half_rn(0.f);   // the three norm columns are filled in below
+                    hq[e] = __float2half_rn(d < dim + B200M_AUG_COLS ? 1.f : 0.f);   // 1s pick up the norm pieces of the train row
+                }
             }
+            *reinterpret_cast<uint2 *>(oq + d0) = *reinterpret_cast<const uint2 *>(hq);
+            *reinterpret_cast<uint2 *>(ot + d0) = *reinterpret_cast<const uint2 *>(ht);
         }
-        *reinterpret_cast<uint2 *>(oq + d0) = *reinterpret_cast<const uint2 *>(hq);
-        *reinterpret_cast<uint2 *>(ot + d0) = *reinterpret_cast<const uint2 *>(ht);
+        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        __syncwarp();
+        if (lane == 0) {
+            float nf = ok ? (float) nrm : 0.f;
+            norm16[row] = nf;
+            float hi_src = ok ? nf : B200M_SENTINEL;
+            __half hi = __float2half_rn(hi_src);
+            float r1 = hi_src - __half2float(hi);
+            __half mid = __float2half_rn(r1);
+            float r2 = r1 - __half2float(mid);
+            __half lo = __float2half_rn(r2);
+            ot[dim + 0] = hi;
+            ot[dim + 1] = mid;
+            ot[dim + 2] = lo;
+            if (ok) max_nf = fmaxf(max_nf, nf);
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-    __syncwarp();
-    if (lane == 0) {
-        float nf = ok ? (float) nrm : 0.f;
-        norm16[row] = nf;
-        float hi_src = ok ? nf : B200M_SENTINEL;
-        __half hi = __float2half_rn(hi_src);
-        float r1 = hi_src - __half2float(hi);
-        __half mid = __float2half_rn(r1);
-        float r2 = r1 - __half2float(mid);
-        __half lo = __float2half_rn(r2);
-        ot[dim + 0] = hi;
-        ot[dim + 1] = mid;
-        ot[dim + 2] = lo;
-        if (ok) atomicMax(&prep->max_norm_bits[side], __float_as_int(sqrtf(nf)));
-    }
+    if (lane == 0 && max_nf > 0.f) atomicMax(&prep->max_norm_bits[side], __float_as_int(sqrtf(max_nf)));
 }
 
 }  // namespace
@@ -272,7 +278,8 @@ cudaError_t launch_tc_prepare(b200m_ctx *ctx) {
         if ((e = sd.op_query.reserve(opb)) != cudaSuccess) return e;
         if ((e = sd.op_train.reserve(opb)) != cudaSuccess) return e;
         if ((e = sd.norm16.reserve(sizeof(float) * sd.n_pad)) != cudaSuccess) return e;
-        unsigned blocks = (unsigned) ((sd.n_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        size_t want = (sd.n_pad + kWarpsPerBlock - 1) / kWarpsPerBlock, cap_blocks = (size_t) ctx->sm_count * 8;
+        unsigned blocks = (unsigned) (want < cap_blocks ? want : cap_blocks);
         pack_operands_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(
             sd.f32.as<float>(), sd.valid.as<uint8_t>(), sd.n, sd.n_pad, dim, dp, sd.kp, pr.mean.as<float>(), dev, s,
             sd.op_query.as<__half>(), sd.op_train.as<__half>(), sd.norm16.as<float>());

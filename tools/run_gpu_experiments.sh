@@ -1,6 +1,6 @@
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; echo tests rc=$?
-tail -15 gpurun_out/t_all.log
-for w in c1 c2 c3; do
-  timeout 300 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_$w.json 2> gpurun_out/n_$w.err; echo $w rc=$?
+tail -5 gpurun_out/t_all.log
+for w in c1 c2 c3 c4; do
+  timeout 600 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_$w.json 2> gpurun_out/n_$w.err; echo $w rc=$?; tail -2 gpurun_out/n_$w.err
 done
 python tools/bench_summary.py gpurun_out/n_*.json
