@@ -552,18 +552,20 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             uint32_t s = 0, ph = 0;
             for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
                 const uint32_t buf = (uint32_t) lt & 1u;
-                mbar_wait(bar_tempty0 + 8u * buf, (((uint32_t) lt >> 1) & 1u) ^ 1u);
-                tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * (uint32_t) B200M_TILE_N;
                 for (int a = 0; a < ka; ++a) {
                     mbar_wait(bar_full0 + 8u * s, ph);
+                    const uint64_t da = desc_a0 + (uint64_t) ((uint32_t) a * a_step);
+                    const uint64_t db = desc_b0 + (uint64_t) (s * b_step);
+                    // K steps of this atom: 4, or what is left of the row in the last one; +32 B (2 descriptor
+                    // units) per K = 16 step inside the 128 B swizzle atom
+                    const uint32_t nk = a + 1 < ka ? nk_full : nk_last;
+                    // The accumulator buffer is waited for LAST, with the operands landed and the descriptors built:
+                    // for short descriptors the hand-back of the buffer by the epilogue is the critical path, and
+                    // everything between that arrival and the first MMA is latency on it.
+                    if (a == 0) mbar_wait(bar_tempty0 + 8u * buf, (((uint32_t) lt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t da = desc_a0 + (uint64_t) ((uint32_t) a * a_step);
-                        const uint64_t db = desc_b0 + (uint64_t) (s * b_step);
-                        // K steps of this atom: 4, or what is left of the row in the last one; +32 B (2 descriptor
-                        // units) per K = 16 step inside the 128 B swizzle atom
-                        const uint32_t nk = a + 1 < ka ? nk_full : nk_last;
                         tc_mma<PAIR>(tmem_d, da, db, idesc, (uint32_t) (a != 0), (uint32_t) (nk > 0));
                         tc_mma<PAIR>(tmem_d, da + 2, db + 2, idesc, 1u, (uint32_t) (nk > 1));
                         tc_mma<PAIR>(tmem_d, da + 4, db + 4, idesc, 1u, (uint32_t) (nk > 2));
@@ -627,7 +629,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tc_fence_after();
             if (prof) { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const uint32_t taddr = lane_base + buf * (uint32_t) B200M_TILE_N;
-            if (EH == 2) st.thr = fminf(st.thr, lds_f32(s_thr_peer));   // pick up what the partner thread has learnt
             // 128 columns at a time: four TMEM loads in flight, one wait.  The accumulator buffer goes back to the MMA
             // issuer as soon as this warp's last load has landed in registers -- the filtering below then overlaps the
             // MMAs of the tile after next instead of sitting on their critical path.
@@ -649,6 +650,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         else mbar_arrive(bar_tempty0 + 8u * buf);
                     }
                 }
+                if (EH == 2) st.thr = fminf(st.thr, lds_f32(s_thr_peer));   // pick up what the partner thread has learnt
                 if (dflags & (1 | 32)) continue;
                 if (dump) {   // debug: raw accumulators of this tile
                     float *d = dump + ((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * kColsPerWarp + h * 128;

@@ -36,10 +36,13 @@ for desc, nq, nt, k in [("fpfh", 5003, 7001, 2), ("shot", 2111, 3005, 2), ("rops
         allrec, n_all = sm.gather_records(rec, n_out)
         got = allrec[:n_all].contiguous().cpu().numpy().view(M.CORR_DTYPE).reshape(-1)
         if rank == 0:
-            exp = orc.match(sd, td, k, oname)[0]
+            exp = orc.match(sd, td, k, oname, M.MATCHING_RATIO_THRESHOLD, np.float32(M.FLT_MAX))[0]
             same = got.shape == exp.shape and all(np.array_equal(got[f], exp[f]) for f in got.dtype.names)
             print("query-sharded %-6s %s %dx%d k=%d world=%d: %d records %s" % (oname, desc, nq, nt, k, world, n_all,
                                                                            "PASS" if same else "FAIL"))
+            if not same:
+                print("   expected %d records; differing fields: %s" % (exp.shape[0], [f for f in got.dtype.names
+                      if got.shape != exp.shape or not np.array_equal(got[f], exp[f])]))
             ok = ok and same
     # --- target-sharded kNN ---
     t0, t1 = D.shard_bounds(nt, rank, world)
