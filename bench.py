@@ -39,6 +39,10 @@ WORKLOADS = {
            "SHOT-352 kNN k=2, 500k queries x (1M target rows per GPU), target-sharded + NCCL top-k merge (BASELINE configs[4])"),
 }
 METRIC = "descriptor queries/sec (k=2 + mutual)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE candidate-kernel launch, from the ncu --set full capture of the
+# same workload on 1 GPU (profiles/r01b_ncu_<wl>_cand.txt).  The kernel is tensor bound; the traffic is the FP16 train
+# operand array streaming through L2 once per wave of query tiles (algorithmic operand bytes: 0.77 GB for c3).
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c3": 19.784716e9 + 219.15264e6, "c2": 55.755776e6 + 14.412032e6}
 
 
 def peaks():
@@ -304,7 +308,10 @@ def run_b200(args, wl):
     achieved = flops_per_step / (cand_ms_per_step * 1e-3) / 1e12 if cand_ms_per_step > 0 else 0.0
     n_launch = st["candidate_launches"] / args.steps
     roofline = {"bound": "tensor", "kernel": "tc_candidates_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(wl) if world == 1 else None,
+                "traffic_source": "bytes per launch, profiles/r01b_ncu_%s_cand.txt (ncu --set full, 1 GPU)" % wl
+                                  if world == 1 and wl in NCU_TRAFFIC_BYTES_PER_LAUNCH else None,
                 "peak_source": pk["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "launch_ms": cand_ms_per_step / max(n_launch, 1), "launches_per_step": n_launch,
                 "algorithmic_flops_per_step": flops_per_step,
