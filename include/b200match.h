@@ -149,6 +149,34 @@ B200M_API int b200m_merge_device(b200m_ctx *ctx, int k, int n_lists, size_t nq,
                                  const int32_t *d_idx_in, const float *d_dist_in, const int32_t *d_count_in,
                                  int32_t *d_idx, float *d_dist, int32_t *d_count);
 
+/* ---- multi-scale merge + spatial vote: the tail of match_multiscale -------------
+ * (include/matching.h:264-354).  The reference runs one kNN per scale over that scale's
+ * keypoint subset and descriptors (:297-311), remaps per-scale row numbers to keypoint ids
+ * (:313-321, kps_indices_multiscale), concatenates the candidates per query keypoint in scale
+ * order and lets a spatial vote keep at most ONE match per keypoint (:327-352).  Here:
+ *   b200m_multiscale_begin(n_query_kps, n_scales, k)
+ *   per scale:  b200m_upload(query side, ...); b200m_upload(train side, ...);
+ *               b200m_multiscale_add(params, direction, scale, query_map, train_map, n_train_kps)
+ *                   -- runs the scale's kNN (as b200m_knn would) and files the lists under
+ *                      query_map[row] with train rows renamed train_map[row] (NULL = identity)
+ *   b200m_multiscale_vote(train_xyz, n_train_kps, stride, iss_radius, idx, dist, count)
+ *                   -- outputs are [n_query_kps]: the chosen train keypoint id (or -1), its
+ *                      descriptor distance, count 0/1 -- the one-entry MultivaluedCorrespondence
+ *                      match_multiscale returns; xyz rows are `stride` bytes apart (pcl::PointXYZ: 16).
+ * The *_device forms take device pointers (k-lists from b200m_knn_device) and queue on the stream. */
+B200M_API int b200m_multiscale_begin(b200m_ctx *ctx, size_t n_query_kps, int n_scales, int k);
+B200M_API int b200m_multiscale_add(b200m_ctx *ctx, const b200m_params *p, int direction, int scale,
+                                   const int32_t *query_map, const int32_t *train_map, size_t n_train_kps);
+B200M_API int b200m_multiscale_vote(b200m_ctx *ctx, const float *train_xyz, size_t n_train_kps,
+                                    size_t xyz_stride_bytes, float iss_radius, int32_t *idx, float *dist,
+                                    int32_t *count);
+B200M_API int b200m_multiscale_add_device(b200m_ctx *ctx, int scale, size_t n_rows, const int32_t *d_idx,
+                                          const float *d_dist, const int32_t *d_count,
+                                          const int32_t *d_query_map, const int32_t *d_train_map,
+                                          size_t n_train_rows, int64_t train_index_offset, size_t n_train_kps);
+B200M_API int b200m_multiscale_vote_device(b200m_ctx *ctx, const float *d_train_xyz, size_t xyz_stride_bytes,
+                                           float iss_radius, int32_t *d_idx, float *d_dist, int32_t *d_count);
+
 B200M_API int b200m_version(void);
 
 /* ---- test hooks (used by tests/ only; not part of the reference-facing surface) ----

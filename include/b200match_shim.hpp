@@ -154,6 +154,52 @@ std::vector<MultivaluedCorrespondence> matchLocal(const FeatureCloud<FeatureT> &
     return matchBF<FeatureT>(query_features, train_features, parameters);
 }
 
+// match_multiscale (reference include/matching.h:264-354) over precomputed per-scale descriptors: one exact kNN per
+// scale (k = parameters.randomness) over that scale's keypoint subset, per-scale row numbers renamed to keypoint ids
+// through the scale's kps_indices_multiscale (:313-321), candidates concatenated per query keypoint in scale order, and
+// the spatial vote over the train keypoints' xyz (:327-352) keeps at most ONE match per query keypoint.
+//   query_features[s] / train_features[s]   kps_features_multiscale[s] of the two Storage objects (common scales only)
+//   query_indices[s] / train_indices[s]     kps_indices_multiscale[s] (row of scale s -> keypoint id)
+//   train_kps_xyz                           st_train.kps: n_train_kps rows, `xyz_stride_bytes` apart (pcl::PointXYZ: 16)
+// Returns st_query.kps->size() entries, each empty or {one match index, its descriptor distance}.
+template <typename FeatureT>
+std::vector<MultivaluedCorrespondence> match_multiscale(const std::vector<FeatureCloud<FeatureT>> &query_features,
+                                                        const std::vector<FeatureCloud<FeatureT>> &train_features,
+                                                        const std::vector<std::vector<int>> &query_indices,
+                                                        const std::vector<std::vector<int>> &train_indices,
+                                                        size_t n_query_kps, const float *train_kps_xyz, size_t n_train_kps,
+                                                        size_t xyz_stride_bytes, float iss_radius,
+                                                        const AlignmentParameters &parameters) {
+    const size_t n_scales = query_features.size();
+    if (n_scales == 0 || train_features.size() != n_scales || query_indices.size() != n_scales || train_indices.size() != n_scales)
+        throw std::runtime_error("match_multiscale: one descriptor cloud and one index map per scale and side are needed");
+    Context ctx(parameters.device);
+    const int k = parameters.randomness;
+    ctx.check(b200m_multiscale_begin(ctx.get(), n_query_kps, (int) n_scales, k));
+    b200m_params p = make_params(parameters, B200M_MODE_KNN_ONLY, k);
+    static_assert(sizeof(int) == sizeof(int32_t), "index maps are passed as int32");
+    for (size_t s = 0; s < n_scales; ++s) {
+        if (query_indices[s].size() != cloud_size<FeatureT>(query_features[s]) ||
+            train_indices[s].size() != cloud_size<FeatureT>(train_features[s]))
+            throw std::runtime_error("match_multiscale: index map length != number of descriptors of the scale");
+        ctx.upload<FeatureT>(0, query_features[s]);
+        ctx.upload<FeatureT>(1, train_features[s]);
+        ctx.check(b200m_multiscale_add(ctx.get(), &p, 0, (int) s, reinterpret_cast<const int32_t *>(query_indices[s].data()),
+                                       reinterpret_cast<const int32_t *>(train_indices[s].data()), n_train_kps));
+    }
+    std::vector<int32_t> idx(n_query_kps), cnt(n_query_kps);
+    std::vector<float> dist(n_query_kps);
+    ctx.check(b200m_multiscale_vote(ctx.get(), train_kps_xyz, n_train_kps, xyz_stride_bytes, iss_radius, idx.data(), dist.data(),
+                                    cnt.data()));
+    std::vector<MultivaluedCorrespondence> out(n_query_kps);
+    for (size_t i = 0; i < n_query_kps; ++i)
+        if (cnt[i] > 0) {
+            out[i].match_indices.push_back(idx[i]);
+            out[i].distances.push_back(dist[i]);
+        }
+    return out;
+}
+
 // FeatureBasedMatcher (reference include/matching.h:25-42) at the descriptor seam.
 class FeatureBasedMatcher {
 public:

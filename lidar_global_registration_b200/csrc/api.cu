@@ -146,6 +146,7 @@ void b200m_destroy(b200m_ctx *ctx) {
                     &ctx->ws_done, &ctx->ws_cand_val, &ctx->ws_cand_thr};
     for (DevBuf *b : ws) b->release();
     tc_release(ctx);
+    multiscale_release(ctx);
     if (ctx->pool) {
         if (ctx->pool->created)
             for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventDestroy(ctx->pool->ev[i]);

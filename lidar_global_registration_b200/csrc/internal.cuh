@@ -64,6 +64,7 @@ struct b200m_ctx {
     DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr, ws_totals;
     bool totals_init = false;
     void *tmap_cache = nullptr;
+    void *multiscale = nullptr;   // MultiscaleState (multiscale.cu)
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     int tc_splits = 0;     // B200M_TC_SPLITS: 0 = chosen per launch (wave balance); > 0 forces the number of train splits
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
@@ -151,3 +152,6 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
                   int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile);
 bool tc_supported(const b200m_ctx *ctx, int dim, int k);
 void tc_release(b200m_ctx *ctx);
+
+// multiscale.cu
+void multiscale_release(b200m_ctx *ctx);

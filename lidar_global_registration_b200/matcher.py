@@ -56,7 +56,8 @@ class Stats(C.Structure):
 EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_stream", "b200m_sync",
            "b200m_set_profiling", "b200m_get_stats", "b200m_reset_stats", "b200m_upload", "b200m_upload_device",
            "b200m_knn", "b200m_knn_device", "b200m_match", "b200m_filter_device", "b200m_merge_device",
-           "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile"]
+           "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile", "b200m_multiscale_begin",
+           "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device"]
 
 _lib = None
 
@@ -88,6 +89,11 @@ def load_library():
     L.b200m_match.argtypes = [vp, C.POINTER(_Params), fp, fp, vp, sz, C.POINTER(sz), C.POINTER(C.c_float)]
     L.b200m_filter_device.argtypes = [vp, C.POINTER(_Params), sz, sz, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, sz, vp, vp]
     L.b200m_merge_device.argtypes = [vp, C.c_int, C.c_int, sz, vp, vp, vp, vp, vp, vp]
+    L.b200m_multiscale_begin.argtypes = [vp, sz, C.c_int, C.c_int]
+    L.b200m_multiscale_add.argtypes = [vp, C.POINTER(_Params), C.c_int, C.c_int, vp, vp, sz]
+    L.b200m_multiscale_vote.argtypes = [vp, fp, sz, sz, C.c_float, vp, vp, vp]
+    L.b200m_multiscale_add_device.argtypes = [vp, C.c_int, sz, vp, vp, vp, vp, vp, sz, i64, sz]
+    L.b200m_multiscale_vote_device.argtypes = [vp, fp, sz, C.c_float, vp, vp, vp]
     L.b200m_version.restype = C.c_int
     L.b200m_debug_operands.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, C.POINTER(C.c_float), C.POINTER(i32),
                                        C.POINTER(i64)]
@@ -246,6 +252,36 @@ class Context:
         self._ck(self._L.b200m_merge_device(self._h, k, n_lists, nq, v(idx_in), v(dist_in), v(cnt_in), v(idx), v(dist),
                                             v(cnt)))
 
+    # -- multi-scale merge + spatial vote (match_multiscale, include/matching.h:264-354) ----
+    def multiscale_begin(self, n_query_kps, n_scales, k):
+        self._ms = (int(n_query_kps), int(k))
+        self._ck(self._L.b200m_multiscale_begin(self._h, n_query_kps, n_scales, k))
+
+    def multiscale_add(self, scale, direction=0, query_map=None, train_map=None, n_train_kps=None, precision=PREC_TC_F16):
+        """kNN of the currently uploaded sides (this scale's descriptors) filed under the scale's index maps."""
+        qm = None if query_map is None else np.ascontiguousarray(query_map, np.int32)
+        tm = None if train_map is None else np.ascontiguousarray(train_map, np.int32)
+        if qm is not None and qm.shape[0] != self.n[direction]:
+            raise B200MatchError("query_map length != number of query rows of this scale")
+        if tm is not None and tm.shape[0] != self.n[1 - direction]:
+            raise B200MatchError("train_map length != number of train rows of this scale")
+        if n_train_kps is None:
+            n_train_kps = self.n[1 - direction] if tm is None else int(tm.max()) + 1 if tm.size else 0
+        p = self._params(self._ms[1], MODE_KNN_ONLY, precision=precision)
+        self._ck(self._L.b200m_multiscale_add(self._h, C.byref(p), direction, scale, None if qm is None else qm.ctypes.data,
+                                              None if tm is None else tm.ctypes.data, n_train_kps))
+
+    def multiscale_vote(self, train_xyz, iss_radius):
+        """-> (match index [n_query_kps] (-1: none), descriptor distance, count 0/1)."""
+        xyz = np.ascontiguousarray(train_xyz, np.float32)
+        if xyz.ndim != 2 or xyz.shape[1] < 3:
+            raise B200MatchError("train_xyz must be [n_train_kps, >= 3] float32 (pcl::PointXYZ rows)")
+        nq = self._ms[0]
+        idx, dist, cnt = np.empty(nq, np.int32), np.empty(nq, np.float32), np.empty(nq, np.int32)
+        self._ck(self._L.b200m_multiscale_vote(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0], float(iss_radius),
+                                               idx.ctypes.data, dist.ctypes.data, cnt.ctypes.data))
+        return idx, dist, cnt
+
     # -- test hooks -------------------------------------------------------------
     def debug_operands(self, side, as_query):
         kp, n_pad, scale = C.c_int32(0), C.c_int64(0), C.c_float(0)
@@ -289,6 +325,26 @@ def match_local(query_features, train_features, parameters, dim=None, device=0):
     """matchLocal<FeatureT> with match_search_radius = inf (include/matching.h:637-678, as the reference's
     test calls it, tests/flann_bf_matcher.h:66-72).  The spatially gated variant is a next-row item."""
     return match_bf(query_features, train_features, parameters, dim, device)
+
+
+def match_multiscale(query_scales, train_scales, n_query_kps, train_kps_xyz, iss_radius, parameters, dim=None, device=0):
+    """FeatureBasedMatcherImpl<FeatureT>::match_multiscale (include/matching.h:264-354) over precomputed per-scale
+    descriptors: `query_scales` / `train_scales` are lists (one entry per common scale, ascending log2 radius) of
+    (features [n_s, >= dim] float32, kps_indices [n_s] int32 or None) -- the reference's kps_features_multiscale[s] and
+    kps_indices_multiscale[s].  Per scale an exact kNN (k = parameters.randomness), remapped to keypoint ids; then the
+    spatial vote over the train keypoints' xyz keeps at most one match per query keypoint.
+    Returns (match_index [n_query_kps] (-1: none), distance, count 0/1)."""
+    if len(query_scales) != len(train_scales) or not query_scales:
+        raise B200MatchError("match_multiscale: need the same, non-zero number of scales on both sides")
+    xyz = np.ascontiguousarray(train_kps_xyz, np.float32)
+    with Context(device) as ctx:
+        ctx.multiscale_begin(n_query_kps, len(query_scales), parameters.randomness)
+        for s, ((qf, qmap), (tf, tmap)) in enumerate(zip(query_scales, train_scales)):
+            d = dim or np.asarray(qf).shape[1]
+            ctx.upload(0, qf, d)
+            ctx.upload(1, tf, d)
+            ctx.multiscale_add(s, 0, qmap, tmap, xyz.shape[0], precision=parameters.precision)
+        return ctx.multiscale_vote(xyz, iss_radius)
 
 
 # ---- the reference's matcher classes --------------------------------------------------------

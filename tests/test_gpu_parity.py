@@ -329,3 +329,45 @@ def test_overflowed_candidate_lists_fall_back_exactly(desc, nq, nt, k, regime):
         assert (0 < flagged <= 256) if regime == "few" else flagged > 256
         _same(got, orc.knn(_dense(src, dim), _dense(tgt, dim), k))
         _same(ctx.knn(k, 0, cand_cap=k), got)   # the split kernel's completion counters are reusable
+
+
+@pytest.mark.parametrize("desc,k,n_scales", [("fpfh", 1, 1), ("fpfh", 3, 3), ("shot", 2, 2), ("rops", 5, 4)])
+def test_match_multiscale_vote_equals_oracle(desc, k, n_scales):
+    """match_multiscale's tail (reference include/matching.h:264-354): per-scale kNN over keypoint subsets, remap to
+    keypoint ids, concatenate in scale order, spatial vote -> one match per query keypoint; == the oracle's restatement
+    (orc.knn per scale + orc.spatial_vote on the concatenated lists), bit for bit."""
+    rng = np.random.default_rng(17 + k)
+    n_qk, n_tk = 900, 1100                      # keypoints of the two clouds
+    xyz = (rng.random((n_tk, 4)) * 2.0).astype(np.float32)      # pcl::PointXYZ rows (16 B)
+    xyz[: n_tk // 3, :3] = xyz[0, :3] + 0.01 * rng.standard_normal((n_tk // 3, 3)).astype(np.float32)   # a tight cluster
+    iss_radius = 0.05
+    q_scales, t_scales, dim = [], [], None
+    comb_i = [[] for _ in range(n_qk)]
+    comb_d = [[] for _ in range(n_qk)]
+    for s in range(n_scales):
+        qmap = np.sort(rng.choice(n_qk, size=n_qk - 60 * s, replace=False)).astype(np.int32)   # the scale's keypoint subset
+        tmap = np.sort(rng.choice(n_tk, size=n_tk - 45 * s, replace=False)).astype(np.int32)
+        src, tgt, dim = synth.make_pair(desc, qmap.shape[0], tmap.shape[0], seed=100 + s, nan_frac=0.01)
+        q_scales.append((src, qmap))
+        t_scales.append((tgt, tmap))
+        ei, ed, ec = orc.knn(_dense(src, dim), _dense(tgt, dim), k)
+        for r in range(qmap.shape[0]):
+            for m in range(ec[r]):
+                comb_i[qmap[r]].append(int(tmap[ei[r, m]]))
+                comb_d[qmap[r]].append(ed[r, m])
+    width = max(max(len(c) for c in comb_i), 1)
+    ci = np.full((n_qk, width), -1, np.int32)
+    cd = np.zeros((n_qk, width), np.float32)
+    cc = np.zeros(n_qk, np.int32)
+    for i in range(n_qk):
+        cc[i] = len(comb_i[i])
+        ci[i, :cc[i]] = comb_i[i]
+        cd[i, :cc[i]] = comb_d[i]
+    vi, vd, vc = orc.spatial_vote(ci, cd, cc, xyz[:, :3], iss_radius)
+    params = M.AlignmentParameters(randomness=k)
+    gi, gd, gc = M.match_multiscale(q_scales, t_scales, n_qk, xyz, iss_radius, params, dim=dim)
+    assert np.array_equal(gc, vc) and np.array_equal(gi, vi[:, 0]) and np.array_equal(gd, vd[:, 0])
+    assert gc.sum() > 0.9 * n_qk - 60 * n_scales
+    if k * n_scales > 1:   # the vote is not the identity: some keypoints do not keep their nearest descriptor
+        first = np.array([c[0] if c else -1 for c in comb_i])
+        assert np.any(gi != first)
