@@ -269,9 +269,13 @@ def run_b200(args, wl):
                    torch.empty((n_src,), dtype=torch.int32).pin_memory()]
     d2h = [0]
 
+    h2d_rank = [0]
+
     def step_e2e():
-        be.upload_host(0, src_h, dim)
-        be.upload_host(1, tgt_h, dim, index_offset=t_off)
+        if tsharded:   # queries replicated (slices over PCIe, all-gather over NVLink), this rank's own target shard
+            h2d_rank[0] = sm.upload_host_sharded(0, src_h, dim) + be.upload_host(1, tgt_h, dim, index_offset=t_off)
+        else:          # both sets replicated
+            h2d_rank[0] = sm.upload_host_sharded(0, src_h, dim) + sm.upload_host_sharded(1, tgt_h, dim)
         if tsharded:
             idx, dst, cnt = sm.knn_target_sharded(k)
             lists_h[0].copy_(idx, non_blocking=True)
@@ -291,10 +295,10 @@ def run_b200(args, wl):
     e2e_steps = max(2, min(args.steps, 5))
     ms_e2e, _ = timed(step_e2e, e2e_steps)
     e2e_value = n_src * e2e_steps / (ms_e2e * 1e-3)
-    h2d = src_h.numel() * 4 + tgt_h.numel() * 4
-    d2h_t = torch.tensor([d2h[0]], device=dev, dtype=torch.int64)
+    d2h_t = torch.tensor([d2h[0], h2d_rank[0]], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(d2h_t)
+    h2d = int(d2h_t[1].item())   # bytes all ranks together copied host -> device per step
 
     # ---- roofline of the dominant kernel (tcgen05 candidate pass): CUDA events around every launch of the
     #      timed region above, on the stream the kernel is launched on ----
@@ -338,8 +342,10 @@ def run_b200(args, wl):
                                        ("query-sharded, target replicated" if world > 1 else "single GPU"),
                            "l2": "inputs larger than L2 (no flush needed)" if n_tgt * dim * 2 > 126e6 else
                                  "inputs smaller than L2; the step rewrites >126 MB of operands/candidates between kNN passes"},
-                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d) * world,
-                        "d2h_bytes_per_step": int(d2h_t.item()), "ms_per_step": ms_e2e / e2e_steps},
+                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h_t[0].item()), "ms_per_step": ms_e2e / e2e_steps,
+                        "replication": "each rank copies 1/N of a replicated set over PCIe, NCCL all-gather over NVLink"
+                                       if world > 1 else "single GPU"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -59,6 +59,7 @@ class GpuBackend:
                                               aos_host.stride(0) * 4, dim, index_offset))
         self.ctx.n[side] = aos_host.shape[0]
         self.ctx.dim = dim
+        return aos_host.shape[0] * aos_host.stride(0) * 4
 
     # -- kernels ----------------------------------------------------------------
     def knn(self, k, direction, row_begin, row_end):
@@ -139,6 +140,20 @@ class ShardedMatcher:
             lo, hi = shard_bounds(n_total, r, self.world)
             parts.append(out[r * max_rows:r * max_rows + (hi - lo)])
         return torch.cat(parts, 0)
+
+    # -- descriptor replication over NVLink instead of PCIe ---------------------------
+    def upload_host_sharded(self, side, aos_host, dim, index_offset=0):
+        """Replicate a HOST descriptor set on every rank: rank r copies only its 1/world slice over PCIe and the
+        slices are all-gathered over NVLink (8 ranks pulling the whole set through the host's memory system at
+        once is what limits the end-to-end rate of a replicated run).  aos_host: pinned float32 [n, stride_floats]."""
+        if self.world == 1:
+            return self.b.upload_host(side, aos_host, dim, index_offset)
+        n = aos_host.shape[0]
+        lo, hi = shard_bounds(n, self.rank, self.world)
+        shard = aos_host[lo:hi].to(self.b.device, non_blocking=True)
+        full = self._all_gather_rows(shard, n)
+        self.b.upload_device(side, full, dim, index_offset)     # the pack kernel reads `full` on this same stream
+        return (hi - lo) * aos_host.stride(0) * 4               # bytes this rank moved host -> device
 
     # -- query-sharded, target replicated (SURVEY 8e, configs C3/C4) -----------------
     def match_query_sharded(self, k, mode, ratio_thr=M.MATCHING_RATIO_THRESHOLD, distance_thr=M.FLT_MAX):

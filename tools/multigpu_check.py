@@ -29,8 +29,9 @@ for desc, nq, nt, k in [("fpfh", 5003, 7001, 2), ("shot", 2111, 3005, 2), ("rops
     s_d, t_d = torch.from_numpy(src).to(dev), torch.from_numpy(tgt).to(dev)
     sd, td = np.ascontiguousarray(src[:, :dim]), np.ascontiguousarray(tgt[:, :dim])
     # --- query-sharded matcher ---
-    be.upload_device(0, s_d, dim)
-    be.upload_device(1, t_d, dim)
+    # (descriptors replicated from pinned HOST memory: 1/world slice per rank over PCIe + NCCL all-gather)
+    sm.upload_host_sharded(0, torch.from_numpy(src).pin_memory(), dim)
+    sm.upload_host_sharded(1, torch.from_numpy(tgt).pin_memory(), dim)
     for mode, oname in [(M.MODE_MUTUAL, "mutual"), (M.MODE_RATIO, "ratio")]:
         rec, n_out = sm.match_query_sharded(k, mode)[:2]
         allrec, n_all = sm.gather_records(rec, n_out)
