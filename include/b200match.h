@@ -44,7 +44,8 @@ enum {
     B200M_MODE_ONE_SIDED = 1,    /* OneSidedMatcher::match_impl, include/matching.h:395-411 */
     B200M_MODE_MUTUAL = 2,       /* LeftToRightMatcher::match_impl (k-list form), include/matching.h:428-453 */
     B200M_MODE_RATIO = 3,        /* RatioMatcher (reference stub :470-473; semantics from include/common.h:50-51) */
-    B200M_MODE_RATIO_MUTUAL = 4  /* ratio test on the forward lists, then the mutual test */
+    B200M_MODE_RATIO_MUTUAL = 4, /* ratio test on the forward lists, then the mutual test */
+    B200M_MODE_CLUSTER = 5       /* ClusterMatcher::match_impl, include/matching.h:492-517 (b200m_match_cluster only) */
 };
 
 /* how candidates are produced; the result is the same exact FP32 answer either way */
@@ -176,6 +177,32 @@ B200M_API int b200m_multiscale_add_device(b200m_ctx *ctx, int scale, size_t n_ro
                                           size_t n_train_rows, int64_t train_index_offset, size_t n_train_kps);
 B200M_API int b200m_multiscale_vote_device(b200m_ctx *ctx, const float *d_train_xyz, size_t xyz_stride_bytes,
                                            float iss_radius, int32_t *d_idx, float *d_dist, int32_t *d_count);
+
+/* ---- ClusterMatcher<FeatureT>::match_impl (include/matching.h:492-517), the reference's default matching_id --
+ * A forward pair (i, j) survives when, of the matches of i's cluster_k nearest keypoints (3-D,
+ * pcl KdTree nearestKSearch on the keypoint cloud, i itself included), fewer than
+ * MATCHING_CLUSTER_THRESHOLD (0.95) fail to land among j's cluster_k nearest keypoints -- and the same with the
+ * roles swapped over the reverse k-lists (calculateCorrespondenceDistance, :519-550).  Emitted distance =
+ * max(d_i, d_j), threshold as in b200m_match, ascending index_query then list order.
+ * b200m_match_cluster: whole call on host buffers over the uploaded sides (forward and reverse kNN, k = p->k, the
+ *   reference's two match_multiscale calls); src/tgt_kps_xyz are the keypoint coordinates of side 0 / side 1, one row
+ *   per descriptor row, `xyz_stride_bytes` apart (pcl::PointXYZ: 16).  cluster_k = AlignmentParameters::cluster_k
+ *   (MATCHING_CLUSTER_K = 40, include/common.h:53), at most 64.
+ * b200m_cluster_filter_device: the filter alone on device k-lists (e.g. b200m_multiscale_vote_device outputs with
+ *   p->k = 1); b200m_knn3d_device: the 3-D neighbourhoods alone ([n][k] int32, -1 padded when n < k; neighbours are
+ *   chosen by (squared distance, lower index)). */
+B200M_API int b200m_match_cluster(b200m_ctx *ctx, const b200m_params *p, int cluster_k, const float *src_kps_xyz,
+                                  const float *tgt_kps_xyz, size_t xyz_stride_bytes, const float *thr_src,
+                                  const float *thr_tgt, b200m_corr *out, size_t cap, size_t *n_out,
+                                  float *avg_first_dist);
+B200M_API int b200m_cluster_filter_device(b200m_ctx *ctx, const b200m_params *p, int cluster_k, float cluster_thr,
+                                          size_t n_src, size_t n_tgt, const int32_t *d_fidx, const float *d_fdist,
+                                          const int32_t *d_fcount, const int32_t *d_ridx, const int32_t *d_rcount,
+                                          const float *d_src_xyz, const float *d_tgt_xyz, size_t xyz_stride_bytes,
+                                          const float *d_thr_src, const float *d_thr_tgt, b200m_corr *d_out,
+                                          size_t cap, unsigned long long *d_n_out, float *d_avg);
+B200M_API int b200m_knn3d_device(b200m_ctx *ctx, const float *d_xyz, size_t n, size_t xyz_stride_bytes, int k,
+                                 int32_t *d_nbr);
 
 B200M_API int b200m_version(void);
 

@@ -147,6 +147,7 @@ void b200m_destroy(b200m_ctx *ctx) {
     for (DevBuf *b : ws) b->release();
     tc_release(ctx);
     multiscale_release(ctx);
+    cluster_release(ctx);
     if (ctx->pool) {
         if (ctx->pool->created)
             for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventDestroy(ctx->pool->ev[i]);
@@ -272,7 +273,7 @@ __global__ void fill_empty_kernel(size_t n_rows, int k, int32_t *idx, float *dis
 static int check_params(b200m_ctx *ctx, const b200m_params *p) {
     if (!p) return b200m_fail_msg(ctx, "null params");
     if (p->k < 1 || p->k > B200M_MAX_K) return b200m_fail_msg(ctx, "params.k must be in [1, 32]");
-    if (p->mode < B200M_MODE_KNN_ONLY || p->mode > B200M_MODE_RATIO_MUTUAL) return b200m_fail_msg(ctx, "params.mode unknown");
+    if (p->mode < B200M_MODE_KNN_ONLY || p->mode > B200M_MODE_CLUSTER) return b200m_fail_msg(ctx, "params.mode unknown");
     if (p->precision != B200M_PREC_TC_F16 && p->precision != B200M_PREC_F32_EXACT)
         return b200m_fail_msg(ctx, "params.precision unknown");
     if ((p->mode == B200M_MODE_RATIO || p->mode == B200M_MODE_RATIO_MUTUAL) && p->k < 2)
@@ -410,6 +411,7 @@ int b200m_filter_device(b200m_ctx *ctx, const b200m_params *p, size_t row_begin,
     REQUIRE_CTX();
     if (check_params(ctx, p)) return 1;
     if (p->mode == B200M_MODE_KNN_ONLY) return b200m_fail_msg(ctx, "b200m_filter: mode KNN_ONLY has no filter");
+    if (p->mode == B200M_MODE_CLUSTER) return b200m_fail_msg(ctx, "b200m_filter: the cluster filter needs keypoint coordinates, use b200m_cluster_filter_device");
     if (row_end < row_begin) return b200m_fail_msg(ctx, "b200m_filter: bad row range");
     const size_t n_rows = row_end - row_begin;
     const bool mutual = p->mode == B200M_MODE_MUTUAL || p->mode == B200M_MODE_RATIO_MUTUAL;
@@ -444,6 +446,7 @@ int b200m_match(b200m_ctx *ctx, const b200m_params *p, const float *thr_src, con
     REQUIRE_CTX();
     if (check_params(ctx, p)) return 1;
     if (p->mode == B200M_MODE_KNN_ONLY) return b200m_fail_msg(ctx, "b200m_match: use b200m_knn for raw k-lists");
+    if (p->mode == B200M_MODE_CLUSTER) return b200m_fail_msg(ctx, "b200m_match: the cluster filter needs keypoint coordinates, use b200m_match_cluster");
     if (!n_out) return b200m_fail_msg(ctx, "b200m_match: null n_out");
     *n_out = 0;
     Side &src = ctx->side[0], &tgt = ctx->side[1];

@@ -33,6 +33,7 @@ struct FilterArgs {
     const int32_t *fidx; const float *fdist; const int32_t *fcount;
     const int32_t *ridx; const float *rdist; const int32_t *rcount;
     const float *thr_src; const float *thr_tgt;
+    const float *cdist;   // cluster mode: per (row, slot) max cluster distance, negative = rejected (cluster.cu)
     long long src_offset;
 };
 
@@ -49,6 +50,11 @@ __device__ __forceinline__ bool eval_elem(const FilterArgs &a, size_t e, b200m_c
     if (a.mode == B200M_MODE_RATIO || a.mode == B200M_MODE_RATIO_MUTUAL) {
         if (fc < 2) return false;
         if (!(fd[1] >= __fmul_rn(a.ratio_thr, fd[0]))) return false;
+    }
+    if (a.mode == B200M_MODE_CLUSTER) {   // ClusterMatcher::match_impl (:503-515): the emitted distance is max(d_i, d_j)
+        const float cd = a.cdist[e];
+        if (!(cd >= 0.f)) return false;
+        d = cd;
     }
     if (a.mode == B200M_MODE_MUTUAL || a.mode == B200M_MODE_RATIO_MUTUAL) {
         if (j < 0 || (size_t) j >= a.n_rev_rows) return false;
@@ -232,10 +238,11 @@ cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, 
                           const int32_t *ridx, const float *rdist, const int32_t *rcount, size_t n_rev_rows,
                           const float *thr_src, const float *thr_tgt, int64_t src_offset,
                           b200m_corr *out, size_t cap, unsigned long long *n_out, float *avg,
-                          void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches) {
+                          void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches, const float *cdist) {
     FilterArgs a;
     a.mode = mode; a.k = k;
-    a.kk = (mode == B200M_MODE_MUTUAL) ? k : 1;
+    a.kk = (mode == B200M_MODE_MUTUAL || mode == B200M_MODE_CLUSTER) ? k : 1;
+    a.cdist = cdist;
     a.ratio_thr = ratio_thr; a.distance_thr = distance_thr;
     a.row_begin = row_begin; a.n_rows = n_rows; a.n_rev_rows = n_rev_rows;
     a.fidx = fidx; a.fdist = fdist; a.fcount = fcount;

@@ -65,6 +65,7 @@ struct b200m_ctx {
     bool totals_init = false;
     void *tmap_cache = nullptr;
     void *multiscale = nullptr;   // MultiscaleState (multiscale.cu)
+    void *cluster = nullptr;      // ClusterState (cluster.cu)
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     int tc_splits = 0;     // B200M_TC_SPLITS: 0 = chosen per launch (wave balance); > 0 forces the number of train splits
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
@@ -137,7 +138,8 @@ cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, 
                           const int32_t *ridx, const float *rdist, const int32_t *rcount, size_t n_rev_rows,
                           const float *thr_src, const float *thr_tgt, int64_t src_offset,
                           b200m_corr *out, size_t cap, unsigned long long *n_out, float *avg,
-                          void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches);
+                          void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches,
+                          const float *cdist = nullptr /* B200M_MODE_CLUSTER: [n_rows][k] from cluster.cu */);
 size_t filter_scan_ws_bytes(size_t n_rows, int k);
 cudaError_t launch_average(const float *fdist, const int32_t *fcount, size_t n_rows, int k, float *avg,
                            cudaStream_t st);
@@ -155,3 +157,6 @@ void tc_release(b200m_ctx *ctx);
 
 // multiscale.cu
 void multiscale_release(b200m_ctx *ctx);
+
+// cluster.cu
+void cluster_release(b200m_ctx *ctx);

@@ -24,12 +24,13 @@ _LIB_PATH = os.path.join(_HERE, "libb200match.so")
 CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"),
                        ("distance", "<f4"), ("threshold", "<f4")])
 
-MODE_KNN_ONLY, MODE_ONE_SIDED, MODE_MUTUAL, MODE_RATIO, MODE_RATIO_MUTUAL = 0, 1, 2, 3, 4
+MODE_KNN_ONLY, MODE_ONE_SIDED, MODE_MUTUAL, MODE_RATIO, MODE_RATIO_MUTUAL, MODE_CLUSTER = 0, 1, 2, 3, 4, 5
 PREC_TC_F16, PREC_F32_EXACT = 0, 2
 
 # reference constants (include/common.h:50-51, :42, :45)
 MATCHING_RATIO_THRESHOLD = 1.1
 MATCHING_RATIO_K = 2
+MATCHING_CLUSTER_K, MATCHING_CLUSTER_THRESHOLD = 40, 0.95   # include/common.h:52-53
 MATCHING_ONE_SIDED, MATCHING_LEFT_TO_RIGHT, MATCHING_RATIO, MATCHING_CLUSTER = "one_sided", "lr", "ratio", "cluster"
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -57,7 +58,8 @@ EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_strea
            "b200m_set_profiling", "b200m_get_stats", "b200m_reset_stats", "b200m_upload", "b200m_upload_device",
            "b200m_knn", "b200m_knn_device", "b200m_match", "b200m_filter_device", "b200m_merge_device",
            "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile", "b200m_multiscale_begin",
-           "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device"]
+           "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device", "b200m_match_cluster",
+           "b200m_cluster_filter_device", "b200m_knn3d_device"]
 
 _lib = None
 
@@ -94,6 +96,11 @@ def load_library():
     L.b200m_multiscale_vote.argtypes = [vp, fp, sz, sz, C.c_float, vp, vp, vp]
     L.b200m_multiscale_add_device.argtypes = [vp, C.c_int, sz, vp, vp, vp, vp, vp, sz, i64, sz]
     L.b200m_multiscale_vote_device.argtypes = [vp, fp, sz, C.c_float, vp, vp, vp]
+    L.b200m_match_cluster.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, fp, fp, vp, sz, C.POINTER(sz),
+                                      C.POINTER(C.c_float)]
+    L.b200m_cluster_filter_device.argtypes = [vp, C.POINTER(_Params), C.c_int, C.c_float, sz, sz, vp, vp, vp, vp, vp, fp, fp,
+                                              sz, fp, fp, vp, sz, vp, vp]
+    L.b200m_knn3d_device.argtypes = [vp, fp, sz, sz, C.c_int, vp]
     L.b200m_version.restype = C.c_int
     L.b200m_debug_operands.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, C.POINTER(C.c_float), C.POINTER(i32),
                                        C.POINTER(i64)]
@@ -111,6 +118,7 @@ class AlignmentParameters:
     bf_block_size: int = 10000          # :145 -- accepted, unused: the GPU streams the whole train set
     distance_thr: float = FLT_MAX       # :139
     ratio_k: int = MATCHING_RATIO_K     # :146
+    cluster_k: int = MATCHING_CLUSTER_K  # :146
     matching_id: str = MATCHING_LEFT_TO_RIGHT   # :149
     ratio_thr: float = MATCHING_RATIO_THRESHOLD
     precision: int = PREC_TC_F16
@@ -251,6 +259,28 @@ class Context:
         v = C.c_void_p
         self._ck(self._L.b200m_merge_device(self._h, k, n_lists, nq, v(idx_in), v(dist_in), v(cnt_in), v(idx), v(dist),
                                             v(cnt)))
+
+    # -- ClusterMatcher::match_impl (include/matching.h:492-517) ---------------------------
+    def match_cluster(self, k, cluster_k, src_kps_xyz, tgt_kps_xyz, distance_thr=FLT_MAX, thr_src=None, thr_tgt=None,
+                      precision=PREC_TC_F16, out=None):
+        """Returns (correspondences as CORR_DTYPE array, average first-NN distance)."""
+        nq, nt = self.n
+        sx = np.ascontiguousarray(src_kps_xyz, np.float32)
+        tx = np.ascontiguousarray(tgt_kps_xyz, np.float32)
+        if sx.ndim != 2 or tx.ndim != 2 or sx.shape[1] < 3 or sx.shape[1] != tx.shape[1]:
+            raise B200MatchError("keypoint coordinates must be [n, >= 3] float32 with the same row length on both sides")
+        if sx.shape[0] != nq or tx.shape[0] != nt:
+            raise B200MatchError("one keypoint per descriptor row is needed on both sides")
+        if out is None:
+            out = np.empty(max(nq * k, 1), CORR_DTYPE)
+        ts = None if thr_src is None else np.ascontiguousarray(thr_src, np.float32)
+        tt = None if thr_tgt is None else np.ascontiguousarray(thr_tgt, np.float32)
+        p = self._params(k, MODE_CLUSTER, distance_thr=distance_thr, precision=precision)
+        n_out, avg = C.c_size_t(0), C.c_float(0)
+        self._ck(self._L.b200m_match_cluster(self._h, C.byref(p), int(cluster_k), sx.ctypes.data, tx.ctypes.data, sx.strides[0],
+                                             None if ts is None else ts.ctypes.data, None if tt is None else tt.ctypes.data,
+                                             out.ctypes.data, out.shape[0], C.byref(n_out), C.byref(avg)))
+        return out[:n_out.value], float(avg.value)
 
     # -- multi-scale merge + spatial vote (match_multiscale, include/matching.h:264-354) ----
     def multiscale_begin(self, n_query_kps, n_scales, k):
@@ -398,6 +428,33 @@ class LeftToRightMatcher(FeatureBasedMatcher):
     mode, name = MODE_MUTUAL, "LeftToRightMatcher"
 
 
+class ClusterMatcher(FeatureBasedMatcher):
+    """ClusterMatcher (include/matching.h:480-551), the reference's default matching_id: needs the keypoint
+    coordinates of both sides (st_src_.kps / st_tgt_.kps) next to the descriptors."""
+    mode, name = MODE_CLUSTER, "ClusterMatcher"
+
+    def __init__(self, src_features, tgt_features, parameters, kps_xyz_src=None, kps_xyz_tgt=None, **kw):
+        super().__init__(src_features, tgt_features, parameters, **kw)
+        if kps_xyz_src is None or kps_xyz_tgt is None:
+            raise B200MatchError("ClusterMatcher needs kps_xyz_src and kps_xyz_tgt (keypoint coordinates of both sides)")
+        self.xyz_src, self.xyz_tgt = kps_xyz_src, kps_xyz_tgt
+
+    def match(self):
+        p = self.parameters
+        with Context(self.device) as ctx:
+            ctx.upload(0, self.src, self.dim)
+            ctx.upload(1, self.tgt, self.dim)
+            corrs, avg = ctx.match_cluster(self._k(), p.cluster_k, self.xyz_src, self.xyz_tgt, p.distance_thr, self.thr_src,
+                                           self.thr_tgt, p.precision)
+        corrs = corrs.copy()
+        self.average_distance_ = avg
+        if self.kps_src is not None:
+            corrs["index_query"] = np.asarray(self.kps_src, np.int32)[corrs["index_query"]]
+        if self.kps_tgt is not None:
+            corrs["index_match"] = np.asarray(self.kps_tgt, np.int32)[corrs["index_match"]]
+        return corrs
+
+
 class RatioMatcher(FeatureBasedMatcher):
     """A stub in the reference (include/matching.h:470-473); semantics defined in DESIGN.md."""
     mode, name = MODE_RATIO, "RatioMatcher"
@@ -415,4 +472,6 @@ def get_feature_based_matcher_from_parameters(src_features, tgt_features, parame
         return LeftToRightMatcher(src_features, tgt_features, parameters, **kw)
     if m == MATCHING_RATIO:
         return RatioMatcher(src_features, tgt_features, parameters, **kw)
-    raise B200MatchError("Matching method %s isn't supported by the B200 matcher (cluster filtering is a next-row item)" % m)
+    if m == MATCHING_CLUSTER:
+        return ClusterMatcher(src_features, tgt_features, parameters, **kw)
+    raise B200MatchError("Matching method %s isn't supported by the B200 matcher" % m)

@@ -448,6 +448,88 @@ ORC_API size_t orc_filter_mutual(size_t nq, int k, const int32_t *fidx, const in
     return n;
 }
 
+/* ---- ClusterMatcher (include/matching.h:480-551) --------------------------
+ * 3-D neighbourhoods: pcl::search::KdTree<PointN>::nearestKSearch(index, k) on the
+ * keypoint clouds (:524-528) -- PCL's KdTreeFLANN, exact, FLANN L2_Simple squared
+ * distance (sequential FP32 sum over x, y, z), the point itself included.  Only the
+ * SET of neighbours is used (std::unordered_set, :521-528); members are chosen here
+ * by (squared distance, lower index), so a tie AT the k-th distance resolves to the
+ * lower index (the kd-tree's choice among exactly equidistant points is unspecified:
+ * parity unpinned for that case).  nbr is [n][k], -1 padded when n < k. */
+ORC_API void orc_knn3d(size_t n, const float *xyz, int k, int32_t *nbr) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long) n; ++i) {
+        int32_t *oi = nbr + (size_t) i * k;
+        float bd[64];
+        int cnt = 0;
+        const float *a = xyz + 3 * (size_t) i;
+        for (size_t j = 0; j < n; ++j) {
+            const float *b = xyz + 3 * j;
+            float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+            float d = 0.f;
+            d += dx * dx;
+            d += dy * dy;
+            d += dz * dz;
+            if (cnt == k && !(d < bd[k - 1])) continue;   /* ascending j: an equal distance never displaces */
+            int pos = cnt < k ? cnt : k - 1;
+            while (pos > 0 && d < bd[pos - 1]) {
+                bd[pos] = bd[pos - 1];
+                oi[pos] = oi[pos - 1];
+                pos--;
+            }
+            bd[pos] = d;
+            oi[pos] = (int32_t) j;
+            if (cnt < k) cnt++;
+        }
+        for (int m = cnt; m < k; ++m) oi[m] = -1;
+    }
+}
+
+/* calculateCorrespondenceDistance (:519-550): 1 - (consistent pairs / pairs) over the matches of
+ * i's 3-D neighbours, a pair being consistent when its match is a 3-D neighbour of j. */
+static float cluster_distance(long i, long j, int ck, int k, const int32_t *fidx, const int32_t *fcount,
+                              const int32_t *nbr_a, const int32_t *nbr_b) {
+    const int32_t *ni = nbr_a + (size_t) i * ck, *nj = nbr_b + (size_t) j * ck;
+    int consistent = 0, pairs = 0;
+    for (int a = 0; a < ck; ++a) {
+        if (ni[a] < 0) continue;
+        const size_t ia = (size_t) ni[a];
+        for (int m = 0; m < fcount[ia]; ++m) {
+            int32_t match = fidx[ia * k + m];
+            for (int b = 0; b < ck; ++b)
+                if (nj[b] >= 0 && nj[b] == match) { consistent++; break; }
+            pairs++;
+        }
+    }
+    if (pairs == 0) return 0.f;
+    return 1.f - (float) consistent / (float) pairs;
+}
+
+/* ClusterMatcher::match_impl (:492-517), k-list form: for i, for j in fwd[i]: keep (i, j,
+ * max(d_i, d_j), threshold) iff both cluster distances < cluster_thr (MATCHING_CLUSTER_THRESHOLD). */
+ORC_API size_t orc_filter_cluster(size_t nq, int k, const int32_t *fidx, const int32_t *fcount, size_t nt,
+                                  const int32_t *ridx, const int32_t *rcount, int ck, const int32_t *nbr_src,
+                                  const int32_t *nbr_tgt, float cluster_thr, const float *thr_q, const float *thr_t,
+                                  float distance_thr, orc_corr *out) {
+    (void) nt;
+    size_t n = 0;
+    for (size_t i = 0; i < nq; ++i) {
+        for (int a = 0; a < fcount[i]; ++a) {
+            int32_t j = fidx[i * k + a];
+            float di = cluster_distance((long) i, j, ck, k, fidx, fcount, nbr_src, nbr_tgt);
+            float dj = cluster_distance(j, (long) i, ck, k, ridx, rcount, nbr_tgt, nbr_src);
+            if (di < cluster_thr && dj < cluster_thr) {
+                out[n].index_query = (int32_t) i;
+                out[n].index_match = j;
+                out[n].distance = di > dj ? di : dj;
+                out[n].threshold = corr_threshold(thr_q, thr_t, (long) i, j, distance_thr);
+                n++;
+            }
+        }
+    }
+    return n;
+}
+
 /* ---- ratio filter: PARITY UNPINNED ---------------------------------------
  * RatioMatcher::match_impl is a stub in the reference (include/matching.h:
  * 470-473).  Defined here from the declared constants MATCHING_RATIO_K 2 and

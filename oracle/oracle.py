@@ -70,6 +70,10 @@ def lib():
         _lib.orc_filter_mutual.restype = sz
         _lib.orc_filter_ratio.argtypes = [sz, C.c_int, ip, fp, ip, C.c_float, fp, fp, C.c_float, vp]
         _lib.orc_filter_ratio.restype = sz
+        _lib.orc_knn3d.argtypes = [sz, fp, C.c_int, ip]
+        _lib.orc_knn3d.restype = None
+        _lib.orc_filter_cluster.argtypes = [sz, C.c_int, ip, ip, sz, ip, ip, C.c_int, ip, ip, C.c_float, fp, fp, C.c_float, vp]
+        _lib.orc_filter_cluster.restype = sz
         _lib.orc_average_distance.argtypes = [sz, C.c_int, fp, ip]
         _lib.orc_average_distance.restype = C.c_float
         _lib.orc_finalize.argtypes = [vp, sz, ip, ip]
@@ -217,6 +221,30 @@ def filter_ratio(fidx, fdist, fcount, ratio_thr, distance_thr, thr_q=None, thr_t
     tq, tt = _thr(thr_q), _thr(thr_t)
     n = lib().orc_filter_ratio(nq, k, _ip(fidx), _fp(fdist), _ip(fcount), ratio_thr, _fp(tq), _fp(tt),
                                distance_thr, out.ctypes.data)
+    return out[:n].copy()
+
+
+def knn3d(xyz, k):
+    """3-D neighbourhoods of ClusterMatcher (pcl KdTree nearestKSearch(index, k), include/matching.h:524-528):
+    [n, k] int32, the point itself included, -1 padded when n < k."""
+    p = np.ascontiguousarray(np.asarray(xyz, np.float32)[:, :3])
+    if not 1 <= k <= 64:
+        raise ValueError("k must be in [1, 64]")
+    out = np.empty((p.shape[0], k), np.int32)
+    lib().orc_knn3d(p.shape[0], _fp(p), k, _ip(out))
+    return out
+
+
+def filter_cluster(fidx, fcount, ridx, rcount, nbr_src, nbr_tgt, distance_thr, cluster_thr=np.float32(0.95), thr_q=None,
+                   thr_t=None):
+    """ClusterMatcher::match_impl, k-list form (include/matching.h:492-517); MATCHING_CLUSTER_THRESHOLD = 0.95f."""
+    nq, k = fidx.shape
+    nt = ridx.shape[0]
+    out = np.empty(max(nq * k, 1), CORR_DTYPE)
+    tq, tt = _thr(thr_q), _thr(thr_t)
+    ns, ng = np.ascontiguousarray(nbr_src, np.int32), np.ascontiguousarray(nbr_tgt, np.int32)
+    n = lib().orc_filter_cluster(nq, k, _ip(fidx), _ip(fcount), nt, _ip(ridx), _ip(rcount), ns.shape[1], _ip(ns), _ip(ng),
+                                 cluster_thr, _fp(tq), _fp(tt), distance_thr, out.ctypes.data)
     return out[:n].copy()
 
 

@@ -371,3 +371,43 @@ def test_match_multiscale_vote_equals_oracle(desc, k, n_scales):
     if k * n_scales > 1:   # the vote is not the identity: some keypoints do not keep their nearest descriptor
         first = np.array([c[0] if c else -1 for c in comb_i])
         assert np.any(gi != first)
+
+
+@pytest.mark.parametrize("desc,nq,nt,k,ck", [("fpfh", 1500, 1700, 1, 40), ("shot", 600, 500, 2, 40), ("rops", 400, 450, 3, 10),
+                                             ("fpfh", 30, 25, 1, 40)])
+def test_cluster_matcher_equals_oracle(desc, nq, nt, k, ck):
+    """ClusterMatcher::match_impl (reference include/matching.h:492-517, the default matching_id): forward and reverse
+    kNN, 3-D neighbourhoods of the keypoints (cluster_k nearest, the point itself included), consistency distances both
+    ways, threshold 0.95 -- the same records as the oracle's restatement; the last case has fewer keypoints than cluster_k."""
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    rng = np.random.default_rng(3)
+    # keypoints: the target cloud is the source cloud moved rigidly + noise where descriptors correspond, so that the
+    # geometric consistency check keeps a real fraction; PointXYZ rows (16 B)
+    sx = np.zeros((nq, 4), np.float32)
+    tx = np.zeros((nt, 4), np.float32)
+    sx[:, :3] = rng.random((nq, 3)) * 10
+    fi, fd, fc = orc.knn(_dense(src, dim), _dense(tgt, dim), 1)
+    tx[:, :3] = rng.random((nt, 3)) * 10
+    good = fc > 0
+    tx[fi[good, 0], :3] = sx[good, :3] + np.float32(0.01) * rng.standard_normal((int(good.sum()), 3)).astype(np.float32)
+    thr_s = rng.random(nq).astype(np.float32)
+    thr_t = rng.random(nt).astype(np.float32)
+    dthr = np.float32(0.6)
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        got, avg = ctx.match_cluster(k, ck, sx, tx, dthr, thr_s, thr_t)
+    fidx, fdist, fcnt = orc.knn(_dense(src, dim), _dense(tgt, dim), k)
+    ridx, rdist, rcnt = orc.knn(_dense(tgt, dim), _dense(src, dim), k)
+    ns, ng = orc.knn3d(sx[:, :3], ck), orc.knn3d(tx[:, :3], ck)
+    exp = orc.filter_cluster(fidx, fcnt, ridx, rcnt, ns, ng, dthr, thr_q=thr_s, thr_t=thr_t)
+    assert len(exp) > 0
+    if min(nq, nt) > ck:
+        assert len(exp) < fcnt.sum()          # the filter keeps some pairs and rejects some
+    assert got.tobytes() == exp.tobytes()
+    assert avg == orc.average_distance(fdist, fcnt)
+    # the reference-shaped class
+    params = M.AlignmentParameters(randomness=k, matching_id=M.MATCHING_CLUSTER, cluster_k=ck, distance_thr=float(dthr))
+    m = M.get_feature_based_matcher_from_parameters(src, tgt, params, dim=dim, kps_xyz_src=sx, kps_xyz_tgt=tx,
+                                                    thresholds_src=thr_s, thresholds_tgt=thr_t)
+    assert m.get_class_name() == "ClusterMatcher" and m.match().tobytes() == exp.tobytes()

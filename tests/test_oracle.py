@@ -201,3 +201,44 @@ def test_simd_layout_is_bit_identical_to_scalar(desc, nq, nt, k):
     b = orc.knn(s[:, :d], t[:, :d], k, scalar=True)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_cluster_filter_matches_a_literal_restatement():
+    """orc_knn3d / orc_filter_cluster against ClusterMatcher::match_impl + calculateCorrespondenceDistance written out
+    with Python sets, line by line (reference include/matching.h:492-550)."""
+    rng = np.random.default_rng(9)
+    nq, nt, k, ck = 120, 140, 2, 7
+    sx, tx = rng.random((nq, 3)).astype(np.float32), rng.random((nt, 3)).astype(np.float32)
+    src, tgt = rng.random((nq, 8)).astype(np.float32), rng.random((nt, 8)).astype(np.float32)
+    fidx, fdist, fcnt = orc.knn(src, tgt, k)
+    ridx, rdist, rcnt = orc.knn(tgt, src, k)
+    ns, ng = orc.knn3d(sx, ck), orc.knn3d(tx, ck)
+
+    def knn_set(p, i):          # nearestKSearch(i, ck): the ck nearest by FLANN's L2_Simple, the point itself included
+        d = np.zeros(p.shape[0], np.float32)
+        for c in range(3):
+            diff = p[i, c] - p[:, c]
+            d = d + diff * diff
+        return set(np.lexsort((np.arange(p.shape[0]), d))[:ck].tolist())
+    for i in (0, 17, nq - 1):
+        assert set(ns[i].tolist()) == knn_set(sx, i)
+
+    def corr_distance(i, j, lists, counts, p_a, p_b):
+        i_nb, j_nb = knn_set(p_a, i), knn_set(p_b, j)
+        consistent = pairs = 0
+        for a in i_nb:
+            for m in range(counts[a]):
+                if int(lists[a, m]) in j_nb:
+                    consistent += 1
+                pairs += 1
+        return np.float32(0) if pairs == 0 else np.float32(1) - np.float32(consistent) / np.float32(pairs)
+    exp = []
+    for i in range(nq):
+        for a in range(fcnt[i]):
+            j = int(fidx[i, a])
+            di, dj = corr_distance(i, j, fidx, fcnt, sx, tx), corr_distance(j, i, ridx, rcnt, tx, sx)
+            if di < np.float32(0.95) and dj < np.float32(0.95):
+                exp.append((i, j, max(di, dj)))
+    got = orc.filter_cluster(fidx, fcnt, ridx, rcnt, ns, ng, np.float32(1.0))
+    assert [(int(c["index_query"]), int(c["index_match"]), np.float32(c["distance"])) for c in got] == exp
+    assert 0 < len(exp) < fcnt.sum()
