@@ -121,6 +121,20 @@ B200M_API int b200m_knn(b200m_ctx *ctx, const b200m_params *p, int direction, si
 B200M_API int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin,
                                size_t row_end, int32_t *d_idx, float *d_dist, int32_t *d_count);
 
+/* ---- matchLocal with a finite match_search_radius (include/matching.h:637-678): the guess-conditioned kNN
+ * match_multiscale uses when AlignmentParameters::guess is set (:297-304).  query_xyz: the query side's keypoints
+ * AFTER the guess transform (pcl::transformPointCloudWithNormals, :644 -- done by the caller, so its arithmetic stays
+ * PCL's), train_xyz: the train side's keypoints; one row per descriptor row, `xyz_stride_bytes` apart.  A train row
+ * is considered iff its squared 3-D distance (FLANN L2_Simple) is < radius*radius; among equal descriptor distances the
+ * spatially nearer row comes first (radiusSearch's sorted order + KNNResult), then the lower index.  Exact CUDA-core
+ * path (one CTA per query row); outputs as b200m_knn's. */
+B200M_API int b200m_knn_local(b200m_ctx *ctx, const b200m_params *p, int direction, const float *query_xyz,
+                              const float *train_xyz, size_t xyz_stride_bytes, float radius, int32_t *idx,
+                              float *dist, int32_t *count);
+B200M_API int b200m_knn_local_device(b200m_ctx *ctx, const b200m_params *p, int direction, const float *d_query_xyz,
+                                     const float *d_train_xyz, size_t xyz_stride_bytes, float radius,
+                                     int32_t *d_idx, float *d_dist, int32_t *d_count);
+
 /* ---- whole matcher call: replaces FeatureBasedMatcher::match()'s match_impl ------
  * (include/matching.h:395-411, :428-453) at the k-list seam, single GPU, host buffers.
  * thr_src / thr_tgt: optional per-point thresholds (calculateSmoothedDensities,

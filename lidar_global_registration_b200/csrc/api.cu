@@ -402,6 +402,65 @@ int b200m_knn(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_b
     return 0;
 }
 
+// ---- matchLocal with a finite radius ------------------------------------------------------------------
+int b200m_knn_local_device(b200m_ctx *ctx, const b200m_params *p, int direction, const float *d_query_xyz,
+                           const float *d_train_xyz, size_t xyz_stride_bytes, float radius, int32_t *d_idx, float *d_dist,
+                           int32_t *d_count) {
+    REQUIRE_CTX();
+    if (check_params(ctx, p)) return 1;
+    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "b200m_knn_local: direction must be 0 or 1");
+    if (xyz_stride_bytes % 4 != 0 || xyz_stride_bytes < 12) return b200m_fail_msg(ctx, "b200m_knn_local: xyz stride must be a multiple of 4 and >= 12 bytes");
+    Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    if (q.n == 0) return 0;
+    if (!d_idx || !d_dist || !d_count) return b200m_fail_msg(ctx, "b200m_knn_local: null output pointer");
+    if (t.n && q.dim != t.dim) return b200m_fail_msg(ctx, "b200m_knn_local: source and target descriptor lengths differ");
+    ctx->stats.rows_total += (int64_t) q.n;
+    if (t.n == 0) {
+        size_t ne = q.n * (size_t) p->k;
+        fill_empty_kernel<<<(unsigned) ((ne + 255) / 256), 256, 0, ctx->stream>>>(q.n, p->k, d_idx, d_dist, d_count);
+        ctx->stats.launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    if (!d_query_xyz || !d_train_xyz) return b200m_fail_msg(ctx, "b200m_knn_local: null keypoint coordinates");
+    StatTimer tf(ctx, &ctx->stats.ms_fallback);
+    CK(launch_local_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, t.f32.as<float>(), t.valid.as<uint8_t>(), t.n,
+                         t.index_offset, q.n, d_query_xyz, d_train_xyz, xyz_stride_bytes, radius, p->k, d_idx, d_dist, d_count,
+                         1 << 30, ctx->stream));
+    ctx->stats.launches += 1;
+    tf.stop();
+    return 0;
+}
+
+int b200m_knn_local(b200m_ctx *ctx, const b200m_params *p, int direction, const float *query_xyz, const float *train_xyz,
+                    size_t xyz_stride_bytes, float radius, int32_t *idx, float *dist, int32_t *count) {
+    REQUIRE_CTX();
+    if (check_params(ctx, p)) return 1;
+    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "b200m_knn_local: direction must be 0 or 1");
+    if (xyz_stride_bytes % 4 != 0 || xyz_stride_bytes < 12) return b200m_fail_msg(ctx, "b200m_knn_local: xyz stride must be a multiple of 4 and >= 12 bytes");
+    Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    const size_t nq = q.n, nt = t.n;
+    if (nq == 0) return 0;
+    if (!idx || !dist || !count) return b200m_fail_msg(ctx, "b200m_knn_local: null output pointer");
+    if (!query_xyz || (nt && !train_xyz)) return b200m_fail_msg(ctx, "b200m_knn_local: null keypoint coordinates");
+    const int k = p->k;
+    CK(ctx->ws_fidx.reserve(sizeof(int32_t) * nq * k));
+    CK(ctx->ws_fdist.reserve(sizeof(float) * nq * k));
+    CK(ctx->ws_fcnt.reserve(sizeof(int32_t) * nq));
+    CK(ctx->ws_thr[0].reserve(nq * xyz_stride_bytes + 16));
+    CK(ctx->ws_thr[1].reserve(nt * xyz_stride_bytes + 16));
+    CK(cudaMemcpyAsync(ctx->ws_thr[0].p, query_xyz, (nq - 1) * xyz_stride_bytes + 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (nt) CK(cudaMemcpyAsync(ctx->ws_thr[1].p, train_xyz, (nt - 1) * xyz_stride_bytes + 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (b200m_knn_local_device(ctx, p, direction, ctx->ws_thr[0].as<float>(), ctx->ws_thr[1].as<float>(), xyz_stride_bytes, radius,
+                               ctx->ws_fidx.as<int32_t>(), ctx->ws_fdist.as<float>(), ctx->ws_fcnt.as<int32_t>()))
+        return 1;
+    CK(cudaMemcpyAsync(idx, ctx->ws_fidx.p, sizeof(int32_t) * nq * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist, ctx->ws_fdist.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(count, ctx->ws_fcnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ---- filters ----------------------------------------------------------------------------
 int b200m_filter_device(b200m_ctx *ctx, const b200m_params *p, size_t row_begin, size_t row_end,
                         const int32_t *d_fidx, const float *d_fdist, const int32_t *d_fcount,

@@ -137,6 +137,103 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
     }
 }
 
+// ---- matchLocal with a finite search radius (reference include/matching.h:637-678) ------------------------
+// One CTA per query row over ALL train rows: the 3-D gate first -- FLANN's L2_Simple squared distance between the
+// (guess-transformed) query keypoint and the train keypoint, strictly below radius^2 (KdTree::radiusSearch, :661) --
+// then pcl::L2_Norm on the descriptors of the gated rows only.  radiusSearch returns its hits sorted by spatial distance
+// and KNNResult keeps the earlier insertion first among equal descriptor distances, so the order is
+// (descriptor distance, spatial distance, index).
+__device__ __forceinline__ bool lex3_less(float d1, float s1, int i1, float d2, float s2, int i2) {
+    return d1 < d2 || (d1 == d2 && (s1 < s2 || (s1 == s2 && i1 < i2)));
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kExactThreads)
+local_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_valid, int dp,
+                  const float *__restrict__ t_f32, const uint8_t *__restrict__ t_valid, size_t nt, long long t_off,
+                  size_t n_rows, const float *__restrict__ q_xyz, const float *__restrict__ t_xyz, size_t xyz_stride_floats,
+                  float r2, int k, int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count) {
+    extern __shared__ float smem[];
+    float *sq = smem;
+    float *red_d = smem + dp;
+    float *red_s = red_d + kExactThreads / 32;
+    int *red_i = reinterpret_cast<int *>(red_s + kExactThreads / 32);
+    int *red_w = red_i + kExactThreads / 32;
+    __shared__ float win_d, win_s;
+    __shared__ int win_i, win_t;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t qi = blockIdx.x; qi < n_rows; qi += gridDim.x) {
+        int32_t *oi = idx + qi * k;
+        float *od = dist + qi * k;
+        if (!q_valid[qi]) {   // non-finite query -> empty entry (:658)
+            if (tid < k) { oi[tid] = -1; od[tid] = 0.f; }
+            if (tid == 0) count[qi] = 0;
+            continue;
+        }
+        __syncthreads();
+        for (int d = tid; d < dp; d += kExactThreads) sq[d] = q_f32[qi * (size_t) dp + d];
+        __syncthreads();
+        const float ax = q_xyz[qi * xyz_stride_floats], ay = q_xyz[qi * xyz_stride_floats + 1], az = q_xyz[qi * xyz_stride_floats + 2];
+        float ld[KMAX], ls[KMAX];
+        int li[KMAX];
+#pragma unroll
+        for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; ls[m] = INFINITY; li[m] = INT_MAX; }
+        for (size_t j = tid; j < nt; j += kExactThreads) {
+            const float *b = t_xyz + j * xyz_stride_floats;
+            const float dx = __fsub_rn(ax, b[0]), dy = __fsub_rn(ay, b[1]), dz = __fsub_rn(az, b[2]);
+            const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (!(s < r2) || !t_valid[j]) continue;
+            float cd = __fsqrt_rn(seq_sqdist(sq, t_f32 + j * (size_t) dp, dp));
+            float cs = s;
+            int ci = (int) j;
+            if (lex3_less(cd, cs, ci, ld[KMAX - 1], ls[KMAX - 1], li[KMAX - 1])) {
+#pragma unroll
+                for (int m = 0; m < KMAX; ++m) {
+                    if (lex3_less(cd, cs, ci, ld[m], ls[m], li[m])) {
+                        float td = ld[m], tsp = ls[m]; int ti = li[m];
+                        ld[m] = cd; ls[m] = cs; li[m] = ci;
+                        cd = td; cs = tsp; ci = ti;
+                    }
+                }
+            }
+        }
+        int head = 0, found = 0;
+        for (int round = 0; round < k; ++round) {
+            float hd = INFINITY, hs = INFINITY;
+            int hi = INT_MAX;
+#pragma unroll
+            for (int m = 0; m < KMAX; ++m)
+                if (m == head) { hd = ld[m]; hs = ls[m]; hi = li[m]; }
+            float bd = hd, bs = hs;
+            int bi = hi, bt = tid;
+            for (int o = 16; o > 0; o >>= 1) {
+                float od2 = __shfl_xor_sync(0xffffffffu, bd, o);
+                float os2 = __shfl_xor_sync(0xffffffffu, bs, o);
+                int oi2 = __shfl_xor_sync(0xffffffffu, bi, o);
+                int ot2 = __shfl_xor_sync(0xffffffffu, bt, o);
+                if (lex3_less(od2, os2, oi2, bd, bs, bi)) { bd = od2; bs = os2; bi = oi2; bt = ot2; }
+            }
+            if (lane == 0) { red_d[warp] = bd; red_s[warp] = bs; red_i[warp] = bi; red_w[warp] = bt; }
+            __syncthreads();
+            if (tid == 0) {
+                float wd = red_d[0], ws = red_s[0];
+                int wi = red_i[0], wt = red_w[0];
+                for (int w = 1; w < kExactThreads / 32; ++w)
+                    if (lex3_less(red_d[w], red_s[w], red_i[w], wd, ws, wi)) { wd = red_d[w]; ws = red_s[w]; wi = red_i[w]; wt = red_w[w]; }
+                win_d = wd; win_s = ws; win_i = wi; win_t = wt;
+            }
+            __syncthreads();
+            if (win_i == INT_MAX) break;
+            if (tid == win_t) head++;
+            if (tid == 0) { oi[round] = (int32_t) (win_i + t_off); od[round] = win_d; }
+            found = round + 1;
+            __syncthreads();
+        }
+        if (tid >= found && tid < k) { oi[tid] = -1; od[tid] = 0.f; }
+        if (tid == 0) count[qi] = found;
+    }
+}
+
 // ---- exact rows, split over the whole grid (a FEW flagged rows) -------------------------------
 // The one-CTA-per-row kernel above streams the entire train set through a single SM per row -- 700 MB at 15 GB/s for
 // SHOT-352 x 500k, tens of milliseconds for one overflowed row.  Here every CTA scans its slice of the train set for
@@ -600,6 +697,30 @@ cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp
     if (k <= 16) B200M_EXACT_CASE(16);
     B200M_EXACT_CASE(32);
 #undef B200M_EXACT_CASE
+}
+
+cudaError_t launch_local_rows(const float *q_f32, const uint8_t *q_valid, int dp, const float *t_f32,
+                              const uint8_t *t_valid, size_t nt, int64_t t_index_offset, size_t n_rows,
+                              const float *q_xyz, const float *t_xyz, size_t xyz_stride_bytes, float radius, int k,
+                              int32_t *idx, float *dist, int32_t *count, int max_blocks, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    const int blocks = (int) (n_rows < (size_t) max_blocks ? n_rows : (size_t) max_blocks);
+    const size_t smem = sizeof(float) * dp + (2 * sizeof(float) + 2 * sizeof(int)) * (kExactThreads / 32);
+    const float r2 = radius * radius;   // radiusSearch is handed radius * radius (FP32 product)
+#define B200M_LOCAL_CASE(K)                                                                                            \
+    do {                                                                                                               \
+        local_rows_kernel<K><<<blocks, kExactThreads, smem, st>>>(q_f32, q_valid, dp, t_f32, t_valid, nt,              \
+                                                                  (long long) t_index_offset, n_rows, q_xyz, t_xyz,    \
+                                                                  xyz_stride_bytes / 4, r2, k, idx, dist, count);      \
+        return cudaGetLastError();                                                                                     \
+    } while (0)
+    if (k <= 1) B200M_LOCAL_CASE(1);
+    if (k <= 2) B200M_LOCAL_CASE(2);
+    if (k <= 4) B200M_LOCAL_CASE(4);
+    if (k <= 8) B200M_LOCAL_CASE(8);
+    if (k <= 16) B200M_LOCAL_CASE(16);
+    B200M_LOCAL_CASE(32);
+#undef B200M_LOCAL_CASE
 }
 
 size_t exact_split_ws_entries(int split_blocks, int k) { return (size_t) kSplitMaxRows * (size_t) split_blocks * (size_t) k; }

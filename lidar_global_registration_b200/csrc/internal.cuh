@@ -121,6 +121,10 @@ cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp
                               // few flagged rows (row_list given): split_blocks CTAs share every row; workspace of
                               // exact_split_ws_entries() int32 + float entries and exact_split_max_rows() zeroed counters
                               int split_blocks, int32_t *part_i, float *part_d, unsigned int *done, cudaStream_t st);
+cudaError_t launch_local_rows(const float *q_f32, const uint8_t *q_valid, int dp, const float *t_f32,
+                              const uint8_t *t_valid, size_t nt, int64_t t_index_offset, size_t n_rows,
+                              const float *q_xyz, const float *t_xyz, size_t xyz_stride_bytes, float radius, int k,
+                              int32_t *idx, float *dist, int32_t *count, int max_blocks, cudaStream_t st);
 size_t exact_split_ws_entries(int split_blocks, int k);
 int exact_split_max_rows();
 cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, int dim,

@@ -59,7 +59,7 @@ EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_strea
            "b200m_knn", "b200m_knn_device", "b200m_match", "b200m_filter_device", "b200m_merge_device",
            "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile", "b200m_multiscale_begin",
            "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device", "b200m_match_cluster",
-           "b200m_cluster_filter_device", "b200m_knn3d_device"]
+           "b200m_cluster_filter_device", "b200m_knn3d_device", "b200m_knn_local", "b200m_knn_local_device"]
 
 _lib = None
 
@@ -101,6 +101,8 @@ def load_library():
     L.b200m_cluster_filter_device.argtypes = [vp, C.POINTER(_Params), C.c_int, C.c_float, sz, sz, vp, vp, vp, vp, vp, fp, fp,
                                               sz, fp, fp, vp, sz, vp, vp]
     L.b200m_knn3d_device.argtypes = [vp, fp, sz, sz, C.c_int, vp]
+    L.b200m_knn_local.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
+    L.b200m_knn_local_device.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
     L.b200m_version.restype = C.c_int
     L.b200m_debug_operands.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, C.POINTER(C.c_float), C.POINTER(i32),
                                        C.POINTER(i64)]
@@ -218,6 +220,19 @@ class Context:
         p = self._params(k, MODE_KNN_ONLY, precision=precision, cand_cap=cand_cap)
         self._ck(self._L.b200m_knn(self._h, C.byref(p), direction, row_begin, re, idx.ctypes.data, dist.ctypes.data,
                                    cnt.ctypes.data))
+        return idx, dist, cnt
+
+    def knn_local(self, k, query_xyz, train_xyz, radius, direction=0):
+        """matchLocal with a finite match_search_radius: query_xyz are the query keypoints after the guess transform."""
+        qx = np.ascontiguousarray(query_xyz, np.float32)
+        tx = np.ascontiguousarray(train_xyz, np.float32)
+        nq, nt = self.n[direction], self.n[1 - direction]
+        if qx.ndim != 2 or tx.ndim != 2 or qx.shape[1] < 3 or qx.shape[1] != tx.shape[1] or qx.shape[0] != nq or tx.shape[0] != nt:
+            raise B200MatchError("keypoint coordinates: [n, >= 3] float32, one row per descriptor row, same row length on both sides")
+        idx, dist, cnt = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32), np.empty((nq,), np.int32)
+        p = self._params(k, MODE_KNN_ONLY)
+        self._ck(self._L.b200m_knn_local(self._h, C.byref(p), direction, qx.ctypes.data, tx.ctypes.data, qx.strides[0],
+                                         float(radius), idx.ctypes.data, dist.ctypes.data, cnt.ctypes.data))
         return idx, dist, cnt
 
     def knn_device(self, k, direction, row_begin, row_end, idx_ptr, dist_ptr, cnt_ptr, precision=PREC_TC_F16, cand_cap=0):
@@ -351,10 +366,26 @@ def match_flann(query_features, train_features, parameters, dim=None, device=0):
     return match_bf(query_features, train_features, parameters, dim, device)
 
 
-def match_local(query_features, train_features, parameters, dim=None, device=0):
-    """matchLocal<FeatureT> with match_search_radius = inf (include/matching.h:637-678, as the reference's
-    test calls it, tests/flann_bf_matcher.h:66-72).  The spatially gated variant is a next-row item."""
-    return match_bf(query_features, train_features, parameters, dim, device)
+def match_local(query_features, train_features, parameters, dim=None, device=0, query_kps_xyz=None, train_kps_xyz=None,
+                guess=None, match_search_radius=None):
+    """matchLocal<FeatureT> (include/matching.h:637-678).  Without keypoints / radius: match_search_radius = inf, as
+    the reference's test calls it (tests/flann_bf_matcher.h:66-72) == the plain exact kNN.  With them: only train rows
+    whose keypoint lies within match_search_radius of the guess-transformed query keypoint are considered.  `guess`
+    (4x4) is applied here in float32 (x' = R x + t); pass already transformed keypoints and guess=None to keep PCL's own
+    transformPointCloudWithNormals arithmetic."""
+    if query_kps_xyz is None or train_kps_xyz is None or match_search_radius is None or not np.isfinite(match_search_radius):
+        return match_bf(query_features, train_features, parameters, dim, device)
+    qx = np.ascontiguousarray(query_kps_xyz, np.float32)
+    if guess is not None:
+        g = np.asarray(guess, np.float32)
+        moved = qx.copy()
+        moved[:, :3] = qx[:, :3] @ g[:3, :3].T + g[:3, 3]
+        qx = moved
+    dim = dim or np.asarray(query_features).shape[1]
+    with Context(device) as ctx:
+        ctx.upload(0, query_features, dim)
+        ctx.upload(1, train_features, dim)
+        return ctx.knn_local(parameters.randomness, qx, train_kps_xyz, match_search_radius)
 
 
 def match_multiscale(query_scales, train_scales, n_query_kps, train_kps_xyz, iss_radius, parameters, dim=None, device=0):

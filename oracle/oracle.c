@@ -219,6 +219,60 @@ ORC_API void orc_knn_scalar(const float *query, size_t nq, size_t q_stride,
     free(tvalid);
 }
 
+/* ---- matchLocal with a finite match_search_radius (include/matching.h:637-678) -------
+ * Per valid query: radiusSearch on the train keypoints around the (already guess-transformed) query keypoint --
+ * FLANN L2_Simple squared distance (sequential FP32 sum) strictly below radius*radius, results sorted by that
+ * distance (PCL's default) -- then pcl::L2_Norm on the descriptors of the gated, valid train rows, inserted into
+ * KNNResult in that order: equal descriptor distances keep the spatially nearer row first.  (Equal spatial distances
+ * too: lower index first here; FLANN's order among them is unspecified -- unpinned.)
+ * query_xyz / train_xyz are [n][3]. */
+typedef struct { float d2; int32_t j; } orc_gate;
+static int gate_cmp(const void *a, const void *b) {
+    const orc_gate *x = (const orc_gate *) a, *y = (const orc_gate *) b;
+    if (x->d2 < y->d2) return -1;
+    if (x->d2 > y->d2) return 1;
+    return (x->j > y->j) - (x->j < y->j);
+}
+ORC_API void orc_match_local(const float *query, size_t nq, size_t q_stride, const float *train, size_t nt,
+                             size_t t_stride, int dim, int k, const float *query_xyz, const float *train_xyz,
+                             float radius, int32_t *idx, float *dist, int32_t *count) {
+    const float r2 = radius * radius;
+#pragma omp parallel
+    {
+        orc_gate *g = (orc_gate *) malloc(sizeof(orc_gate) * (nt ? nt : 1));
+#pragma omp for schedule(dynamic, 16)
+        for (long i = 0; i < (long) nq; ++i) {
+            int32_t *oi = idx + (size_t) i * k;
+            float *od = dist + (size_t) i * k;
+            for (int m = 0; m < k; ++m) { oi[m] = -1; od[m] = 0.f; }
+            count[i] = 0;
+            const float *q = row_at(query, q_stride, i);
+            if (!orc_is_valid(q, dim)) continue;
+            const float *a = query_xyz + 3 * (size_t) i;
+            size_t ng = 0;
+            for (size_t j = 0; j < nt; ++j) {
+                const float *b = train_xyz + 3 * j;
+                float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+                float d2 = 0.f;
+                d2 += dx * dx;
+                d2 += dy * dy;
+                d2 += dz * dz;
+                if (d2 < r2) { g[ng].d2 = d2; g[ng].j = (int32_t) j; ng++; }
+            }
+            qsort(g, ng, sizeof(orc_gate), gate_cmp);
+            orc_knn_result r;
+            orc_knn_result_init(&r, k, oi, od);
+            for (size_t e = 0; e < ng; ++e) {
+                const float *t = row_at(train, t_stride, g[e].j);
+                if (!orc_is_valid(t, dim)) continue;
+                orc_knn_result_add(&r, orc_l2_norm(q, t, dim), g[e].j);
+            }
+            count[i] = r.count;
+        }
+        free(g);
+    }
+}
+
 /* Same function, same per-pair arithmetic (bit-identical output, asserted in
  * tests/test_oracle.py), laid out for the CPU baseline timing: 8 train rows per
  * SIMD vector (one lane == one (query, train) pair, still a sequential

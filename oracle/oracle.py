@@ -70,6 +70,8 @@ def lib():
         _lib.orc_filter_mutual.restype = sz
         _lib.orc_filter_ratio.argtypes = [sz, C.c_int, ip, fp, ip, C.c_float, fp, fp, C.c_float, vp]
         _lib.orc_filter_ratio.restype = sz
+        _lib.orc_match_local.argtypes = [fp, sz, sz, fp, sz, sz, C.c_int, C.c_int, fp, fp, C.c_float, ip, fp, ip]
+        _lib.orc_match_local.restype = None
         _lib.orc_knn3d.argtypes = [sz, fp, C.c_int, ip]
         _lib.orc_knn3d.restype = None
         _lib.orc_filter_cluster.argtypes = [sz, C.c_int, ip, ip, sz, ip, ip, C.c_int, ip, ip, C.c_float, fp, fp, C.c_float, vp]
@@ -222,6 +224,23 @@ def filter_ratio(fidx, fdist, fcount, ratio_thr, distance_thr, thr_q=None, thr_t
     n = lib().orc_filter_ratio(nq, k, _ip(fidx), _fp(fdist), _ip(fcount), ratio_thr, _fp(tq), _fp(tt),
                                distance_thr, out.ctypes.data)
     return out[:n].copy()
+
+
+def match_local(query, train, k, query_xyz, train_xyz, radius):
+    """matchLocal with a finite match_search_radius (include/matching.h:637-678); query_xyz are the query keypoints
+    AFTER the guess transform.  Returns (idx, dist, count) like knn()."""
+    q, _, qs = _rows(query)
+    t, _, ts = _rows(train)
+    qx = np.ascontiguousarray(np.asarray(query_xyz, np.float32)[:, :3])
+    tx = np.ascontiguousarray(np.asarray(train_xyz, np.float32)[:, :3])
+    assert qx.shape[0] == q.shape[0] and tx.shape[0] == t.shape[0]
+    dim = q.shape[1]
+    idx = np.empty((q.shape[0], k), np.int32)
+    dist = np.empty((q.shape[0], k), np.float32)
+    cnt = np.empty((q.shape[0],), np.int32)
+    lib().orc_match_local(_fp(q), q.shape[0], qs, _fp(t), t.shape[0], ts, dim, k, _fp(qx), _fp(tx), radius, _ip(idx),
+                          _fp(dist), _ip(cnt))
+    return idx, dist, cnt
 
 
 def knn3d(xyz, k):

@@ -411,3 +411,38 @@ def test_cluster_matcher_equals_oracle(desc, nq, nt, k, ck):
     m = M.get_feature_based_matcher_from_parameters(src, tgt, params, dim=dim, kps_xyz_src=sx, kps_xyz_tgt=tx,
                                                     thresholds_src=thr_s, thresholds_tgt=thr_t)
     assert m.get_class_name() == "ClusterMatcher" and m.match().tobytes() == exp.tobytes()
+
+
+@pytest.mark.parametrize("desc,nq,nt,k,radius", [("fpfh", 900, 1200, 2, 1.5), ("shot", 300, 500, 5, 3.0), ("rops", 250, 300, 1, 0.4),
+                                                 ("fpfh", 400, 300, 3, 100.0)])
+def test_match_local_with_search_radius_equals_oracle(desc, nq, nt, k, radius):
+    """matchLocal with a finite match_search_radius (reference include/matching.h:637-678): only train rows whose keypoint
+    is within the radius of the (transformed) query keypoint compete; lists shorter than k where the gate leaves fewer
+    rows; the last case's radius covers everything (== plain kNN up to the order of exactly tied distances)."""
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    rng = np.random.default_rng(5)
+    qx = np.zeros((nq, 4), np.float32)
+    tx = np.zeros((nt, 4), np.float32)
+    qx[:, :3] = rng.random((nq, 3)) * 6
+    tx[:, :3] = rng.random((nt, 3)) * 6
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        got = ctx.knn_local(k, qx, tx, radius)
+        got_rev = ctx.knn_local(k, tx, qx, radius, direction=1)
+    exp = orc.match_local(_dense(src, dim), _dense(tgt, dim), k, qx[:, :3], tx[:, :3], radius)
+    _same(got, exp)
+    _same(got_rev, orc.match_local(_dense(tgt, dim), _dense(src, dim), k, tx[:, :3], qx[:, :3], radius))
+    if radius < 50:
+        assert (exp[2] < k).any() and (exp[2] > 0).any()      # the gate bites
+        full = orc.knn(_dense(src, dim), _dense(tgt, dim), k)
+        assert not np.array_equal(full[0], exp[0])
+    # the reference-shaped free function, with a guess: a pure translation moves the query keypoints into place
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = [0.5, -0.25, 1.0]
+    moved = qx.copy()
+    moved[:, :3] = qx[:, :3] - guess[:3, 3]
+    params = M.AlignmentParameters(randomness=k)
+    got2 = M.match_local(src, tgt, params, dim=dim, query_kps_xyz=moved, train_kps_xyz=tx, guess=guess, match_search_radius=radius)
+    back = moved[:, :3] @ guess[:3, :3].T + guess[:3, 3]
+    _same(got2, orc.match_local(_dense(src, dim), _dense(tgt, dim), k, back, tx[:, :3], radius))
