@@ -324,6 +324,16 @@ def run_b200(args, wl):
                 "candidates_per_row": st["candidates"] / max(st["rows_total"], 1),
                 "rows_overflowed_frac": st["rows_flagged"] / max(st["rows_total"], 1)}
 
+    # Second yardstick (for short descriptors the limiter is the accumulator drain + select epilogue, not the
+    # tensor pipe): every (query, train) pair's accumulator has to pass the min pipe once.  Measured on this part
+    # (tools/ubench/min_ubench.cu): one three-input FMNMX3 (two new values per lane) per 2.25 cycles per scheduler.
+    pairs_per_step = flops_per_step / (2.0 * dim)
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    select_peak = 148 * 4 * (64.0 / 2.25) * sm_clock * 1e6
+    select_ach = pairs_per_step / (cand_ms_per_step * 1e-3) if cand_ms_per_step > 0 else 0.0
+    roofline["select_epilogue"] = {"achieved": select_ach, "peak": select_peak, "unit": "pairs/s", "frac": select_ach / select_peak,
+                                   "peak_source": "148 SMs x 4 schedulers x 64 values per 2.25 cycles (measured FMNMX3 rate) x SM clock under load"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, cores, sample, secs = CpuReference(desc, n_src, n_tgt, k, "one_sided" if tsharded else mode_name).rate(12.0)

@@ -446,3 +446,17 @@ def test_match_local_with_search_radius_equals_oracle(desc, nq, nt, k, radius):
     got2 = M.match_local(src, tgt, params, dim=dim, query_kps_xyz=moved, train_kps_xyz=tx, guess=guess, match_search_radius=radius)
     back = moved[:, :3] @ guess[:3, :3].T + guess[:3, 3]
     _same(got2, orc.match_local(_dense(src, dim), _dense(tgt, dim), k, back, tx[:, :3], radius))
+
+
+@pytest.mark.parametrize("workload", ["c3", "c4"])
+def test_full_size_workloads_match_oracle_on_sampled_rows(workload):
+    """BASELINE.json's full sizes (SHOT-352 500k x 500k k=2; FPFH-33 2M x 2M k=5), both directions, device-resident:
+    bit-exact against the oracle on sampled query rows vs the FULL train set, plus the size-independent properties on
+    all rows (tools/fullsize_parity.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fullsize_parity.py"), workload, "256"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("bit-exact") == 2

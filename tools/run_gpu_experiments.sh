@@ -1,11 +1,1 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "dual_mode or candidate_kernel_modes or tc_operands or bench_scale" > gpurun_out/t_tc.log 2>&1; echo tests rc=$?
-tail -4 gpurun_out/t_tc.log
-for d in 0 1 32 512; do
-B200M_TC_DEBUG=$d timeout 600 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_c2_dbg$d.json 2> gpurun_out/n_c2_dbg$d.err
-grep -A1 "CTAs per SM" gpurun_out/n_c2_dbg$d.err | head -2
-done
-B200M_TC_DUAL=0 timeout 600 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_c2_dual0.json 2> gpurun_out/n_c2_dual0.err
-timeout 600 python bench.py --workload c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_c4.json 2> gpurun_out/n_c4.err
-timeout 600 python bench.py --workload c1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/n_c1.json 2> gpurun_out/n_c1.err
-python tools/bench_summary.py gpurun_out/n_*.json
-grep -h epi-prof gpurun_out/n_c2_dbg512.json | tail -4
+for w in c3 c4 c2; do timeout 900 python tools/fullsize_parity.py $w 384 2>&1 | grep -v Warning | tee -a gpurun_out/fullsize_parity.log; done
