@@ -239,18 +239,11 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
-    return old;
-}
-
 template <int KT>
 struct RowState {
     float tk[KT];   // k smallest accumulator values this thread has seen (of distinct columns), ascending
