@@ -72,6 +72,7 @@ struct AlignmentParameters {
     bool use_bfmatcher = true;      // :144  either backend maps to the same exact GPU search
     int bf_block_size = 10000;      // :145  accepted, unused
     int ratio_k = 2;                // :146  MATCHING_RATIO_K
+    int cluster_k = 40;             // :146  MATCHING_CLUSTER_K (include/common.h:53)
     int randomness = 1;             // :147  k
     float distance_thr = std::numeric_limits<float>::max();   // :139
     std::string matching_id = "lr"; // :149  one_sided | lr | ratio
@@ -280,7 +281,48 @@ protected:
     int mode() const override { return B200M_MODE_RATIO; }
 };
 
-// getFeatureBasedMatcherFromParameters (reference src/matching.cpp:21-76) for one feature type.
+// ClusterMatcher (reference include/matching.h:480-551, the default matching_id): needs the keypoint coordinates of
+// both sides (st_src_.kps / st_tgt_.kps), one row per descriptor, `xyz_stride_bytes` apart (pcl::PointXYZ / PointN rows).
+template <typename FeatureT>
+class ClusterMatcher : public FeatureBasedMatcherImpl<FeatureT> {
+public:
+    ClusterMatcher(FeatureCloud<FeatureT> src, FeatureCloud<FeatureT> tgt, AlignmentParameters parameters,
+                   const float *src_kps_xyz, const float *tgt_kps_xyz, size_t xyz_stride_bytes,
+                   std::vector<float> thresholds_src = {}, std::vector<float> thresholds_tgt = {},
+                   std::vector<int> kps_indices_src = {}, std::vector<int> kps_indices_tgt = {})
+        : FeatureBasedMatcherImpl<FeatureT>(std::move(src), std::move(tgt), std::move(parameters), std::move(thresholds_src),
+                                            std::move(thresholds_tgt), std::move(kps_indices_src), std::move(kps_indices_tgt)),
+          sx_(src_kps_xyz), tx_(tgt_kps_xyz), stride_(xyz_stride_bytes) {}
+    std::string getClassName() override { return "ClusterMatcher"; }
+
+    CorrespondencesPtr match() override {
+        Context ctx(this->parameters_.device);
+        ctx.template upload<FeatureT>(0, this->src_);
+        ctx.template upload<FeatureT>(1, this->tgt_);
+        const int k = this->parameters_.randomness;
+        b200m_params p = make_params(this->parameters_, B200M_MODE_CLUSTER, k);
+        auto out = std::make_shared<Correspondences>(cloud_size<FeatureT>(this->src_) * k);
+        size_t n = 0;
+        const bool thr = !this->thr_src_.empty() && !this->thr_tgt_.empty();
+        ctx.check(b200m_match_cluster(ctx.get(), &p, this->parameters_.cluster_k, sx_, tx_, stride_,
+                                      thr ? this->thr_src_.data() : nullptr, thr ? this->thr_tgt_.data() : nullptr,
+                                      reinterpret_cast<b200m_corr *>(out->data()), out->size(), &n, &this->average_distance_));
+        out->resize(n);
+        for (auto &c : *out) {   // finalize
+            if (!this->kps_src_.empty()) c.index_query = this->kps_src_[c.index_query];
+            if (!this->kps_tgt_.empty()) c.index_match = this->kps_tgt_[c.index_match];
+        }
+        return out;
+    }
+
+protected:
+    int mode() const override { return B200M_MODE_CLUSTER; }
+    const float *sx_, *tx_;
+    size_t stride_;
+};
+
+// getFeatureBasedMatcherFromParameters (reference src/matching.cpp:21-76) for one feature type.  ("cluster" needs the
+// keypoint coordinates: construct b200match::ClusterMatcher<FeatureT> directly.)
 template <typename FeatureT, typename... Args>
 FeatureBasedMatcher::Ptr getFeatureBasedMatcherFromParameters(const FeatureCloud<FeatureT> &src, const FeatureCloud<FeatureT> &tgt,
                                                               const AlignmentParameters &parameters, Args &&...rest) {

@@ -59,11 +59,45 @@ static int run(char **argv) {
         fprintf(out, "matcher %s %s %zu %.9g\n", id, matcher->getClassName().c_str(), corrs->size(), matcher->getAverageDistance());
         for (const auto &c : *corrs) fprintf(out, "corr %s %d %d %.9g\n", id, c.index_query, c.index_match, c.distance);
     }
-    try {
+    try {   // the factory has no keypoints to hand to the cluster filter
         parameters.matching_id = "cluster";
         getFeatureBasedMatcherFromParameters<FeatureT>(src, tgt, parameters);
         abort();
     } catch (const std::runtime_error &) {
+    }
+    // ClusterMatcher and match_multiscale over keypoints laid out on a deterministic lattice (the pytest driver builds
+    // the same coordinates): pcl::PointXYZ-like rows of 4 floats
+    auto lattice = [](size_t n, float step) {
+        std::vector<float> xyz(4 * n, 0.f);
+        for (size_t i = 0; i < n; ++i) {
+            xyz[4 * i + 0] = step * (float) (i % 17);
+            xyz[4 * i + 1] = step * (float) ((i / 17) % 13);
+            xyz[4 * i + 2] = step * (float) (i / 221);
+        }
+        return xyz;
+    };
+    const auto sx = lattice(ns, 0.5f), tx = lattice(nt, 0.25f);
+    {
+        parameters.cluster_k = 12;
+        ClusterMatcher<FeatureT> cm(src, tgt, parameters, sx.data(), tx.data(), 16);
+        auto corrs = cm.match();
+        fprintf(out, "matcher cluster %s %zu %.9g\n", cm.getClassName().c_str(), corrs->size(), cm.getAverageDistance());
+        for (const auto &c : *corrs) fprintf(out, "corr cluster %d %d %.9g\n", c.index_query, c.index_match, c.distance);
+    }
+    {   // two "scales": all keypoints, then every second one on both sides
+        std::vector<FeatureCloud<FeatureT>> qf{src, {}}, tf{tgt, {}};
+        std::vector<std::vector<int>> qi(2), ti(2);
+        for (size_t i = 0; i < ns; ++i) qi[0].push_back((int) i);
+        for (size_t i = 0; i < nt; ++i) ti[0].push_back((int) i);
+        for (size_t i = 0; i < ns; i += 2) { qf[1].push_back(src[i]); qi[1].push_back((int) i); }
+        for (size_t i = 0; i < nt; i += 2) { tf[1].push_back(tgt[i]); ti[1].push_back((int) i); }
+        auto mv = match_multiscale<FeatureT>(qf, tf, qi, ti, ns, tx.data(), nt, 16, 0.3f, parameters);
+        if (mv.size() != ns) abort();
+        for (size_t i = 0; i < ns; ++i) {
+            fprintf(out, "ms %zu %zu", i, mv[i].match_indices.size());
+            for (size_t m = 0; m < mv[i].match_indices.size(); ++m) fprintf(out, " %d %.9g", mv[i].match_indices[m], mv[i].distances[m]);
+            fprintf(out, "\n");
+        }
     }
     fclose(out);
     return 0;

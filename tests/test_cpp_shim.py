@@ -44,7 +44,8 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
     assert r.returncode == 0, r.stderr
     s_d, t_d = src[:, :dim], tgt[:, :dim]
     exp = {0: orc.knn(s_d, t_d, k), 1: orc.knn(t_d, s_d, k)}
-    got_corr = {"one_sided": [], "lr": [], "ratio": []}
+    got_corr = {"one_sided": [], "lr": [], "ratio": [], "cluster": []}
+    got_ms = {}
     heads = {}
     n_knn = 0
     for line in open(op):
@@ -60,6 +61,8 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
             heads[w[1]] = (w[2], int(w[3]), np.float32(w[4]))
         elif w[0] == "corr":
             got_corr[w[1]].append((int(w[2]), int(w[3]), np.float32(w[4])))
+        elif w[0] == "ms":
+            got_ms[int(w[1])] = [(int(a), np.float32(b)) for a, b in zip(w[3::2], w[4::2])]
     assert n_knn == ns + nt
     fmax = np.float32(np.finfo(np.float32).max)
     for mid, mode, cls in (("one_sided", "one_sided", "OneSidedMatcher"), ("lr", "mutual", "LeftToRightMatcher"),
@@ -69,3 +72,30 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
         e, eavg = orc.match(s_d, t_d, max(k, 2) if mid == "ratio" else k, mode, 1.1, fmax)
         assert heads[mid][0] == cls and heads[mid][1] == len(e) and heads[mid][2] == np.float32(eavg)
         assert got_corr[mid] == [(int(a), int(b), np.float32(c)) for a, b, c in zip(e["index_query"], e["index_match"], e["distance"])]
+
+    # ClusterMatcher and match_multiscale over the same keypoint lattice shim_test.cpp builds
+    def lattice(n, step):
+        i = np.arange(n)
+        return np.stack([step * (i % 17), step * ((i // 17) % 13), step * (i // 221)], 1).astype(np.float32)
+    sx, tx = lattice(ns, np.float32(0.5)), lattice(nt, np.float32(0.25))
+    f = orc.knn(s_d, t_d, k)
+    r = orc.knn(t_d, s_d, k)
+    e = orc.filter_cluster(f[0], f[2], r[0], r[2], orc.knn3d(sx, 12), orc.knn3d(tx, 12), fmax)
+    assert heads["cluster"][0] == "ClusterMatcher" and heads["cluster"][1] == len(e)
+    assert got_corr["cluster"] == [(int(a), int(b), np.float32(c)) for a, b, c in zip(e["index_query"], e["index_match"], e["distance"])]
+    q2, t2 = np.arange(0, ns, 2), np.arange(0, nt, 2)
+    f2 = orc.knn(np.ascontiguousarray(s_d[q2]), np.ascontiguousarray(t_d[t2]), k)
+    ci = np.full((ns, 2 * k), -1, np.int32)
+    cd = np.zeros((ns, 2 * k), np.float32)
+    cc = np.zeros(ns, np.int32)
+    for i in range(ns):
+        ent = [(int(f[0][i, m]), f[1][i, m]) for m in range(f[2][i])]
+        if i % 2 == 0:
+            ent += [(int(t2[f2[0][i // 2, m]]), f2[1][i // 2, m]) for m in range(f2[2][i // 2])]
+        cc[i] = len(ent)
+        for m, (a, b) in enumerate(ent):
+            ci[i, m], cd[i, m] = a, b
+    vi, vd, vc = orc.spatial_vote(ci, cd, cc, tx, np.float32(0.3))
+    assert len(got_ms) == ns
+    for i in range(ns):
+        assert got_ms[i] == ([(int(vi[i, 0]), np.float32(vd[i, 0]))] if vc[i] else [])
