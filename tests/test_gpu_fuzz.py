@@ -19,7 +19,7 @@ def _built():
 
 
 DIMS = [1, 2, 3, 13, 16, 33, 45, 61, 62, 64, 77, 125, 126, 135, 200, 352, 353, 500, 637, 638, 700]
-KINDS = ["uniform", "clustered", "duplicates", "offset", "tiny", "huge", "sparse", "integers"]
+KINDS = ["uniform", "clustered", "duplicates", "offset", "tiny", "huge", "sparse", "integers", "near_ties"]
 
 
 def _make(rng, kind, n, dim):
@@ -37,6 +37,9 @@ def _make(rng, kind, n, dim):
         a = 1e-32 * rng.random((n, dim))
     elif kind == "huge":
         a = 1e32 * rng.random((n, dim))
+    elif kind == "near_ties":           # hundreds of rows within 1e-6 of each other: far below FP16 resolution, so the
+        base = rng.random((max(n // 200, 1), dim))   # candidate lists overflow and the exact fallback has to answer
+        a = base[rng.integers(0, base.shape[0], n)] + 1e-6 * rng.standard_normal((n, dim))
     elif kind == "sparse":
         a = rng.random((n, dim)) * (rng.random((n, dim)) < 0.2)
     else:                               # small integers: lots of equal distances between different rows
@@ -64,7 +67,7 @@ def _case(seed):
     return q, t, dim, k, kind
 
 
-@pytest.mark.parametrize("seed", range(48))
+@pytest.mark.parametrize("seed", range(81))
 def test_knn_fuzz(seed):
     q, t, dim, k, kind = _case(seed)
     with M.Context(0) as ctx:
