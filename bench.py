@@ -307,6 +307,10 @@ def run_b200(args, wl):
     flops_per_step = 2.0 * dim * ((q1 - q0) * n_tgt + ((t1 - t0) * n_src if both else 0))
     if tsharded:   # every rank: all queries against its own target shard
         flops_per_step = 2.0 * dim * n_src * n_tgt
+    # FLOPs the candidate kernel actually had to do: the masked reverse pass answers only the target rows that forward
+    # lists name (st["pairs_scored"] = sum over the launches of rows searched x train rows)
+    if st.get("pairs_scored", 0) > 0:
+        flops_per_step = 2.0 * dim * st["pairs_scored"] / args.steps
     cand_ms_per_step = st["ms_candidates"] / args.steps
     pk = peaks()
     achieved = flops_per_step / (cand_ms_per_step * 1e-3) / 1e12 if cand_ms_per_step > 0 else 0.0
@@ -321,7 +325,8 @@ def run_b200(args, wl):
                 "algorithmic_flops_per_step": flops_per_step,
                 "breakdown_ms_per_step": {x: st[x] / args.steps for x in ("ms_pack", "ms_prepare", "ms_candidates", "ms_rerank",
                                                                      "ms_fallback", "ms_filter")},
-                "candidates_per_row": st["candidates"] / max(st["rows_total"], 1),
+                "candidates_per_row": st["candidates"] / max(st.get("rows_answered") or st["rows_total"], 1),
+                "query_rows_searched_frac": (st.get("rows_answered") or st["rows_total"]) / max(st["rows_total"], 1),
                 "rows_overflowed_frac": st["rows_flagged"] / max(st["rows_total"], 1)}
 
     # Second yardstick (for short descriptors the limiter is the accumulator drain + select epilogue, not the

@@ -81,6 +81,9 @@ typedef struct {
     int64_t rows_total;    /* query rows processed by knn */
     int64_t rows_flagged;  /* rows whose candidate list overflowed and went through the exact row kernel */
     int64_t candidates;    /* candidate (query, train) pairs re-ranked exactly */
+    int64_t rows_answered; /* query rows actually searched (masked kNN: the selected rows only) */
+    int64_t pairs_scored;  /* (query, train) pairs whose distance the candidate kernel evaluated: sum of
+                              rows_answered x train rows over the tensor-core launches */
 } b200m_stats;
 
 /* ---- context -------------------------------------------------------------- */
@@ -120,6 +123,19 @@ B200M_API int b200m_knn(b200m_ctx *ctx, const b200m_params *p, int direction, si
                         size_t row_end, int32_t *idx, float *dist, int32_t *count);
 B200M_API int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin,
                                size_t row_end, int32_t *d_idx, float *d_dist, int32_t *d_count);
+
+/* ---- masked kNN: only the flagged query rows are answered (the rest get empty lists) --------------
+ * The mutual filter reads the reverse list of target row j only if some forward list names j
+ * (LeftToRightMatcher::match_impl, include/matching.h:433-449), so the reverse pass may skip every other target row
+ * (b200m_match does this by itself for large problems).  b200m_mark_referenced_device sets flags[j - index_offset] = 1
+ * for every entry j of the given k-lists (flags must be zeroed by the caller; sharded runs OR / max-reduce the flags of
+ * all ranks); b200m_knn_masked_device is b200m_knn_device restricted to rows with flags[row] != 0 (flags cover ALL rows of
+ * the query side).  Device pointers, queued on the context's stream; one host round trip (the number of selected rows). */
+B200M_API int b200m_mark_referenced_device(b200m_ctx *ctx, int k, const int32_t *d_fidx, const int32_t *d_fcount,
+                                           size_t n_rows, int64_t index_offset, uint8_t *d_flags, size_t n_flags);
+B200M_API int b200m_knn_masked_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin,
+                                      size_t row_end, const uint8_t *d_row_flags, int32_t *d_idx, float *d_dist,
+                                      int32_t *d_count);
 
 /* ---- matchLocal with a finite match_search_radius (include/matching.h:637-678): the guess-conditioned kNN
  * match_multiscale uses when AlignmentParameters::guess is set (:297-304).  query_xyz: the query side's keypoints

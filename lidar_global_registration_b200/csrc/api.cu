@@ -121,6 +121,7 @@ int b200m_create(b200m_ctx **out, int device) {
     }
     if (const char *e = getenv("B200M_TC_DEBUG")) ctx->tc_debug = atoi(e);
     if (const char *e = getenv("B200M_TC_SPLITS")) ctx->tc_splits = atoi(e);
+    if (const char *e = getenv("B200M_MASKED_MIN_PAIRS")) ctx->masked_min_pairs = atof(e);
     if (const char *e = getenv("B200M_TC_MODE")) {
         if (!strcmp(e, "mcast")) ctx->tc_pair = 0;
         if (!strcmp(e, "pair")) ctx->tc_pair = 1;
@@ -143,7 +144,8 @@ void b200m_destroy(b200m_ctx *ctx) {
     DevBuf *ws[] = {&ctx->ws_cand_idx, &ctx->ws_cand_cnt, &ctx->ws_flag_rows, &ctx->ws_counters, &ctx->ws_scan,
                     &ctx->ws_out, &ctx->ws_misc, &ctx->ws_fidx, &ctx->ws_fdist, &ctx->ws_fcnt, &ctx->ws_ridx,
                     &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr, &ctx->ws_totals, &ctx->ws_part_i, &ctx->ws_part_d,
-                    &ctx->ws_done, &ctx->ws_cand_val, &ctx->ws_cand_thr};
+                    &ctx->ws_done, &ctx->ws_cand_val, &ctx->ws_cand_thr, &ctx->ws_row_list, &ctx->ws_row_flags,
+                    &ctx->ws_sel_ops, &ctx->ws_sel_norm};
     for (DevBuf *b : ws) b->release();
     tc_release(ctx);
     multiscale_release(ctx);
@@ -281,18 +283,56 @@ static int check_params(b200m_ctx *ctx, const b200m_params *p) {
     return 0;
 }
 
-int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t row_end,
-                     int32_t *d_idx, float *d_dist, int32_t *d_count) {
-    REQUIRE_CTX();
-    if (check_params(ctx, p)) return 1;
-    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "b200m_knn: direction must be 0 or 1");
+// ---- row selection (masked kNN) ---------------------------------------------------------------------
+// The mutual filter only ever looks at the reverse lists of target rows that some forward list names
+// (LeftToRightMatcher::match_impl, reference include/matching.h:433-449: rev[j] is read for j in fwd[i] only), so
+// the reverse pass can skip every other target row -- 30 % of them in the benchmark's data.
+__global__ void mark_referenced_kernel(const int32_t *__restrict__ fidx, const int32_t *__restrict__ fcount, size_t n_rows,
+                                       int k, long long index_offset, uint8_t *__restrict__ flags, size_t n_flags) {
+    const size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * (size_t) k) return;
+    if ((int) (e % k) >= fcount[e / k]) return;
+    const long long j = (long long) fidx[e] - index_offset;
+    if (j >= 0 && (size_t) j < n_flags) flags[j] = 1;
+}
+
+// rows of [row_begin, row_begin + n_rows) that are flagged AND valid -> row_list (unordered; warp-aggregated append)
+__global__ void select_rows_kernel(const uint8_t *__restrict__ flags, const uint8_t *__restrict__ valid, size_t row_begin,
+                                   size_t n_rows, int32_t *__restrict__ row_list, int32_t *__restrict__ n_selected) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = i < n_rows && flags[row_begin + i] && valid[row_begin + i];
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int) m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(n_selected, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) row_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t) (row_begin + i);
+}
+
+// compact copy of the selected rows' query-form operands and norms (zero rows behind the last one, up to n_pad)
+__global__ void gather_query_rows_kernel(const int32_t *__restrict__ row_list, size_t n_sel, size_t n_pad, int kp,
+                                         const uint4 *__restrict__ op_query, const float *__restrict__ norm16,
+                                         uint4 *__restrict__ op_out, float *__restrict__ norm_out) {
+    const int lane = threadIdx.x & 31;
+    const size_t r = (size_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_pad) return;
+    const int per_row = kp / 8;   // uint4 = 8 halves
+    if (r < n_sel) {
+        const size_t src = (size_t) row_list[r];
+        for (int c = lane; c < per_row; c += 32) op_out[r * per_row + c] = __ldg(op_query + src * per_row + c);
+        if (lane == 0) norm_out[r] = norm16[src];
+    } else {
+        for (int c = lane; c < per_row; c += 32) op_out[r * per_row + c] = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) norm_out[r] = 0.f;
+    }
+}
+
+// kNN of query rows [row_begin, row_begin + n_rows) of `direction`; with d_flags, only of the flagged (and valid) rows --
+// every other row gets an empty list.  Outputs are indexed by (row - row_begin).
+static int knn_core(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t n_rows,
+                    const uint8_t *d_flags, int32_t *d_idx, float *d_dist, int32_t *d_count) {
     Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
-    if (row_end == 0) row_end = q.n;
-    if (row_begin > row_end || row_end > q.n) return b200m_fail_msg(ctx, "b200m_knn: query row range out of bounds");
-    const size_t n_rows = row_end - row_begin;
-    if (n_rows == 0) return 0;
-    if (!d_idx || !d_dist || !d_count) return b200m_fail_msg(ctx, "b200m_knn: null output pointer");
-    if (t.n && q.dim != t.dim) return b200m_fail_msg(ctx, "b200m_knn: source and target descriptor lengths differ");
     const int k = p->k;
     cudaStream_t st = ctx->stream;
     ctx->stats.rows_total += (int64_t) n_rows;
@@ -312,34 +352,77 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
         }
         use_tc = ctx->prep.usable;
     }
+    // row selection: compact list of the rows to answer (the one host round trip of this path: the launch geometry
+    // of the candidate kernel depends on how many there are)
+    const int32_t *row_map = nullptr;
+    size_t n_work = n_rows;
+    if (d_flags) {
+        size_t ne = n_rows * (size_t) k;
+        fill_empty_kernel<<<(unsigned) ((ne + 255) / 256), 256, 0, st>>>(n_rows, k, d_idx, d_dist, d_count);
+        CK(ctx->ws_row_list.reserve(sizeof(int32_t) * n_rows + 64));
+        int32_t *d_nsel = ctx->ws_row_list.as<int32_t>();          // [0] = number selected, list from [16]
+        int32_t *d_list = d_nsel + 16;
+        CK(cudaMemsetAsync(d_nsel, 0, sizeof(int32_t), st));
+        select_rows_kernel<<<(unsigned) ((n_rows + 255) / 256), 256, 0, st>>>(d_flags, q.valid.as<uint8_t>(), row_begin, n_rows,
+                                                                              d_list, d_nsel);
+        CK(cudaGetLastError());
+        ctx->stats.launches += 2;
+        int32_t n_sel = 0;
+        CK(cudaMemcpyAsync(&n_sel, d_nsel, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (n_sel == 0) return 0;
+        row_map = d_list;
+        n_work = (size_t) n_sel;
+    }
     if (!use_tc) {
         StatTimer tf(ctx, &ctx->stats.ms_fallback);
         CK(launch_exact_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(),
-                             t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_rows, nullptr, nullptr, k, d_idx,
-                             d_dist, d_count, 1 << 30, 0, nullptr, nullptr, nullptr, st));
+                             t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_work, nullptr, nullptr, k, d_idx,
+                             d_dist, d_count, 1 << 30, 0, nullptr, nullptr, nullptr, row_map, st));
         ctx->stats.launches += 1;
         tf.stop();
         return 0;
     }
     // 1. tensor-core candidate pass: per row a certified superset of the exact top-k
     int n_lists = 0, cap = 0, has_values = 0;
+    ctx->stats.rows_answered += (int64_t) n_work;
+    ctx->stats.pairs_scored += (int64_t) n_work * (int64_t) t.n;
     {
+        const void *q_ops = nullptr;
+        const float *q_norm = nullptr;
+        size_t q_pad = 0;
+        if (row_map) {   // the candidate kernel reads whole 128-row operand tiles: give it the selected rows back to back
+            q_pad = (n_work + B200M_TILE_N - 1) / B200M_TILE_N * B200M_TILE_N;
+            CK(ctx->ws_sel_ops.reserve(sizeof(__half) * q_pad * (size_t) q.kp));
+            CK(ctx->ws_sel_norm.reserve(sizeof(float) * q_pad));
+            StatTimer tg(ctx, &ctx->stats.ms_prepare);
+            gather_query_rows_kernel<<<(unsigned) ((q_pad + 7) / 8), 256, 0, st>>>(
+                row_map, n_work, q_pad, q.kp, q.op_query.as<uint4>(), q.norm16.as<float>(), ctx->ws_sel_ops.as<uint4>(),
+                ctx->ws_sel_norm.as<float>());
+            CK(cudaGetLastError());
+            ctx->stats.launches += 1;
+            tg.stop();
+            q_ops = ctx->ws_sel_ops.p;
+            q_norm = ctx->ws_sel_norm.as<float>();
+        }
         StatTimer tc(ctx, &ctx->stats.ms_candidates);
-        if (tc_candidates(ctx, direction, row_begin, n_rows, k, p->cand_cap, &n_lists, &cap, &has_values, nullptr, 0)) return 1;
+        if (tc_candidates(ctx, direction, row_map ? 0 : row_begin, n_work, k, p->cand_cap, &n_lists, &cap, &has_values, nullptr, 0,
+                          q_ops, q_norm, q_pad))
+            return 1;
         tc.stop();
     }
     // 2. exact FP32 re-rank of the candidates (bit-identical arithmetic to the reference)
-    CK(ctx->ws_flag_rows.reserve(sizeof(int32_t) * n_rows));
+    CK(ctx->ws_flag_rows.reserve(sizeof(int32_t) * n_work));
     CK(ctx->ws_counters.reserve(64));
     CK(cudaMemsetAsync(ctx->ws_counters.p, 0, 64, st));
     {
         StatTimer tr(ctx, &ctx->stats.ms_rerank);
         CK(launch_rerank(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(), t.valid.as<uint8_t>(),
-                         t.n, t.index_offset, row_begin, n_rows, k, ctx->ws_cand_idx.as<int32_t>(),
+                         t.n, t.index_offset, row_begin, n_work, k, ctx->ws_cand_idx.as<int32_t>(),
                          ctx->ws_cand_cnt.as<int32_t>(), n_lists, cap,
                          has_values ? ctx->ws_cand_val.as<float>() : nullptr,
                          has_values ? ctx->ws_cand_thr.as<float>() : nullptr, d_idx, d_dist, d_count,
-                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), ctx->sm_count, st));
+                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), ctx->sm_count, row_map, st));
         ctx->stats.launches += 1;
         tr.stop();
     }
@@ -357,10 +440,10 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
             ctx->done_init = true;
         }
         CK(launch_exact_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, q.dim, t.f32.as<float>(),
-                             t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_rows,
+                             t.valid.as<uint8_t>(), t.n, t.index_offset, row_begin, n_work,
                              ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), k, d_idx, d_dist, d_count,
-                             (int) (n_rows < max_blocks ? n_rows : max_blocks), split_blocks, ctx->ws_part_i.as<int32_t>(),
-                             ctx->ws_part_d.as<float>(), ctx->ws_done.as<unsigned int>(), st));
+                             (int) (n_work < max_blocks ? n_work : max_blocks), split_blocks, ctx->ws_part_i.as<int32_t>(),
+                             ctx->ws_part_d.as<float>(), ctx->ws_done.as<unsigned int>(), row_map, st));
         ctx->stats.launches += 2;
         tf.stop();
     }
@@ -374,6 +457,49 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
                                                     ctx->ws_totals.as<unsigned long long>());
         CK(cudaGetLastError());
     }
+    return 0;
+}
+
+static int check_knn_args(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t *row_end,
+                          const void *d_idx, const void *d_dist, const void *d_count) {
+    if (check_params(ctx, p)) return 1;
+    if (direction != 0 && direction != 1) return b200m_fail_msg(ctx, "b200m_knn: direction must be 0 or 1");
+    Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
+    if (*row_end == 0) *row_end = q.n;
+    if (row_begin > *row_end || *row_end > q.n) return b200m_fail_msg(ctx, "b200m_knn: query row range out of bounds");
+    if (*row_end > row_begin && (!d_idx || !d_dist || !d_count)) return b200m_fail_msg(ctx, "b200m_knn: null output pointer");
+    if (t.n && q.dim != t.dim) return b200m_fail_msg(ctx, "b200m_knn: source and target descriptor lengths differ");
+    return 0;
+}
+
+int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t row_end,
+                     int32_t *d_idx, float *d_dist, int32_t *d_count) {
+    REQUIRE_CTX();
+    if (check_knn_args(ctx, p, direction, row_begin, &row_end, d_idx, d_dist, d_count)) return 1;
+    if (row_end == row_begin) return 0;
+    return knn_core(ctx, p, direction, row_begin, row_end - row_begin, nullptr, d_idx, d_dist, d_count);
+}
+
+int b200m_knn_masked_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t row_end,
+                            const uint8_t *d_row_flags, int32_t *d_idx, float *d_dist, int32_t *d_count) {
+    REQUIRE_CTX();
+    if (check_knn_args(ctx, p, direction, row_begin, &row_end, d_idx, d_dist, d_count)) return 1;
+    if (row_end == row_begin) return 0;
+    if (!d_row_flags) return b200m_fail_msg(ctx, "b200m_knn_masked: null row flags");
+    return knn_core(ctx, p, direction, row_begin, row_end - row_begin, d_row_flags, d_idx, d_dist, d_count);
+}
+
+int b200m_mark_referenced_device(b200m_ctx *ctx, int k, const int32_t *d_fidx, const int32_t *d_fcount, size_t n_rows,
+                                 int64_t index_offset, uint8_t *d_flags, size_t n_flags) {
+    REQUIRE_CTX();
+    if (k < 1 || k > B200M_MAX_K) return b200m_fail_msg(ctx, "b200m_mark_referenced: k must be in [1, 32]");
+    if (n_rows == 0) return 0;
+    if (!d_fidx || !d_fcount || !d_flags) return b200m_fail_msg(ctx, "b200m_mark_referenced: null pointer");
+    const size_t ne = n_rows * (size_t) k;
+    mark_referenced_kernel<<<(unsigned) ((ne + 255) / 256), 256, 0, ctx->stream>>>(d_fidx, d_fcount, n_rows, k,
+                                                                                   (long long) index_offset, d_flags, n_flags);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 1;
     return 0;
 }
 
@@ -531,7 +657,18 @@ int b200m_match(b200m_ctx *ctx, const b200m_params *p, const float *thr_src, con
         CK(ctx->ws_ridx.reserve(sizeof(int32_t) * nt * k));
         CK(ctx->ws_rdist.reserve(sizeof(float) * nt * k));
         CK(ctx->ws_rcnt.reserve(sizeof(int32_t) * nt));
-        if (b200m_knn_device(ctx, p, 1, 0, nt, ctx->ws_ridx.as<int32_t>(), ctx->ws_rdist.as<float>(), ctx->ws_rcnt.as<int32_t>()))
+        // reverse lists are only ever read for target rows that a forward list names: skip the rest when the pass is big
+        // enough to pay for the extra host round trip (row selection)
+        const uint8_t *d_flags = nullptr;
+        if ((double) nq * (double) nt >= ctx->masked_min_pairs) {
+            CK(ctx->ws_row_flags.reserve(nt));
+            CK(cudaMemsetAsync(ctx->ws_row_flags.p, 0, nt, st));
+            if (b200m_mark_referenced_device(ctx, k, ctx->ws_fidx.as<int32_t>(), ctx->ws_fcnt.as<int32_t>(), nq, tgt.index_offset,
+                                             ctx->ws_row_flags.as<uint8_t>(), nt))
+                return 1;
+            d_flags = ctx->ws_row_flags.as<uint8_t>();
+        }
+        if (knn_core(ctx, p, 1, 0, nt, d_flags, ctx->ws_ridx.as<int32_t>(), ctx->ws_rdist.as<float>(), ctx->ws_rcnt.as<int32_t>()))
             return 1;
     }
     const float *d_thr_s = nullptr, *d_thr_t = nullptr;

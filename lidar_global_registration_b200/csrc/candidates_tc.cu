@@ -705,7 +705,8 @@ struct TmapCache {
     } e[4];   // [side][as_query]
 };
 
-int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtensorMap **out) {
+int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtensorMap **out, const void *q_ops = nullptr,
+             size_t q_pad = 0) {
     TmapCache *tc = static_cast<TmapCache *>(ctx->tmap_cache);
     if (!tc) {
         tc = new TmapCache();
@@ -720,11 +721,12 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
         tc->encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     Side &sd = ctx->side[side];
-    const void *ptr = as_query ? sd.op_query.p : sd.op_train.p;
+    const void *ptr = as_query ? (q_ops ? q_ops : sd.op_query.p) : sd.op_train.p;
+    const size_t rows = as_query && q_ops ? q_pad : sd.n_pad;
     const int box_rows = as_query ? B200M_TILE_M : B200M_TILE_N / cluster;
     TmapCache::Entry &en = tc->e[side * 2 + (as_query ? 1 : 0)];
-    if (en.ptr != ptr || en.n_pad != sd.n_pad || en.kp != sd.kp || en.box_rows != box_rows) {
-        cuuint64_t dims[2] = {(cuuint64_t) sd.kp, (cuuint64_t) sd.n_pad};
+    if (en.ptr != ptr || en.n_pad != rows || en.kp != sd.kp || en.box_rows != box_rows) {
+        cuuint64_t dims[2] = {(cuuint64_t) sd.kp, (cuuint64_t) rows};
         cuuint64_t strides[1] = {(cuuint64_t) sd.kp * 2};
         cuuint32_t box[2] = {64, (cuuint32_t) box_rows};
         cuuint32_t estr[2] = {1, 1};
@@ -733,7 +735,7 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return b200m_fail_msg(ctx, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int) r));
         en.ptr = ptr;
-        en.n_pad = sd.n_pad;
+        en.n_pad = rows;
         en.kp = sd.kp;
         en.box_rows = box_rows;
     }
@@ -781,7 +783,8 @@ void tc_release(b200m_ctx *ctx) {
 }
 
 int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
-                  int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile) {
+                  int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile,
+                  const void *q_ops, const float *q_norm, size_t q_pad) {
     Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
     const int n_qtiles = (int) ((n_rows + B200M_TILE_M - 1) / B200M_TILE_M);
     // Default = CTA-pair mode (cta_group::2): the two CTAs of a cluster form one M=256 MMA, each keeps its own 128
@@ -791,7 +794,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     int pair = ctx->tc_pair;
     int cluster = pair ? 2 : (ctx->tc_cluster > 0 ? ctx->tc_cluster : 2);
     const CUtensorMap *mq = nullptr, *mt = nullptr;
-    if (get_tmap(ctx, direction, true, 1, &mq)) return 1;
+    if (get_tmap(ctx, direction, true, 1, &mq, q_ops, q_pad)) return 1;
     if (get_tmap(ctx, 1 - direction, false, cluster, &mt)) return 1;
 
     TcParams p{};
@@ -833,7 +836,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.k = k;
     p.dim = q.dim;
     p.bmax = ctx->prep.max_norm[1 - direction];
-    p.q_norm16 = q.norm16.as<float>();
+    p.q_norm16 = q_ops ? q_norm : q.norm16.as<float>();
     // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
     // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and there a thread that owns its whole row
     // also records the accumulator values so that the re-rank can prune by the row's final threshold.

@@ -53,7 +53,8 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
                   const float *__restrict__ t_f32, const uint8_t *__restrict__ t_valid, size_t nt,
                   long long t_off, size_t row_begin, size_t n_rows, const int32_t *__restrict__ row_list,
                   const int32_t *__restrict__ row_list_count, int k, int32_t *__restrict__ idx,
-                  float *__restrict__ dist, int32_t *__restrict__ count, int split_max) {
+                  float *__restrict__ dist, int32_t *__restrict__ count, int split_max,
+                  const int32_t *__restrict__ row_map) {
     extern __shared__ float smem[];
     float *sq = smem;                                   // [dp] query row
     float *red_d = smem + dp;                           // [warps]
@@ -66,13 +67,15 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
     if (row_list && split_max > 0 && total <= (size_t) split_max) return;   // few flagged rows: exact_rows_split_kernel has them
 
     for (size_t r = blockIdx.x; r < total; r += gridDim.x) {
+        // `local` numbers the rows of this call (compacted when a row map is given); results are stored by original row
         const size_t local = row_list ? (size_t) row_list[r] : r;
-        const size_t qi = row_begin + local;
-        int32_t *oi = idx + local * k;
-        float *od = dist + local * k;
+        const size_t qi = row_map ? (size_t) row_map[local] : row_begin + local;
+        const size_t orow = qi - row_begin;
+        int32_t *oi = idx + orow * k;
+        float *od = dist + orow * k;
         if (!q_valid[qi]) {   // non-finite query -> empty entry (reference include/matching.h:576)
             if (tid < k) { oi[tid] = -1; od[tid] = 0.f; }
-            if (tid == 0) count[local] = 0;
+            if (tid == 0) count[orow] = 0;
             continue;
         }
         __syncthreads();
@@ -133,7 +136,7 @@ exact_rows_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q
             __syncthreads();
         }
         if (tid >= found && tid < k) { oi[tid] = -1; od[tid] = 0.f; }
-        if (tid == 0) count[local] = found;
+        if (tid == 0) count[orow] = found;
     }
 }
 
@@ -284,7 +287,8 @@ exact_rows_split_kernel(const float *__restrict__ q_f32, int dp, const float *__
                         const uint8_t *__restrict__ t_valid, size_t nt, long long t_off, size_t row_begin,
                         const int32_t *__restrict__ row_list, const int32_t *__restrict__ row_list_count, int k,
                         int32_t *__restrict__ part_i, float *__restrict__ part_d, unsigned int *__restrict__ done,
-                        int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count) {
+                        int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count,
+                        const int32_t *__restrict__ row_map) {
     extern __shared__ float smem[];
     float *sq = smem;
     float *red_d = smem + dp;
@@ -300,7 +304,8 @@ exact_rows_split_kernel(const float *__restrict__ q_f32, int dp, const float *__
     const size_t j0 = (size_t) blockIdx.x * chunk, j1 = j0 + chunk < nt ? j0 + chunk : nt;
     for (int r = 0; r < total; ++r) {
         const size_t local = (size_t) row_list[r];
-        const size_t qi = row_begin + local;
+        const size_t qi = row_map ? (size_t) row_map[local] : row_begin + local;
+        const size_t orow = qi - row_begin;
         __syncthreads();
         for (int d = tid; d < dp; d += kExactThreads) sq[d] = q_f32[qi * (size_t) dp + d];
         __syncthreads();
@@ -360,13 +365,13 @@ exact_rows_split_kernel(const float *__restrict__ q_f32, int dp, const float *__
         __shared__ int fin_i[B200M_MAX_K];
         block_select<KMAX>(ld, li, k, red_d, red_i, red_w, &win_d, &win_i, &win_t, fin_d, fin_i, &found);
         __syncthreads();
-        int32_t *oi = idx + local * k;
-        float *od = dist + local * k;
+        int32_t *oi = idx + orow * k;
+        float *od = dist + orow * k;
         if (tid < k) {
             oi[tid] = tid < found ? (int32_t) (fin_i[tid] + t_off) : -1;
             od[tid] = tid < found ? fin_d[tid] : 0.f;
         }
-        if (tid == 0) { count[local] = found; done[r] = 0u; }   // counter ready for the next call
+        if (tid == 0) { count[orow] = found; done[r] = 0u; }   // counter ready for the next call
     }
 }
 
@@ -415,7 +420,8 @@ __host__ __device__ inline size_t rerank_warp_bytes(int dp) { return (size_t) (r
 // being filled and consumed.
 struct RerankLens {   // stage 1: issued two rows ahead
     int len;          // lanes 0..n_lists-1: appended entries of list `lane` (may exceed cap: overflow)
-    int qv;           // q_valid of the row
+    int qv;           // q_valid of the row (rows of a row map are valid by construction)
+    long long qi;     // original row number of the query
     float thr;        // lanes 0..n_lists-1: final append threshold of list `lane` (+inf when values were not recorded)
 };
 struct RerankRow {    // stage 2: issued one row ahead
@@ -423,23 +429,32 @@ struct RerankRow {    // stage 2: issued one row ahead
     int my_len;       // capped length of list `lane`
     int j0;           // candidate of this lane in the first group of 32 (-1: none or pruned); range-checked, validity not yet
     float thr;        // pruning threshold of the row
+    long long qi;     // original row number of the query
     bool overflow, qv;
 };
 
 __device__ __forceinline__ RerankLens rerank_fetch_lens(size_t local, size_t n_rows, size_t row_begin,
                                                         const int32_t *__restrict__ cand_cnt,
                                                         const float *__restrict__ cand_thr,
-                                                        const uint8_t *__restrict__ q_valid, int n_lists, int lane) {
+                                                        const uint8_t *__restrict__ q_valid, int n_lists, int lane,
+                                                        const int32_t *__restrict__ row_map) {
     RerankLens m;
     m.len = 0;
     m.qv = 0;
+    m.qi = 0;
     m.thr = INFINITY;
     if (local < n_rows) {
         if (lane < n_lists) {
             m.len = __ldg(cand_cnt + (size_t) lane * n_rows + local);
             if (cand_thr) m.thr = __ldg(cand_thr + (size_t) lane * n_rows + local);
         }
-        m.qv = q_valid[row_begin + local];
+        if (row_map) {
+            m.qi = (long long) __ldg(row_map + local);
+            m.qv = 1;
+        } else {
+            m.qi = (long long) (row_begin + local);
+            m.qv = q_valid[row_begin + local];
+        }
     }
     return m;
 }
@@ -472,6 +487,7 @@ __device__ __forceinline__ RerankRow rerank_fetch_row(const RerankLens &m, size_
                                                       int lane) {
     RerankRow r;
     r.qv = m.qv != 0;
+    r.qi = m.qi;
     r.overflow = __any_sync(0xffffffffu, m.len > cap);
     r.my_len = m.len > cap ? cap : m.len;
     int t = r.my_len;
@@ -498,7 +514,7 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
               const int32_t *__restrict__ cand_idx, const int32_t *__restrict__ cand_cnt, int n_lists, int cap,
               const float *__restrict__ cand_val, const float *__restrict__ cand_thr,
               int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count,
-              int32_t *__restrict__ flag_rows, int32_t *__restrict__ counters) {
+              int32_t *__restrict__ flag_rows, int32_t *__restrict__ counters, const int32_t *__restrict__ row_map) {
     extern __shared__ __align__(128) uint8_t rr_smem[];
     __shared__ unsigned long long blk_cands;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -522,13 +538,15 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
     const size_t stride = (size_t) gridDim.x * n_warps;
     size_t local = (size_t) blockIdx.x * n_warps + warp;
     // pipeline prologue
-    RerankRow cur = rerank_fetch_row(rerank_fetch_lens(local, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane), local,
+    RerankRow cur = rerank_fetch_row(rerank_fetch_lens(local, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map), local,
                                      n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
-    RerankLens nxt_lens = rerank_fetch_lens(local + stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+    RerankLens nxt_lens = rerank_fetch_lens(local + stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
     for (; local < n_rows; local += stride) {
-        const size_t qi = row_begin + local;
-        int32_t *oi = idx + local * k;
-        float *od = dist + local * k;
+        // `local` numbers the rows of this call (and its candidate lists); results are stored by original row
+        const size_t qi = (size_t) cur.qi;
+        const size_t orow = qi - row_begin;
+        int32_t *oi = idx + orow * k;
+        float *od = dist + orow * k;
         const bool work = cur.qv && !cur.overflow;
         float ld[KMAX];
         int li[KMAX];
@@ -538,7 +556,7 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
         RerankRow nxt;
         if (!work || cur.total == 0) {
             nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
-            nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+            nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
         } else {
             my_cands += (unsigned long long) cur.total;
             for (int base = 0; base < cur.total; base += 32) {
@@ -573,7 +591,7 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
                     if (first) {
                         // metadata of the rows behind this one: their loads land while this row's slab fills
                         nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
-                        nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+                        nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
                         first = false;
                     }
                     bar_wait_parity(bar, phase);
@@ -613,7 +631,7 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
             }
             if (first) {   // every candidate was pruned or invalid: nothing was gathered
                 nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
-                nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane);
+                nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
             }
         }
         // k rounds of warp arg-min over the per-lane list heads
@@ -641,7 +659,7 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
         // a non-finite query has an empty entry (reference include/matching.h:576); overflowed rows are redone exactly
         for (int m = found + lane; m < k; m += 32) { oi[m] = -1; od[m] = 0.f; }
         if (lane == 0) {
-            count[local] = found;
+            count[orow] = found;
             if (cur.qv && cur.overflow) {
                 int pos = atomicAdd(counters, 1);
                 flag_rows[pos] = (int32_t) local;
@@ -660,20 +678,20 @@ cudaError_t launch_exact_t(const float *q_f32, const uint8_t *q_valid, int dp, i
                            const uint8_t *t_valid, size_t nt, int64_t t_off, size_t row_begin, size_t n_rows,
                            const int32_t *row_list, const int32_t *row_list_count, int k, int32_t *idx, float *dist,
                            int32_t *count, int blocks, int split_blocks, int32_t *part_i, float *part_d,
-                           unsigned int *done, cudaStream_t st) {
+                           unsigned int *done, const int32_t *row_map, cudaStream_t st) {
     size_t smem = sizeof(float) * dp + (sizeof(float) + 2 * sizeof(int)) * (kExactThreads / 32);
     const bool split = row_list && split_blocks > 0 && part_i && part_d && done;
     if (split) {
         exact_rows_split_kernel<KMAX><<<split_blocks, kExactThreads, smem, st>>>(
             q_f32, dp, t_f32, t_valid, nt, (long long) t_off, row_begin, row_list, row_list_count, k, part_i, part_d, done,
-            idx, dist, count);
+            idx, dist, count, row_map);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     exact_rows_kernel<KMAX><<<blocks, kExactThreads, smem, st>>>(q_f32, q_valid, dp, dim, t_f32, t_valid, nt,
                                                                  (long long) t_off, row_begin, n_rows, row_list,
                                                                  row_list_count, k, idx, dist, count,
-                                                                 split ? kSplitMaxRows : 0);
+                                                                 split ? kSplitMaxRows : 0, row_map);
     return cudaGetLastError();
 }
 
@@ -683,13 +701,13 @@ cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp
                               const float *t_f32, const uint8_t *t_valid, size_t nt, int64_t t_index_offset,
                               size_t row_begin, size_t n_rows, const int32_t *row_list, const int32_t *row_list_count,
                               int k, int32_t *idx, float *dist, int32_t *count, int max_blocks, int split_blocks,
-                              int32_t *part_i, float *part_d, unsigned int *done, cudaStream_t st) {
+                              int32_t *part_i, float *part_d, unsigned int *done, const int32_t *row_map, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     int blocks = (int) (n_rows < (size_t) max_blocks ? n_rows : (size_t) max_blocks);
 #define B200M_EXACT_CASE(K)                                                                                   \
     return launch_exact_t<K>(q_f32, q_valid, dp, dim, t_f32, t_valid, nt, t_index_offset, row_begin, n_rows,  \
                              row_list, row_list_count, k, idx, dist, count, blocks, split_blocks, part_i, part_d, \
-                             done, st)
+                             done, row_map, st)
     if (k <= 1) B200M_EXACT_CASE(1);
     if (k <= 2) B200M_EXACT_CASE(2);
     if (k <= 4) B200M_EXACT_CASE(4);
@@ -732,7 +750,7 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
                           const int32_t *cand_idx, const int32_t *cand_cnt, int n_lists, int cap,
                           const float *cand_val, const float *cand_thr,
                           int32_t *idx, float *dist, int32_t *count,
-                          int32_t *flag_rows, int32_t *counters, int sm_count, cudaStream_t st) {
+                          int32_t *flag_rows, int32_t *counters, int sm_count, const int32_t *row_map, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     if (n_lists > kMaxLists) return cudaErrorInvalidValue;
     // one CTA per SM holding as many warps (each with its own gather slab) as shared memory allows
@@ -752,7 +770,8 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
         if (e != cudaSuccess) return e;                                                                         \
         rerank_kernel<K><<<blocks, warps * 32, smem, st>>>(                                                     \
             q_f32, q_valid, dp, dim, t_f32, t_valid, nt, (long long) t_index_offset, row_begin, n_rows, k,      \
-            cand_idx, cand_cnt, n_lists, cap, cand_val, cand_thr, idx, dist, count, flag_rows, counters);       \
+            cand_idx, cand_cnt, n_lists, cap, cand_val, cand_thr, idx, dist, count, flag_rows, counters,        \
+            row_map);                                                                                           \
         return cudaGetLastError();                                                                              \
     } while (0)
     if (k <= 1) B200M_RERANK_CASE(1);

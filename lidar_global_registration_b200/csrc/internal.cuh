@@ -60,6 +60,7 @@ struct b200m_ctx {
     TcPrep prep;
     DevBuf ws_cand_idx, ws_cand_cnt, ws_flag_rows, ws_counters, ws_scan, ws_out, ws_misc;
     DevBuf ws_part_i, ws_part_d, ws_done, ws_cand_val, ws_cand_thr;
+    DevBuf ws_row_list, ws_row_flags, ws_sel_ops, ws_sel_norm;   // row selection (masked kNN)
     bool done_init = false;
     DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr, ws_totals;
     bool totals_init = false;
@@ -67,6 +68,9 @@ struct b200m_ctx {
     void *multiscale = nullptr;   // MultiscaleState (multiscale.cu)
     void *cluster = nullptr;      // ClusterState (cluster.cu)
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
+    double masked_min_pairs = 1e9;   // B200M_MASKED_MIN_PAIRS: b200m_match skips unreferenced target rows in the reverse pass
+                                     // from this many (source, target) pairs on (below, the row selection's host round trip
+                                     // costs more than it saves)
     int tc_splits = 0;     // B200M_TC_SPLITS: 0 = chosen per launch (wave balance); > 0 forces the number of train splits
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
     int tc_pair = 1;       // 1 = CTA-pair (cta_group::2) candidate kernel; 0 = cta_group::1 + multicast (B200M_TC_MODE=mcast)
@@ -120,7 +124,10 @@ cudaError_t launch_exact_rows(const float *q_f32, const uint8_t *q_valid, int dp
                               int k, int32_t *idx, float *dist, int32_t *count, int max_blocks,
                               // few flagged rows (row_list given): split_blocks CTAs share every row; workspace of
                               // exact_split_ws_entries() int32 + float entries and exact_split_max_rows() zeroed counters
-                              int split_blocks, int32_t *part_i, float *part_d, unsigned int *done, cudaStream_t st);
+                              int split_blocks, int32_t *part_i, float *part_d, unsigned int *done,
+                              // row_map (or null): the call's rows are row_map[0..n_rows) instead of row_begin + 0..n_rows;
+                              // results are always stored at (row - row_begin)
+                              const int32_t *row_map, cudaStream_t st);
 cudaError_t launch_local_rows(const float *q_f32, const uint8_t *q_valid, int dp, const float *t_f32,
                               const uint8_t *t_valid, size_t nt, int64_t t_index_offset, size_t n_rows,
                               const float *q_xyz, const float *t_xyz, size_t xyz_stride_bytes, float radius, int k,
@@ -134,7 +141,7 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
                           const float *cand_val, const float *cand_thr /* both null: no pruning */,
                           int32_t *idx, float *dist, int32_t *count,
                           int32_t *flag_rows, int32_t *counters /*[0]=flagged rows, [1..2]=candidate pairs (u64)*/,
-                          int sm_count, cudaStream_t st);
+                          int sm_count, const int32_t *row_map, cudaStream_t st);
 
 // filter.cu
 cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, size_t row_begin, size_t n_rows,
@@ -154,8 +161,11 @@ cudaError_t launch_merge(int k, int n_lists, size_t nq, const int32_t *idx_in, c
 // Fills ws_cand_idx [n_lists][n_rows][cap] and ws_cand_cnt [n_lists][n_rows] (entries appended per list; a
 // count above cap marks an overflowed list).  dump != nullptr: single tile, raw accumulators to dump[128][256].
 // *has_values_out = 1: ws_cand_val [n_lists][n_rows][cap] and ws_cand_thr [n_lists][n_rows] are filled too.
+// q_ops != null: the query rows are rows 0..n_rows of this compact [q_pad][kp] operand array (norms in q_norm) instead of
+// rows row_begin.. of the query side's own array.
 int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
-                  int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile);
+                  int *n_lists_out, int *cap_out, int *has_values_out, float *dump, size_t dump_t_tile,
+                  const void *q_ops = nullptr, const float *q_norm = nullptr, size_t q_pad = 0);
 bool tc_supported(const b200m_ctx *ctx, int dim, int k);
 void tc_release(b200m_ctx *ctx);
 

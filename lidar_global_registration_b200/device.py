@@ -15,6 +15,10 @@ import torch
 from . import matcher as M
 
 
+# below this many (query, train) pairs the row selection's host round trip costs more than the skipped rows save
+MASKED_REVERSE_MIN_PAIRS = 10 ** 9
+
+
 def shard_bounds(n, rank, world):
     """Contiguous, balanced row ranges: rank r owns [lo, hi)."""
     base, rem = divmod(n, world)
@@ -72,6 +76,26 @@ class GpuBackend:
                                 self.precision, self.cand_cap)
         return idx, dist, cnt
 
+    def knn_masked(self, k, direction, row_begin, row_end, flags):
+        """kNN of the rows of [row_begin, row_end) whose flag is set (uint8 CUDA tensor over ALL rows of the query side);
+        the other rows get empty lists."""
+        rows = row_end - row_begin
+        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((rows, k), dtype=torch.float32, device=self.device)
+        cnt = torch.empty((rows,), dtype=torch.int32, device=self.device)
+        if rows:
+            self.ctx.knn_masked_device(k, direction, row_begin, row_end, flags.data_ptr(), idx.data_ptr(), dist.data_ptr(),
+                                       cnt.data_ptr(), self.precision, self.cand_cap)
+        return idx, dist, cnt
+
+    def referenced_rows(self, k, fwd, n_flags, index_offset=0):
+        """uint8 flags [n_flags]: 1 for every row of the other side that the k-lists `fwd` name."""
+        flags = torch.zeros((n_flags,), dtype=torch.uint8, device=self.device)
+        if fwd[0].shape[0]:
+            self.ctx.mark_referenced_device(k, fwd[0].data_ptr(), fwd[2].data_ptr(), fwd[0].shape[0], index_offset,
+                                            flags.data_ptr(), n_flags)
+        return flags
+
     def filter(self, k, mode, row_begin, row_end, fwd, rev, n_rev_rows, ratio_thr=M.MATCHING_RATIO_THRESHOLD,
                distance_thr=M.FLT_MAX, thr_src=None, thr_tgt=None, want_avg=False):
         """-> (records int32 [cap, 4] (reinterpret as CORR_DTYPE), n_out uint64-as-int64 [1], avg float32 [1] or None)."""
@@ -104,7 +128,10 @@ class GpuBackend:
         fwd = self.knn(k, 0, 0, nq)
         rev = None
         if mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL):
-            rev = self.knn(k, 1, 0, nt)
+            if nq * nt >= MASKED_REVERSE_MIN_PAIRS:
+                rev = self.knn_masked(k, 1, 0, nt, self.referenced_rows(k, fwd, nt))
+            else:
+                rev = self.knn(k, 1, 0, nt)
         return self.filter(k, mode, 0, nq, fwd, rev, nt if rev is not None else 0, ratio_thr, distance_thr,
                            want_avg=want_avg)
 
@@ -166,7 +193,16 @@ class ShardedMatcher:
         rev = None
         if mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL):
             t0, t1 = shard_bounds(nt, self.rank, self.world)
-            r = self.b.knn(k, 1, t0, t1)
+            if nq * nt >= MASKED_REVERSE_MIN_PAIRS:
+                # the mutual test reads rev[j] only for targets j that a forward list names: every rank marks the ones its
+                # own source rows name, the flags are max-reduced (nt bytes), and the reverse pass skips the rest
+                flags = self.b.referenced_rows(k, fwd, nt)
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+                r = self.b.knn_masked(k, 1, t0, t1, flags)
+            else:
+                r = self.b.knn(k, 1, t0, t1)
             rev = tuple(self._all_gather_rows(x, nt) for x in r)     # the path's one exchange step
         return self.b.filter(k, mode, q0, q1, fwd, rev, nt if rev is not None else 0, ratio_thr, distance_thr)
 

@@ -48,7 +48,8 @@ class Stats(C.Structure):
     _fields_ = [("ms_pack", C.c_double), ("ms_prepare", C.c_double), ("ms_candidates", C.c_double),
                 ("ms_rerank", C.c_double), ("ms_fallback", C.c_double), ("ms_filter", C.c_double),
                 ("launches", C.c_int64), ("candidate_launches", C.c_int64), ("rows_total", C.c_int64),
-                ("rows_flagged", C.c_int64), ("candidates", C.c_int64)]
+                ("rows_flagged", C.c_int64), ("candidates", C.c_int64), ("rows_answered", C.c_int64),
+                ("pairs_scored", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -59,7 +60,7 @@ EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_strea
            "b200m_knn", "b200m_knn_device", "b200m_match", "b200m_filter_device", "b200m_merge_device",
            "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile", "b200m_multiscale_begin",
            "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device", "b200m_match_cluster",
-           "b200m_cluster_filter_device", "b200m_knn3d_device", "b200m_knn_local", "b200m_knn_local_device"]
+           "b200m_cluster_filter_device", "b200m_knn3d_device", "b200m_knn_local", "b200m_knn_local_device", "b200m_mark_referenced_device", "b200m_knn_masked_device"]
 
 _lib = None
 
@@ -101,6 +102,8 @@ def load_library():
     L.b200m_cluster_filter_device.argtypes = [vp, C.POINTER(_Params), C.c_int, C.c_float, sz, sz, vp, vp, vp, vp, vp, fp, fp,
                                               sz, fp, fp, vp, sz, vp, vp]
     L.b200m_knn3d_device.argtypes = [vp, fp, sz, sz, C.c_int, vp]
+    L.b200m_mark_referenced_device.argtypes = [vp, C.c_int, vp, vp, sz, i64, vp, sz]
+    L.b200m_knn_masked_device.argtypes = [vp, C.POINTER(_Params), C.c_int, sz, sz, vp, vp, vp, vp]
     L.b200m_knn_local.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
     L.b200m_knn_local_device.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
     L.b200m_version.restype = C.c_int
@@ -239,6 +242,18 @@ class Context:
         p = self._params(k, MODE_KNN_ONLY, precision=precision, cand_cap=cand_cap)
         self._ck(self._L.b200m_knn_device(self._h, C.byref(p), direction, row_begin, row_end, C.c_void_p(idx_ptr),
                                           C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr)))
+
+    def knn_masked_device(self, k, direction, row_begin, row_end, flags_ptr, idx_ptr, dist_ptr, cnt_ptr, precision=PREC_TC_F16,
+                          cand_cap=0):
+        p = self._params(k, MODE_KNN_ONLY, precision=precision, cand_cap=cand_cap)
+        v = C.c_void_p
+        self._ck(self._L.b200m_knn_masked_device(self._h, C.byref(p), direction, row_begin, row_end, v(flags_ptr), v(idx_ptr),
+                                                 v(dist_ptr), v(cnt_ptr)))
+
+    def mark_referenced_device(self, k, fidx_ptr, fcnt_ptr, n_rows, index_offset, flags_ptr, n_flags):
+        v = C.c_void_p
+        self._ck(self._L.b200m_mark_referenced_device(self._h, k, v(fidx_ptr), v(fcnt_ptr), n_rows, index_offset, v(flags_ptr),
+                                                      n_flags))
 
     # -- whole matcher call ----------------------------------------------------
     def match(self, k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, thr_src=None, thr_tgt=None,

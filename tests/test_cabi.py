@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     # b200m_corr == reference Correspondence (include/common.h:120-131): 16 bytes
     assert M.CORR_DTYPE.itemsize == 16
     assert C.sizeof(M._Params) == 24
-    assert C.sizeof(M.Stats) == 6 * 8 + 5 * 8
+    assert C.sizeof(M.Stats) == 6 * 8 + 7 * 8
 
 
 def test_version(lib):

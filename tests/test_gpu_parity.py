@@ -150,6 +150,31 @@ def test_tc_operands_and_accumulators(desc, nq, nt, k):
 
 
 @pytest.mark.parametrize("prec", PRECS, ids=["exact", "tc"])
+def test_match_mutual_with_masked_reverse_pass(monkeypatch, golden_dir, prec):
+    """b200m_match's large-problem path (reverse kNN only for the target rows the forward lists name), forced on at
+    test size: the same records, distances and thresholds as the oracle."""
+    monkeypatch.setenv("B200M_MASKED_MIN_PAIRS", "0")
+    for case in ("fpfh_k5", "shot_k2", "fpfh_k1"):
+        g = np.load(os.path.join(golden_dir, case + ".npz"))
+        dim, k = int(g["dim"]), int(g["k"])
+        src, tgt = g["src"], g["tgt"]
+        with M.Context(0) as ctx:
+            ctx.upload(0, src, dim)
+            ctx.upload(1, tgt, dim)
+            got, avg = ctx.match(k, M.MODE_MUTUAL, 1.1, np.float32(0.7), precision=prec)
+            got_rm, _ = ctx.match(max(k, 2), M.MODE_RATIO_MUTUAL, 1.1, np.float32(0.7), precision=prec)
+        exp, eavg = orc.match(_dense(src, dim), _dense(tgt, dim), k, "mutual", 1.1, np.float32(0.7))
+        assert got.tobytes() == exp.tobytes() and avg == eavg and len(exp) > 0
+        monkeypatch.setenv("B200M_MASKED_MIN_PAIRS", "1e30")
+        with M.Context(0) as ctx:
+            ctx.upload(0, src, dim)
+            ctx.upload(1, tgt, dim)
+            ref_rm, _ = ctx.match(max(k, 2), M.MODE_RATIO_MUTUAL, 1.1, np.float32(0.7), precision=prec)
+        monkeypatch.setenv("B200M_MASKED_MIN_PAIRS", "0")
+        assert got_rm.tobytes() == ref_rm.tobytes()
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=["exact", "tc"])
 @pytest.mark.parametrize("mode,name", [("one_sided", M.MODE_ONE_SIDED), ("mutual", M.MODE_MUTUAL), ("ratio", M.MODE_RATIO)])
 def test_match_equals_oracle(golden_dir, mode, name, prec):
     """b200m_match == OneSided/LeftToRight(/Ratio) match_impl restated in the oracle: same records, same order,
@@ -460,3 +485,41 @@ def test_full_size_workloads_match_oracle_on_sampled_rows(workload):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("bit-exact") == 2
+
+
+@pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 2500, 3100, 2), ("shot", 900, 1300, 2), ("rops", 700, 600, 5)])
+def test_masked_reverse_pass_gives_the_same_mutual_records(desc, nq, nt, k):
+    """The mutual filter reads rev[j] only for targets j named by a forward list, so the reverse kNN may skip the other
+    target rows (b200m_knn_masked_device + b200m_mark_referenced_device; b200m_match does it for large problems):
+    skipped rows come back empty, answered rows are the oracle's, and the filter output is unchanged."""
+    import torch
+    from lidar_global_registration_b200 import device as D
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    be = D.GpuBackend(0)
+    try:
+        be.upload_device(0, torch.from_numpy(src).cuda(), dim)
+        be.upload_device(1, torch.from_numpy(tgt).cuda(), dim)
+        fwd = be.knn(k, 0, 0, nq)
+        flags = be.referenced_rows(k, fwd, nt)
+        fi, fd, fc = orc.knn(_dense(src, dim), _dense(tgt, dim), k)
+        exp_flags = np.zeros(nt, np.uint8)
+        for i in range(nq):
+            exp_flags[fi[i, :fc[i]]] = 1
+        assert np.array_equal(flags.cpu().numpy(), exp_flags) and 0 < exp_flags.sum() < nt
+        lo, hi = nt // 5, nt - 3                       # a row range, as a sharded rank would ask for
+        ridx, rdist, rcnt = [x.cpu().numpy() for x in be.knn_masked(k, 1, lo, hi, flags)]
+        ei, ed, ec = orc.knn(_dense(tgt, dim), _dense(src, dim), k)
+        keep = (exp_flags[lo:hi] == 1) & np.isfinite(tgt[lo:hi, :dim]).all(1)
+        assert np.array_equal(ridx[keep], ei[lo:hi][keep]) and np.array_equal(rdist[keep], ed[lo:hi][keep])
+        assert np.array_equal(rcnt[keep], ec[lo:hi][keep]) and np.all(rcnt[~keep] == 0) and np.all(ridx[~keep] == -1)
+        old = D.MASKED_REVERSE_MIN_PAIRS
+        D.MASKED_REVERSE_MIN_PAIRS = 0
+        try:
+            rec, n_out, _ = be.match_device(k, M.MODE_MUTUAL)
+        finally:
+            D.MASKED_REVERSE_MIN_PAIRS = old
+        got = D.records_to_numpy(rec, n_out)
+        exp, _ = orc.match(_dense(src, dim), _dense(tgt, dim), k, "mutual", 1.1, np.float32(M.FLT_MAX))
+        assert got.tobytes() == exp.tobytes()
+    finally:
+        be.close()

@@ -32,6 +32,19 @@ class OracleBackend:
             idx = np.where(idx >= 0, idx + self.tgt_offset, idx).astype(np.int32)
         return torch.from_numpy(idx), torch.from_numpy(dist_), torch.from_numpy(cnt)
 
+    def referenced_rows(self, k, fwd, n_flags, index_offset=0):
+        idx, cnt = fwd[0].numpy(), fwd[2].numpy()
+        flags = np.zeros(n_flags, np.uint8)
+        for i in range(idx.shape[0]):
+            flags[idx[i, :cnt[i]] - index_offset] = 1
+        return torch.from_numpy(flags)
+
+    def knn_masked(self, k, direction, row_begin, row_end, flags):
+        idx, dist_, cnt = [x.numpy().copy() for x in self.knn(k, direction, row_begin, row_end)]
+        skip = flags.numpy()[row_begin:row_end] == 0
+        idx[skip], dist_[skip], cnt[skip] = -1, 0, 0
+        return torch.from_numpy(idx), torch.from_numpy(dist_), torch.from_numpy(cnt)
+
     def filter(self, k, mode, row_begin, row_end, fwd, rev, n_rev_rows, ratio_thr=1.1, distance_thr=M.FLT_MAX,
                thr_src=None, thr_tgt=None, want_avg=False):
         nq = self.n[0]
@@ -86,6 +99,13 @@ def _worker(rank, world, port, desc, ns, nt, k, q):
             rec, n_out, _ = sm.match_query_sharded(k, mode)
             allrec, n = sm.gather_records(rec, n_out)
             res[name] = allrec[:n].numpy().view(M.CORR_DTYPE).reshape(-1).copy()
+        # the same mutual run with the reverse pass restricted to the target rows the forward lists name
+        # (flags max-reduced over the ranks): identical records
+        D.MASKED_REVERSE_MIN_PAIRS = 0
+        rec, n_out, _ = sm.match_query_sharded(k, M.MODE_MUTUAL)
+        allrec, n = sm.gather_records(rec, n_out)
+        res["mutual_masked"] = allrec[:n].numpy().view(M.CORR_DTYPE).reshape(-1).copy()
+        D.MASKED_REVERSE_MIN_PAIRS = 10 ** 9
         # target-sharded: this rank holds target rows [t0, t1)
         t0, t1 = D.shard_bounds(nt, rank, world)
         sm2 = D.ShardedMatcher(OracleBackend(src, tgt[t0:t1], dim, tgt_offset=t0), rank, world)
@@ -116,6 +136,8 @@ def test_sharded_matcher_two_ranks_gloo(desc, ns, nt, k):
         exp, _ = orc.match(s_d, t_d, k, name, 1.1, fmax)
         for r in range(2):
             assert got[r][name].tobytes() == exp.tobytes(), (name, r)
+            if name == "mutual":
+                assert got[r]["mutual_masked"].tobytes() == exp.tobytes()
         assert len(exp) > 0
     e = orc.knn(s_d, t_d, k)
     for r in range(2):

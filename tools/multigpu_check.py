@@ -32,14 +32,17 @@ for desc, nq, nt, k in [("fpfh", 5003, 7001, 2), ("shot", 2111, 3005, 2), ("rops
     # (descriptors replicated from pinned HOST memory: 1/world slice per rank over PCIe + NCCL all-gather)
     sm.upload_host_sharded(0, torch.from_numpy(src).pin_memory(), dim)
     sm.upload_host_sharded(1, torch.from_numpy(tgt).pin_memory(), dim)
-    for mode, oname in [(M.MODE_MUTUAL, "mutual"), (M.MODE_RATIO, "ratio")]:
+    for mode, oname in [(M.MODE_MUTUAL, "mutual"), (M.MODE_RATIO, "ratio"), (M.MODE_MUTUAL, "mutual-masked")]:
+        # "mutual-masked": the reverse pass answers only the target rows that forward lists name (flags max-reduced over
+        # the ranks with NCCL) -- what large runs do by default
+        D.MASKED_REVERSE_MIN_PAIRS = 0 if oname == "mutual-masked" else 10 ** 18
         rec, n_out = sm.match_query_sharded(k, mode)[:2]
         allrec, n_all = sm.gather_records(rec, n_out)
         got = allrec[:n_all].contiguous().cpu().numpy().view(M.CORR_DTYPE).reshape(-1)
         if rank == 0:
-            exp = orc.match(sd, td, k, oname, M.MATCHING_RATIO_THRESHOLD, np.float32(M.FLT_MAX))[0]
+            exp = orc.match(sd, td, k, oname.split("-")[0], M.MATCHING_RATIO_THRESHOLD, np.float32(M.FLT_MAX))[0]
             same = got.shape == exp.shape and all(np.array_equal(got[f], exp[f]) for f in got.dtype.names)
-            print("query-sharded %-6s %s %dx%d k=%d world=%d: %d records %s" % (oname, desc, nq, nt, k, world, n_all,
+            print("query-sharded %-13s %s %dx%d k=%d world=%d: %d records %s" % (oname, desc, nq, nt, k, world, n_all,
                                                                            "PASS" if same else "FAIL"))
             if not same:
                 print("   expected %d records; differing fields: %s" % (exp.shape[0], [f for f in got.dtype.names
