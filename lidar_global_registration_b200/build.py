@@ -17,6 +17,8 @@ LINK_VERSION = "cudart-shared-1"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wall",
          "-diag-suppress", "177"]
+if os.environ.get("B200M_TC_TRACE"):   # cycle-stamp tracing of the candidate kernel (tools/run_trace.sh)
+    FLAGS.append("-DB200M_TC_TRACE")
 
 
 STAMP = LIB + ".stamp"

@@ -39,6 +39,14 @@ constexpr int kTailBytes = 2048;         // barriers (<= 29 x 8 B) + TMEM slot +
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
+// Cycle stamps (B200M_TC_DEBUG & 1024) exist only in a library built with -DB200M_TC_TRACE (B200M_TC_TRACE=1 in the
+// environment of build.py): their local arrays slow every debug instantiation down, also with the flag off.
+#ifdef B200M_TC_TRACE
+constexpr bool kTraceBuild = true;
+#else
+constexpr bool kTraceBuild = false;
+#endif
+constexpr int kTraceTile0 = 300, kTraceTiles = 12;   // which tiles of a sweep get cycle stamps
 constexpr long long kWaitLimitCycles = 4000000000LL;   // ~2 s: a wedged pipeline traps instead of hanging the GPU
 
 struct TcParams {
@@ -48,6 +56,7 @@ struct TcParams {
     int cluster;          // CTAs per cluster sharing every train tile by TMA multicast (1, 2 or 4)
     int pair;             // 1: CTA-pair mode (cta_group::2, M=256 across two SMs, each CTA holds half of B); cluster == 2
     int stage_bytes;      // bytes of one B stage in this CTA's shared memory (32 KB, or 16 KB in pair mode)
+    int lean;             // 1: the MMA issuer runs the fully unrolled loop for one-atom descriptors (PAIR, 12 stages)
     int n_ttiles;         // 256-row train tiles
     int tiles_per_split;
     int q_row0;           // first query row of this call (row_begin)
@@ -64,7 +73,8 @@ struct TcParams {
     float *dump;          // debug: raw accumulators of one tile [128][256]
     int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
                           // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages, 32 = epilogue only
-                          // drains TMEM (no filtering), 64 / 128 = force EH = 1 / 2
+                          // drains TMEM (no filtering), 64 / 128 = force EH = 1 / 2, 256 = fast path only,
+                          // 512 = per-warp cycle totals, 1024 = cycle stamps of a few tiles (CTA pair 0)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -487,7 +497,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             __syncwarp();
             uint32_t s = 0, ph = 1;
-            for (int t = t0; t < t1; ++t) {
+            for (int t = (dflags & 65536) ? t1 : t0; t < t1; ++t) {
                 for (int a = 0; a < ka; ++a) {
                     mbar_wait(bar_empty0 + 8u * s, ph);
                     if (elect_one()) {
@@ -542,31 +552,88 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t nk_full = (dflags & 2) ? 0u : 4u;
             const uint32_t nk_last = (dflags & 2) ? 0u : (uint32_t) (p.ksteps - 4 * (ka - 1));   // K steps of the last atom (1..4)
             constexpr uint32_t idesc = PAIR ? kInstrDescPair : kInstrDesc;
+            if (PAIR && EH == 2 && p.lean && !(DBG && (dflags & ~(1 | 32 | 256 | 512)))) {
+                // One-atom descriptors (FPFH-33: 3 MMAs = 384 tensor-pipe cycles per tile).  The general loop below costs
+                // this warp ~100 dependent instructions per tile (stage index in a vector register: R2UR moves, address
+                // arithmetic, descriptor adds) -- ~630 cycles when it has its scheduler to itself, far more while the two
+                // epilogue warps on the same scheduler stream their min chains, and all of it sits on the accumulator
+                // hand-off chain.  Here the ring is unrolled over its 12 stages: stage, accumulator buffer, barrier
+                // addresses and even the accumulator barrier's parity (lt = 12 r + i, (lt >> 1) & 1 = (i >> 1) & 1) are
+                // immediates of the unrolled body.
+                static_assert(kMaxStages == 12, "unrolled issue loop is written for a 12-stage ring");
+                const int nt = t1 - t0;
+                const uint32_t nk = nk_last;
+                uint32_t ph = 0;
+                int lt = 0;
+                while (lt < nt) {
+#pragma unroll
+                    for (int i = 0; i < kMaxStages; ++i) {
+                        if (lt + i < nt) {
+                            const uint32_t buf = (uint32_t) (i & 1);
+                            mbar_wait(bar_full0 + 8u * (uint32_t) i, ph);
+                            mbar_wait(bar_tempty0 + 8u * buf, (uint32_t) (((i >> 1) & 1) ^ 1));
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t db = desc_b0 + (uint64_t) ((uint32_t) i * (uint32_t) ((kStageBytes / 2) >> 4));
+                                const uint32_t tmem_d = tmem_base + buf * (uint32_t) B200M_TILE_N;
+                                tc_mma<PAIR>(tmem_d, desc_a0, db, idesc, 0u, (uint32_t) (nk > 0));
+                                tc_mma<PAIR>(tmem_d, desc_a0 + 2, db + 2, idesc, 1u, (uint32_t) (nk > 1));
+                                tc_mma<PAIR>(tmem_d, desc_a0 + 4, db + 4, idesc, 1u, (uint32_t) (nk > 2));
+                                tc_mma<PAIR>(tmem_d, desc_a0 + 6, db + 6, idesc, 1u, (uint32_t) (nk > 3));
+                                tc_commit_2sm_mcast(bar_empty0 + 8u * (uint32_t) i, (uint16_t) 3);
+                                tc_commit_2sm_mcast(bar_tfull0 + 8u * buf, (uint16_t) 3);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    lt += kMaxStages;
+                    ph ^= 1u;
+                }
+            } else {
             uint32_t s = 0, ph = 0;
-            for (int t = t0, lt = 0; t < t1; ++t, ++lt) {
+            const bool trace = kTraceBuild && (dflags & 1024) && blockIdx.x == 0 && blockIdx.y == 0;   // cycle stamps of kTraceTiles tiles
+            const uint32_t nk_force = ((uint32_t) dflags >> 12) & 7u;   // timing experiment: K steps per tile forced to 1..4
+            const bool one_buf = (dflags & 32768) != 0;                 // timing experiment: every tile into accumulator 0
+            const bool no_ring = (dflags & 65536) != 0;                 // timing experiment: no operand ring (no full wait, no empty commit)
+            long long tr[kTraceTiles][7];
+            if (trace)
+                for (int i = 0; i < kTraceTiles; ++i)
+                    for (int j = 0; j < 7; ++j) tr[i][j] = 0;
+            for (int lt = 0; lt < t1 - t0; ++lt) {
                 const uint32_t buf = (uint32_t) lt & 1u;
-                const uint32_t tmem_d = tmem_base + buf * (uint32_t) B200M_TILE_N;
+                const uint32_t tmem_d = tmem_base + (one_buf ? 0u : buf * (uint32_t) B200M_TILE_N);
+                const int ti = lt - kTraceTile0;
+                const bool tr_on = trace && ti >= 0 && ti < kTraceTiles;
                 for (int a = 0; a < ka; ++a) {
-                    mbar_wait(bar_full0 + 8u * s, ph);
+                    if (!no_ring) mbar_wait(bar_full0 + 8u * s, ph);
                     const uint64_t da = desc_a0 + (uint64_t) ((uint32_t) a * a_step);
                     const uint64_t db = desc_b0 + (uint64_t) (s * b_step);
                     // K steps of this atom: 4, or what is left of the row in the last one; +32 B (2 descriptor
                     // units) per K = 16 step inside the 128 B swizzle atom
-                    const uint32_t nk = a + 1 < ka ? nk_full : nk_last;
+                    uint32_t nk = a + 1 < ka ? nk_full : nk_last;
+                    if (nk_force) nk = nk_force;
                     // The accumulator buffer is waited for LAST, with the operands landed and the descriptors built:
                     // for short descriptors the hand-back of the buffer by the epilogue is the critical path, and
                     // everything between that arrival and the first MMA is latency on it.
+                    if (tr_on && a == 0) tr[ti][0] = clock64();   // operands landed
                     if (a == 0) mbar_wait(bar_tempty0 + 8u * buf, (((uint32_t) lt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
+                    if (tr_on && a == 0) tr[ti][1] = clock64();   // accumulator buffer handed back
                     if (elect_one()) {
                         tc_mma<PAIR>(tmem_d, da, db, idesc, (uint32_t) (a != 0), (uint32_t) (nk > 0));
+                        if (tr_on && a == 0) tr[ti][2] = clock64();
                         tc_mma<PAIR>(tmem_d, da + 2, db + 2, idesc, 1u, (uint32_t) (nk > 1));
+                        if (tr_on && a == 0) tr[ti][3] = clock64();
                         tc_mma<PAIR>(tmem_d, da + 4, db + 4, idesc, 1u, (uint32_t) (nk > 2));
                         tc_mma<PAIR>(tmem_d, da + 6, db + 6, idesc, 1u, (uint32_t) (nk > 3));
+                        if (tr_on && a == 0) tr[ti][4] = clock64();
                         // frees the B stage once these MMAs have read it (in every CTA that writes into it)
-                        if (PAIR) tc_commit_2sm_mcast(bar_empty0 + 8u * s, (uint16_t) 3);
-                        else if (p.cluster == 1) tc_commit(bar_empty0 + 8u * s);
-                        else tc_commit_mcast(bar_empty0 + 8u * s, cmask);
+                        if (!no_ring) {
+                            if (PAIR) tc_commit_2sm_mcast(bar_empty0 + 8u * s, (uint16_t) 3);
+                            else if (p.cluster == 1) tc_commit(bar_empty0 + 8u * s);
+                            else tc_commit_mcast(bar_empty0 + 8u * s, cmask);
+                        }
+                        if (tr_on && a == 0) tr[ti][5] = clock64();
                     }
                     __syncwarp();
                     if (++s == (uint32_t) stages) { s = 0; ph ^= 1u; }
@@ -574,9 +641,18 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 if (elect_one()) {   // accumulators of this tile complete (in both CTAs of a pair)
                     if (PAIR) tc_commit_2sm_mcast(bar_tfull0 + 8u * buf, (uint16_t) 3);
                     else tc_commit(bar_tfull0 + 8u * buf);
+                    if (tr_on) tr[ti][6] = clock64();   // MMAs and commits issued
                 }
                 __syncwarp();
             }
+            if (trace) {
+                // the stamps live in whichever lane was elected (the same one every time); the others hold zeros
+                for (int i = 0; i < kTraceTiles && kTraceTile0 + i < t1 - t0; ++i)
+                    if (tr[i][6] != 0 && tr[i][2] != 0)
+                        printf("b200match trace mma tile %d: %lld %lld %lld %lld %lld %lld %lld\n", kTraceTile0 + i, tr[i][0],
+                               tr[i][1], tr[i][2], tr[i][3], tr[i][4], tr[i][5], tr[i][6]);
+            }
+            }   // general issue loop
         }
     } else {
         // ===== epilogue: a thread owns one TMEM lane (query row) and kColsPerWarp columns of every tile.  With EH = 2
@@ -615,11 +691,16 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         int n_slow = 0;
         const bool prof = (dflags & 512) != 0;
         int col_base = t0 * B200M_TILE_N + half * kColsPerWarp;
+        const bool trace = kTraceBuild && (dflags & 1024) && blockIdx.x < 2 && blockIdx.y == 0;
+        long long tr[kTraceTiles][4];
         for (int lt = 0; lt < t1 - t0; ++lt, col_base += B200M_TILE_N) {
             const uint32_t buf = (uint32_t) lt & 1u;
+            const int ti = lt - kTraceTile0;
+            const bool tr_on = trace && ti >= 0 && ti < kTraceTiles;
             long long c0 = prof ? clock64() : 0;
             mbar_wait(bar_tfull0 + 8u * buf, ((uint32_t) lt >> 1) & 1u);
             tc_fence_after();
+            if (tr_on) tr[ti][0] = clock64();   // accumulators seen complete
             if (prof) { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const uint32_t taddr = lane_base + buf * (uint32_t) B200M_TILE_N;
             // 128 columns at a time: four TMEM loads in flight, one wait.  The accumulator buffer goes back to the MMA
@@ -635,6 +716,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tmem_ld_wait();
                 }
                 if (prof) { long long c1 = clock64(); c_ld += c1 - c0; c0 = c1; }
+                if (tr_on && h == kColsPerWarp / 128 - 1) tr[ti][1] = clock64();   // last TMEM load landed
                 if (h == kColsPerWarp / 128 - 1) {
                     tc_fence_before();
                     __syncwarp();
@@ -643,6 +725,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         else mbar_arrive(bar_tempty0 + 8u * buf);
                     }
                 }
+                if (tr_on && h == kColsPerWarp / 128 - 1) tr[ti][2] = clock64();   // buffer handed back
                 if (EH == 2) st.thr = fminf(st.thr, lds_f32(s_thr_peer));   // pick up what the partner thread has learnt
                 if (dflags & (1 | 32)) continue;
                 if (dump) {   // debug: raw accumulators of this tile
@@ -657,10 +740,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
                 if (dflags & 256) {   // timing experiment: fast path only
                     if (fminf(fminf(min32(r0), min32(r1)), fminf(min32(r2), min32(r3))) < st.thr) st.na += 1.f;
+                    if (tr_on) tr[ti][3] = clock64();
                     continue;
                 }
                 const float thr_before = st.thr;
                 process128<KT, EH>(r0, r1, r2, r3, col_base + h * 128, st, k, out, out_v, cap);
+                if (tr_on) tr[ti][3] = clock64();   // filtering done
                 if (prof) {
                     long long c1 = clock64();
                     const bool slow = __any_sync(0xffffffffu, st.thr != thr_before);
@@ -672,6 +757,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (prof && lane == 0 && blockIdx.x < 2 && blockIdx.y == 0)
             printf("b200match epi-prof cta %d warp %d tiles %d: wait %lld ld %lld fast %lld slow %lld (entries that tightened: %d)\n",
                    blockIdx.x, warp, t1 - t0, c_wait, c_ld, c_fast, c_slow, n_slow);
+        if (trace && lane == 0)
+            for (int i = 0; i < kTraceTiles && kTraceTile0 + i < t1 - t0; ++i)
+                printf("b200match trace epi cta %d warp %d tile %d: %lld %lld %lld %lld\n", blockIdx.x, warp, kTraceTile0 + i,
+                       tr[i][0], tr[i][1], tr[i][2], tr[i][3]);
         if ((dflags & 256) && st.na == -1.f) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
         if (active && !dump) {
             p.cand_cnt[list_row] = st.cnt;
@@ -869,6 +958,9 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
         p.cand_val = ctx->ws_cand_val.as<float>();
         p.cand_thr = ctx->ws_cand_thr.as<float>();
     }
+    // One-atom descriptors (FPFH) in pair mode with the full 12-stage ring: fully unrolled issue loop (B200M_TC_LEAN=0
+    // falls back to the general loop).
+    p.lean = (pair && p.ka == 1 && stages == kMaxStages && ctx->tc_lean != 0) ? 1 : 0;
     *has_values_out = eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
