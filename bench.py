@@ -40,9 +40,10 @@ WORKLOADS = {
 }
 METRIC = "descriptor queries/sec (k=2 + mutual)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE candidate-kernel launch, from the ncu --set full capture of the
-# same workload on 1 GPU (profiles/r01b_ncu_<wl>_cand.txt).  The kernel is tensor bound; the traffic is the FP16 train
+# same workload on 1 GPU (profiles/r01b_ncu_c3_cand.txt, profiles/r01c_ncu_c2_cand.txt).  The kernel is tensor bound; the traffic is the FP16 train
 # operand array streaming through L2 once per wave of query tiles (algorithmic operand bytes: 0.77 GB for c3).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c3": 19.784716e9 + 219.15264e6, "c2": 55.755776e6 + 14.412032e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c3": 19.784716e9 + 219.15264e6, "c2": 61.290240e6 + 21.985280e6}
+NCU_TRAFFIC_SOURCE = {"c3": "profiles/r01b_ncu_c3_cand.txt", "c2": "profiles/r01c_ncu_c2_cand.txt"}
 
 
 def peaks():
@@ -318,7 +319,7 @@ def run_b200(args, wl):
     roofline = {"bound": "tensor", "kernel": "tc_candidates_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(wl) if world == 1 else None,
-                "traffic_source": "bytes per launch, profiles/r01b_ncu_%s_cand.txt (ncu --set full, 1 GPU)" % wl
+                "traffic_source": "bytes per launch, %s (ncu --set full, 1 GPU)" % NCU_TRAFFIC_SOURCE.get(wl, "-")
                                   if world == 1 and wl in NCU_TRAFFIC_BYTES_PER_LAUNCH else None,
                 "peak_source": pk["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "launch_ms": cand_ms_per_step / max(n_launch, 1), "launches_per_step": n_launch,
