@@ -49,6 +49,11 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
     headers = [os.path.join(CSRC, "internal.cuh"), os.path.join(HERE, "..", "include", "b200match.h")]
+    # objects are reused by mtime, which knows nothing about the flags they were compiled with
+    flags_stamp = os.path.join(CSRC, ".flags")
+    flags_now = " ".join(FLAGS)
+    if not os.path.exists(flags_stamp) or open(flags_stamp).read() != flags_now:
+        force = True
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
@@ -67,6 +72,8 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libb200match build failed")
+    with open(flags_stamp, "w") as f:
+        f.write(flags_now)
     # The stamp did not match, so always relink.  One CUDA runtime per process: bind to the shared libcudart.so.12
     # (the one torch has already loaded when the library is used next to torch; /usr/local/cuda/lib64 for
     # stand-alone C++ users) instead of a private static copy -- two runtimes in one process can disagree about

@@ -74,7 +74,9 @@ struct TcParams {
     int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
                           // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages, 32 = epilogue only
                           // drains TMEM (no filtering), 64 / 128 = force EH = 1 / 2, 256 = fast path only,
-                          // 512 = per-warp cycle totals, 1024 = cycle stamps of a few tiles (CTA pair 0)
+                          // 512 = per-warp cycle totals, 1024 = cycle stamps of a few tiles (CTA pair 0),
+                          // (n << 12) = n K steps per tile, 32768 = one accumulator, 65536 = no operand ring,
+                          // 131072 / 262144 = service-scheduler / all epilogue warps skip a quarter of their columns
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -497,15 +499,19 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             __syncwarp();
             uint32_t s = 0, ph = 1;
+            // opaque register copies of the ring's addresses (see the epilogue: keeps ptxas from re-deriving them per tile)
+            uint32_t r_empty = bar_empty0, r_full = bar_full0, r_lead_full = lead_full0, r_sb = sB_u;
+            asm volatile("" : "+r"(r_empty), "+r"(r_full), "+r"(r_lead_full), "+r"(r_sb));
+            const uint32_t stage_bytes = (uint32_t) (kStageBytes / 2);   // pair mode: half a train tile per CTA
             for (int t = (dflags & 65536) ? t1 : t0; t < t1; ++t) {
                 for (int a = 0; a < ka; ++a) {
-                    mbar_wait(bar_empty0 + 8u * s, ph);
+                    mbar_wait(r_empty + 8u * s, ph);
                     if (elect_one()) {
                         if (dflags & 4) {   // timing experiment: no B traffic at all
-                            if (crank == 0) mbar_arrive(bar_full0 + 8u * s);
+                            if (crank == 0) mbar_arrive(r_full + 8u * s);
                         } else {
-                            if (crank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, (uint32_t) (2 * p.stage_bytes));
-                            tma_load_2d_2sm(sB_u + s * (uint32_t) p.stage_bytes, &tmap_t, lead_full0 + 8u * s, a * 64,
+                            if (crank == 0) mbar_arrive_expect_tx(r_full + 8u * s, 2u * stage_bytes);
+                            tma_load_2d_2sm(r_sb + s * stage_bytes, &tmap_t, r_lead_full + 8u * s, a * 64,
                                             t * B200M_TILE_N + row_off);
                         }
                     }
@@ -552,7 +558,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t nk_full = (dflags & 2) ? 0u : 4u;
             const uint32_t nk_last = (dflags & 2) ? 0u : (uint32_t) (p.ksteps - 4 * (ka - 1));   // K steps of the last atom (1..4)
             constexpr uint32_t idesc = PAIR ? kInstrDescPair : kInstrDesc;
-            if (PAIR && EH == 2 && p.lean && !(DBG && (dflags & ~(1 | 32 | 256 | 512)))) {
+            if (PAIR && EH == 2 && p.lean && !(DBG && (dflags & ~(1 | 32 | 256 | 512 | 131072 | 262144)))) {
                 // One-atom descriptors (FPFH-33: 3 MMAs = 384 tensor-pipe cycles per tile).  The general loop below costs
                 // this warp ~100 dependent instructions per tile (stage index in a vector register: R2UR moves, address
                 // arithmetic, descriptor adds) -- ~630 cycles when it has its scheduler to itself, far more while the two
@@ -686,6 +692,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int k = p.k, cap = p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(bar_tempty0, 0) : bar_tempty0;
+        // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
+        // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
+        // half of them a dependent chain in front of the barrier test and of the first TMEM load) -- on the hand-off
+        // chain of every tile.
+        uint32_t e_tfull = bar_tfull0, e_tempty = tempty_dst0, e_tmem = lane_base, e_peer = s_thr_peer;
+        asm volatile("" : "+r"(e_tfull), "+r"(e_tempty), "+r"(e_tmem), "+r"(e_peer));
         uint32_t r0[32], r1[32], r2[32], r3[32];
         long long c_wait = 0, c_ld = 0, c_fast = 0, c_slow = 0;   // B200M_TC_DEBUG & 512: where this warp's cycles go
         int n_slow = 0;
@@ -698,21 +710,24 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const int ti = lt - kTraceTile0;
             const bool tr_on = trace && ti >= 0 && ti < kTraceTiles;
             long long c0 = prof ? clock64() : 0;
-            mbar_wait(bar_tfull0 + 8u * buf, ((uint32_t) lt >> 1) & 1u);
+            mbar_wait(e_tfull + 8u * buf, ((uint32_t) lt >> 1) & 1u);
             tc_fence_after();
             if (tr_on) tr[ti][0] = clock64();   // accumulators seen complete
             if (prof) { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
-            const uint32_t taddr = lane_base + buf * (uint32_t) B200M_TILE_N;
+            const uint32_t taddr = e_tmem + buf * (uint32_t) B200M_TILE_N;
             // 128 columns at a time: four TMEM loads in flight, one wait.  The accumulator buffer goes back to the MMA
             // issuer as soon as this warp's last load has landed in registers -- the filtering below then overlaps the
             // MMAs of the tile after next instead of sitting on their critical path.
 #pragma unroll 1
             for (int h = 0; h < kColsPerWarp / 128; ++h) {
+                // timing experiments (with the fast-path-only flag 256): 131072 = the warps that share a scheduler with the
+                // TMA producer / MMA issuer (quarters 0, 1) skip a quarter of their columns, 262144 = every warp does
+                const bool skip4 = DBG && (((dflags & 131072) && quarter < 2) || (dflags & 262144));
                 if (!(dflags & 1)) {
                     tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128), r0);
                     tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 32), r1);
                     tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 64), r2);
-                    tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 96), r3);
+                    if (!skip4) tmem_ld_32x32b_x32(taddr + (uint32_t) (h * 128 + 96), r3);
                     tmem_ld_wait();
                 }
                 if (prof) { long long c1 = clock64(); c_ld += c1 - c0; c0 = c1; }
@@ -721,12 +736,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (PAIR) mbar_arrive_cluster(tempty_dst0 + 8u * buf);
-                        else mbar_arrive(bar_tempty0 + 8u * buf);
+                        if (PAIR) mbar_arrive_cluster(e_tempty + 8u * buf);
+                        else mbar_arrive(e_tempty + 8u * buf);
                     }
                 }
                 if (tr_on && h == kColsPerWarp / 128 - 1) tr[ti][2] = clock64();   // buffer handed back
-                if (EH == 2) st.thr = fminf(st.thr, lds_f32(s_thr_peer));   // pick up what the partner thread has learnt
+                if (EH == 2) st.thr = fminf(st.thr, lds_f32(e_peer));   // pick up what the partner thread has learnt
                 if (dflags & (1 | 32)) continue;
                 if (dump) {   // debug: raw accumulators of this tile
                     float *d = dump + ((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * kColsPerWarp + h * 128;
@@ -739,7 +754,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     }
                 }
                 if (dflags & 256) {   // timing experiment: fast path only
-                    if (fminf(fminf(min32(r0), min32(r1)), fminf(min32(r2), min32(r3))) < st.thr) st.na += 1.f;
+                    float m = fminf(fminf(min32(r0), min32(r1)), min32(r2));
+                    if (!skip4) m = fminf(m, min32(r3));
+                    if (m < st.thr) st.na += 1.f;
                     if (tr_on) tr[ti][3] = clock64();
                     continue;
                 }
