@@ -42,7 +42,7 @@ METRIC = "descriptor queries/sec (k=2 + mutual)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE candidate-kernel launch, from the ncu --set full capture of the
 # same workload on 1 GPU (profiles/r01b_ncu_c3_cand.txt, profiles/r01c_ncu_c2_cand.txt).  The kernel is tensor bound; the traffic is the FP16 train
 # operand array streaming through L2 once per wave of query tiles (algorithmic operand bytes: 0.77 GB for c3).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c3": 19.784716e9 + 219.15264e6, "c2": 61.290240e6 + 21.985280e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c3": 19.784716e9 + 219.15264e6, "c2": 61.222400e6 + 21.200384e6}
 NCU_TRAFFIC_SOURCE = {"c3": "profiles/r01b_ncu_c3_cand.txt", "c2": "profiles/r01c_ncu_c2_cand.txt"}
 
 
@@ -56,24 +56,37 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region.  The sampler process is started before the
+    warm-up (nvidia-smi needs a few hundred ms before its first line) and streams a time-stamped line every 20 ms;
+    stop() keeps the lines whose time stamps fall inside the timed region's host-clock window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_begin = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def begin(self):
+        """Call right before the timed region starts (after the barrier)."""
+        self.t_begin = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+
     def stop(self):
+        t_end = time.time()
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -82,20 +95,35 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
-                for n, v in zip(names, r[3:7]):
-                    if v.strip().lower() == "active":
-                        reasons.add(n)
+                try:
+                    ts = self._stamp(r[0])
+                except Exception:
+                    ts = t_end   # unparsable time stamp: count the line as inside the window
+                parsed.append((ts, float(r[1]), float(r[2]), float(r[3]),
+                               [n for n, v in zip(names, r[4:8]) if v.strip().lower() == "active"]))
             except Exception:
                 pass
-        if not sm:
+        if not parsed:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        t0 = self.t_begin if self.t_begin is not None else parsed[0][0]
+        window = "timed region"
+        inside = [q for q in parsed if t0 <= q[0] <= t_end]
+        if not inside:
+            # a timed region shorter than the sampling period: the samples closest to it (the warm-up runs the same
+            # steps back to back, so these are still samples under load)
+            mid = 0.5 * (t0 + t_end)
+            inside = sorted(parsed, key=lambda q: abs(q[0] - mid))[:3]
+            window = "nearest samples (timed region of %.0f ms is shorter than the sampling period)" % (1e3 * (t_end - t0))
+        reasons = set()
+        for q in inside:
+            reasons.update(q[4])
+        return {"sm_mhz": float(np.median([q[1] for q in inside])), "sm_max_mhz": float(max(q[2] for q in inside)),
+                "power_w_max": float(max(q[3] for q in inside)), "samples": len(inside), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -231,8 +259,10 @@ def run_b200(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, sampler=None):
         barrier()
+        if sampler:
+            sampler.begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -246,11 +276,11 @@ def run_b200(args, wl):
 
     # ---- device-resident value (per-kernel CUDA events are recorded on the stream without host syncs) ----
     be.ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
     be.ctx.reset_stats()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_total, out = timed(step_device, args.steps)
+    ms_total, out = timed(step_device, args.steps, sampler)
     clocks = sampler.stop() if sampler else None
     st = be.ctx.stats()
     be.ctx.set_profiling(False)
