@@ -379,17 +379,19 @@ __device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
 // re-derived, and the columns under it are appended.  Tracking only chunk minima keeps the list an upper bound of the
 // true k smallest -- all the certificate needs -- and misses a tightening only when two of the k smallest fall into
 // one 32-column chunk.
+// The four 32-column chunks sit at train rows col0, col0 + 32, col0 + hi, col0 + hi + 32 (hi = 64: 128 consecutive columns;
+// hi = 128 in the split-N kernel, where a warp's columns 64..127 come from the other CTA's half of the train tile).
 template <int KT, int EH>
 __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const uint32_t (&r2)[32],
-                                           const uint32_t (&r3)[32], int col0, RowState<KT> &st, int k,
+                                           const uint32_t (&r3)[32], int col0, int hi, RowState<KT> &st, int k,
                                            int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
     const float m0 = min32(r0), m1 = min32(r1), m2 = min32(r2), m3 = min32(r3);
     if (fminf(min3(m0, m1, m2), m3) < st.thr) {   // inactive rows carry thr = -inf
         if (kth_smallest<KT>(st, k) == INFINITY) {
             if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, out_v, cap);
             if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, out_v, cap);
-            if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + 64, st, k, out, out_v, cap);
-            if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + 96, st, k, out, out_v, cap);
+            if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + hi, st, k, out, out_v, cap);
+            if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + hi + 32, st, k, out, out_v, cap);
         } else {
             tk_insert<KT>(st, m0);
             tk_insert<KT>(st, m1);
@@ -399,8 +401,8 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
             const float thr = st.thr;
             if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
             if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
-            if (m2 < thr) append_chunk<EH>(r2, col0 + 64, thr, st.cnt, out, out_v, cap);
-            if (m3 < thr) append_chunk<EH>(r3, col0 + 96, thr, st.cnt, out, out_v, cap);
+            if (m2 < thr) append_chunk<EH>(r2, col0 + hi, thr, st.cnt, out, out_v, cap);
+            if (m3 < thr) append_chunk<EH>(r3, col0 + hi + 32, thr, st.cnt, out, out_v, cap);
         }
     }
 }
@@ -410,14 +412,23 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
 //       scheduler), warp w drains TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of every tile.
 // DBG:  compiles the timing experiments (TcParams::debug_flags) and the accumulator dump in; the production
 //       instantiation carries none of it in its loops.
-template <int KT, bool PAIR, int EH, bool DBG>
-__global__ void __launch_bounds__(64 + 128 * EH, 1)
+// SPLITN: (pair mode, EH = 2, one-atom descriptors) every 256-column accumulator is two independent 128-column halves:
+//       MMAs of N = 128 issued by one issuer warp per half (warp 1 and the extra warp 10), a full / empty barrier pair per
+//       (buffer, half), handed back by the eight epilogue warps (four per CTA) that own the half.  Four hand-off chains
+//       of 192 MMA cycles are in flight instead of two of 384, and a slow epilogue warp only holds up its own half.
+//       Column c of half h is train row h*64 + c of the tile for c < 64 (CTA 0's stage rows) and 128 + h*64 + (c - 64)
+//       beyond (CTA 1's).
+template <int KT, bool PAIR, int EH, bool SPLITN, bool DBG>
+__global__ void __launch_bounds__(64 + 128 * EH + (SPLITN ? 32 : 0), 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
                      const TcParams p) {
     const int dflags = DBG ? p.debug_flags : 0;
     float *const dump = DBG ? p.dump : nullptr;
     constexpr int kEpiWarps = 4 * EH;
     constexpr int kEpiThreads = 128 * EH;
+    constexpr int kIssuer2 = 2 + kEpiWarps;          // SPLITN: the warp that issues the second column half
+    constexpr uint32_t kAcc = SPLITN ? 4u : 2u;      // accumulator hand-off units: buffers, or (buffer, half) pairs
+    static_assert(!SPLITN || (PAIR && EH == 2), "split-N is a pair-mode, two-column-half kernel");
     constexpr int kColsPerWarp = B200M_TILE_N / EH;
     // Everything in shared memory is addressed through the shared window (32-bit addresses).  The operand tiles need
     // 1024-byte alignment (128B-swizzle atoms of 8 rows); the dynamic segment starts at a 1024-aligned window offset as
@@ -434,9 +445,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t bar_empty0 = bar_full0 + 8u * (uint32_t) stages;
     const uint32_t bar_a = bar_full0 + 8u * (uint32_t) (2 * stages);
     const uint32_t bar_tfull0 = bar_a + 8u;
-    const uint32_t bar_tempty0 = bar_a + 24u;
-    const uint32_t tmem_slot = bars_u + 8u * (uint32_t) (2 * stages + 5);
-    const uint32_t s_thr = bars_u + 8u * (uint32_t) (2 * stages + 6);     // [2][128] f32: published thresholds per column half
+    const uint32_t bar_tempty0 = bar_tfull0 + 8u * kAcc;                  // SPLITN: index buf * 2 + half
+    const uint32_t tmem_slot = bar_tempty0 + 8u * kAcc;
+    const uint32_t s_thr = tmem_slot + 8u;                               // [2][128] f32: published thresholds per column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -450,14 +461,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int s = 0; s < stages; ++s) {
             mbar_init(bar_full0 + 8u * s, 1);
             // multicast mode: every CTA of the cluster must have read the stage; pair mode: one commit frees it
-            mbar_init(bar_empty0 + 8u * s, PAIR ? 1u : (uint32_t) p.cluster);
+            mbar_init(bar_empty0 + 8u * s, SPLITN ? 2u : PAIR ? 1u : (uint32_t) p.cluster);   // SPLITN: both issuers commit
         }
         mbar_init(bar_a, 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < (int) kAcc; ++b) {
             mbar_init(bar_tfull0 + 8u * b, 1);
             // one arrival per epilogue WARP (a per-thread count serialises hundreds of barrier updates per tile);
             // pair mode: both CTAs' epilogue warps report to the leader, whose MMA thread owns the accumulators
-            mbar_init(bar_tempty0 + 8u * b, PAIR ? 2u * kEpiWarps : (uint32_t) kEpiWarps);
+            mbar_init(bar_tempty0 + 8u * b, SPLITN ? 8u : PAIR ? 2u * kEpiWarps : (uint32_t) kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -545,7 +556,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (SPLITN && warp == kIssuer2)) {
         // ===== MMA issuer.  One MMA (K = 16) is 128 tensor-pipe cycles, so the issue loop has to stay far below that
         // per instruction: warp-uniform control flow, ring position kept as counters (no divisions), descriptors
         // advanced by adding to their low word, the four K steps of an atom unrolled. =====
@@ -558,7 +569,44 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t nk_full = (dflags & 2) ? 0u : 4u;
             const uint32_t nk_last = (dflags & 2) ? 0u : (uint32_t) (p.ksteps - 4 * (ka - 1));   // K steps of the last atom (1..4)
             constexpr uint32_t idesc = PAIR ? kInstrDescPair : kInstrDesc;
-            if (PAIR && EH == 2 && p.lean && !(DBG && (dflags & ~(1 | 32 | 256 | 512 | 131072 | 262144)))) {
+            if (SPLITN) {
+                // one issuer per column half: N = 128 MMAs on this CTA pair's rows [half*64, half*64 + 64) of every stage
+                // (8 KB into each CTA's half tile), accumulator columns [buf*256 + half*128, +128); the unrolled loop of
+                // the one-atom case below with the half's constants
+                const uint32_t hf = warp == 1 ? 0u : 1u;
+                constexpr uint32_t idesc_h = (1u << 4) | ((uint32_t) ((B200M_TILE_N / 2) >> 3) << 17) |
+                                             ((uint32_t) ((2 * B200M_TILE_M) >> 4) << 24);
+                const uint64_t desc_bh = desc_b0 + (uint64_t) (hf * (uint32_t) ((64 * 128) >> 4));
+                const uint32_t tmem_h = tmem_base + hf * (uint32_t) (B200M_TILE_N / 2);
+                const int nt = t1 - t0;
+                const uint32_t nk = nk_last;
+                uint32_t ph = 0;
+                int lt = 0;
+                while (lt < nt) {
+#pragma unroll
+                    for (int i = 0; i < kMaxStages; ++i) {
+                        if (lt + i < nt) {
+                            const uint32_t buf = (uint32_t) (i & 1);
+                            mbar_wait(bar_full0 + 8u * (uint32_t) i, ph);
+                            mbar_wait(bar_tempty0 + 8u * (buf * 2u + hf), (uint32_t) (((i >> 1) & 1) ^ 1));
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t db = desc_bh + (uint64_t) ((uint32_t) i * (uint32_t) ((kStageBytes / 2) >> 4));
+                                const uint32_t tmem_d = tmem_h + buf * (uint32_t) B200M_TILE_N;
+                                tc_mma<PAIR>(tmem_d, desc_a0, db, idesc_h, 0u, (uint32_t) (nk > 0));
+                                tc_mma<PAIR>(tmem_d, desc_a0 + 2, db + 2, idesc_h, 1u, (uint32_t) (nk > 1));
+                                tc_mma<PAIR>(tmem_d, desc_a0 + 4, db + 4, idesc_h, 1u, (uint32_t) (nk > 2));
+                                tc_mma<PAIR>(tmem_d, desc_a0 + 6, db + 6, idesc_h, 1u, (uint32_t) (nk > 3));
+                                tc_commit_2sm_mcast(bar_empty0 + 8u * (uint32_t) i, (uint16_t) 3);
+                                tc_commit_2sm_mcast(bar_tfull0 + 8u * (buf * 2u + hf), (uint16_t) 3);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    lt += kMaxStages;
+                    ph ^= 1u;
+                }
+            } else if (PAIR && EH == 2 && p.lean && !(DBG && (dflags & ~(1 | 32 | 256 | 512 | 131072 | 262144)))) {
                 // One-atom descriptors (FPFH-33: 3 MMAs = 384 tensor-pipe cycles per tile).  The general loop below costs
                 // this warp ~100 dependent instructions per tile (stage index in a vector register: R2UR moves, address
                 // arithmetic, descriptor adds) -- ~630 cycles when it has its scheduler to itself, far more while the two
@@ -660,7 +708,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             }   // general issue loop
         }
-    } else {
+    } else if (warp < 2 + kEpiWarps) {
         // ===== epilogue: a thread owns one TMEM lane (query row) and kColsPerWarp columns of every tile.  With EH = 2
         // the two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
         const int quarter = warp & 3;
@@ -691,18 +739,24 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         float *const out_v = EH == 1 ? p.cand_val + list_row * p.cap : nullptr;
         const int k = p.k, cap = p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
-        const uint32_t tempty_dst0 = PAIR ? map_to_cta(bar_tempty0, 0) : bar_tempty0;
+        // SPLITN: this warp's hand-off barriers are those of its column half (index buf * 2 + half)
+        const uint32_t acc_stride = SPLITN ? 16u : 8u;
+        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u);
+        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u);
+        const uint32_t tempty_dst0 = PAIR ? map_to_cta(tempty_mine, 0) : tempty_mine;
         // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
         // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
         // half of them a dependent chain in front of the barrier test and of the first TMEM load) -- on the hand-off
         // chain of every tile.
-        uint32_t e_tfull = bar_tfull0, e_tempty = tempty_dst0, e_tmem = lane_base, e_peer = s_thr_peer;
+        uint32_t e_tfull = tfull_mine, e_tempty = tempty_dst0, e_tmem = lane_base, e_peer = s_thr_peer;
         asm volatile("" : "+r"(e_tfull), "+r"(e_tempty), "+r"(e_tmem), "+r"(e_peer));
         uint32_t r0[32], r1[32], r2[32], r3[32];
         long long c_wait = 0, c_ld = 0, c_fast = 0, c_slow = 0;   // B200M_TC_DEBUG & 512: where this warp's cycles go
         int n_slow = 0;
         const bool prof = (dflags & 512) != 0;
-        int col_base = t0 * B200M_TILE_N + half * kColsPerWarp;
+        // first train row of this warp's columns in the current tile, and where its upper 64 columns continue
+        int col_base = t0 * B200M_TILE_N + half * (SPLITN ? 64 : kColsPerWarp);
+        const int col_hi = SPLITN ? 128 : 64;
         const bool trace = kTraceBuild && (dflags & 1024) && blockIdx.x < 2 && blockIdx.y == 0;
         long long tr[kTraceTiles][4];
         for (int lt = 0; lt < t1 - t0; ++lt, col_base += B200M_TILE_N) {
@@ -710,7 +764,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const int ti = lt - kTraceTile0;
             const bool tr_on = trace && ti >= 0 && ti < kTraceTiles;
             long long c0 = prof ? clock64() : 0;
-            mbar_wait(e_tfull + 8u * buf, ((uint32_t) lt >> 1) & 1u);
+            mbar_wait(e_tfull + acc_stride * buf, ((uint32_t) lt >> 1) & 1u);
             tc_fence_after();
             if (tr_on) tr[ti][0] = clock64();   // accumulators seen complete
             if (prof) { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
@@ -736,21 +790,22 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (PAIR) mbar_arrive_cluster(e_tempty + 8u * buf);
-                        else mbar_arrive(e_tempty + 8u * buf);
+                        if (PAIR) mbar_arrive_cluster(e_tempty + acc_stride * buf);
+                        else mbar_arrive(e_tempty + acc_stride * buf);
                     }
                 }
                 if (tr_on && h == kColsPerWarp / 128 - 1) tr[ti][2] = clock64();   // buffer handed back
                 if (EH == 2) st.thr = fminf(st.thr, lds_f32(e_peer));   // pick up what the partner thread has learnt
                 if (dflags & (1 | 32)) continue;
                 if (dump) {   // debug: raw accumulators of this tile
-                    float *d = dump + ((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N + half * kColsPerWarp + h * 128;
+                    float *d = dump + ((size_t) qtile * B200M_TILE_M + row_in_tile) * B200M_TILE_N +
+                               half * (SPLITN ? 64 : kColsPerWarp) + h * 128;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         d[i] = __uint_as_float(r0[i]);
                         d[32 + i] = __uint_as_float(r1[i]);
-                        d[64 + i] = __uint_as_float(r2[i]);
-                        d[96 + i] = __uint_as_float(r3[i]);
+                        d[col_hi + i] = __uint_as_float(r2[i]);
+                        d[col_hi + 32 + i] = __uint_as_float(r3[i]);
                     }
                 }
                 if (dflags & 256) {   // timing experiment: fast path only
@@ -761,7 +816,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     continue;
                 }
                 const float thr_before = st.thr;
-                process128<KT, EH>(r0, r1, r2, r3, col_base + h * 128, st, k, out, out_v, cap);
+                process128<KT, EH>(r0, r1, r2, r3, col_base + h * 128, col_hi, st, k, out, out_v, cap);
                 if (tr_on) tr[ti][3] = clock64();   // filtering done
                 if (prof) {
                     long long c1 = clock64();
@@ -849,12 +904,12 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
     return 0;
 }
 
-template <int KT, bool PAIR, int EH, bool DBG>
+template <int KT, bool PAIR, int EH, bool SPLITN, bool DBG>
 int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
-    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, SPLITN, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(64 + 128 * EH, 1, 1);
+    cfg.blockDim = dim3(64 + 128 * EH + (SPLITN ? 32 : 0), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -864,7 +919,7 @@ int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, DBG>, *mq, *mt, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, SPLITN, DBG>, *mq, *mt, p);
     if (e != cudaSuccess) {
         cudaGetLastError();   // do not leave the launch error behind for the next call
         return b200m_fail_msg(ctx, std::string("tc_candidates launch failed: ") + cudaGetErrorString(e) + " (grid " +
@@ -978,6 +1033,9 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // One-atom descriptors (FPFH) in pair mode with the full 12-stage ring: fully unrolled issue loop (B200M_TC_LEAN=0
     // falls back to the general loop).
     p.lean = (pair && p.ka == 1 && stages == kMaxStages && ctx->tc_lean != 0) ? 1 : 0;
+    // split-N (two 128-column halves per accumulator, an issuer warp per half) for one-atom descriptors: C2 launch
+    // 4.18 -> 3.92 ms; B200M_TC_SPLITN=0 selects the single N = 256 MMA per tile (comparison)
+    const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
     *has_values_out = eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
@@ -988,10 +1046,11 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     int rc;
     const bool dbg = dump != nullptr || ctx->tc_debug != 0;
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \
-    rc = pair ? (eh == 2 ? launch_tc<KT_, true, 2, DBG_>(ctx, mq, mt, p, grid, smem)          \
-                         : launch_tc<KT_, true, 1, DBG_>(ctx, mq, mt, p, grid, smem))         \
-              : (eh == 2 ? launch_tc<KT_, false, 2, DBG_>(ctx, mq, mt, p, grid, smem)         \
-                         : launch_tc<KT_, false, 1, DBG_>(ctx, mq, mt, p, grid, smem))
+    rc = pair ? (eh == 2 ? (splitn ? launch_tc<KT_, true, 2, true, DBG_>(ctx, mq, mt, p, grid, smem)          \
+                                   : launch_tc<KT_, true, 2, false, DBG_>(ctx, mq, mt, p, grid, smem))        \
+                         : launch_tc<KT_, true, 1, false, DBG_>(ctx, mq, mt, p, grid, smem))                  \
+              : (eh == 2 ? launch_tc<KT_, false, 2, false, DBG_>(ctx, mq, mt, p, grid, smem)                  \
+                         : launch_tc<KT_, false, 1, false, DBG_>(ctx, mq, mt, p, grid, smem))
 #define B200M_TC_CASE(KT_)               \
     if (dbg) { B200M_TC_CASE2(KT_, true); } \
     else { B200M_TC_CASE2(KT_, false); }
