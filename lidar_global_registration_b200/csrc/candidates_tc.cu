@@ -31,7 +31,8 @@
 
 namespace {
 
-// threads per CTA = 64 + 128 * EH: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, then 4 * EH epilogue warps
+// threads per CTA = 64 + 128 * EH (+ 32 in split-N mode): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, then 4 * EH
+// epilogue warps, then (split-N) the issuer of the second column half
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
