@@ -36,7 +36,7 @@ namespace {
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
-constexpr int kTailBytes = 2048;         // barriers (<= 29 x 8 B) + TMEM slot + per-row shared state (3 x 128 x 4 B)
+constexpr int kTailBytes = 2048;         // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (2 x 128 x 4 B)
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
@@ -440,7 +440,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t sA_u = smem_u;
     const uint32_t sB_u = sA_u + (uint32_t) (p.ka * kATileBytes);
     const uint32_t bars_u = sB_u + (uint32_t) (p.stages * p.stage_bytes);
-    // barrier map: [0..S) full, [S..2S) empty, 2S a_full, 2S+1.. tmem_full[2], 2S+3.. tmem_empty[2]
+    // barrier map: [0..S) full, [S..2S) empty, 2S a_full, then tmem_full[kAcc], tmem_empty[kAcc], the TMEM slot, thresholds
     const int stages = p.stages;
     const uint32_t bar_full0 = bars_u;
     const uint32_t bar_empty0 = bar_full0 + 8u * (uint32_t) stages;

@@ -1,0 +1,61 @@
+"""Host-side pieces of bench.py that need no GPU: the clock sampler's time-window logic."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def _sampler_with(lines, t_begin):
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    import tempfile
+
+    class _Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+    s.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    s.f.write("\n".join(lines) + "\n")
+    s.f.flush()
+    s.p = _Done()
+    s.t_begin = t_begin
+    return s
+
+
+def _line(t, sm, reasons=("Not Active",) * 4):
+    import datetime
+    ts = datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    return "%s, %d, 1965, 500.0, %s" % (ts, sm, ", ".join(reasons))
+
+
+def test_stamp_round_trip():
+    t = 1792335361.123
+    import datetime
+    text = datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    assert abs(bench.ClockSampler._stamp(text) - t) < 2e-3
+
+
+def test_only_samples_inside_the_timed_region_count():
+    now = time.time()
+    lines = [_line(now - 2.0, 1000),                                                    # warm-up: outside
+             _line(now - 0.5, 1400, ("Not Active", "Not Active", "Not Active", "Active")),
+             _line(now - 0.3, 1500)]
+    out = _sampler_with(lines, now - 1.0).stop()
+    assert out["samples"] == 2 and out["window"] == "timed region"
+    assert out["sm_mhz"] == 1450.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_short_region_falls_back_to_nearest_samples_and_says_so():
+    now = time.time()
+    lines = [_line(now - 3.0, 1000), _line(now - 2.0, 1100), _line(now - 1.5, 1200), _line(now - 1.0, 1300)]
+    out = _sampler_with(lines, now - 0.01).stop()
+    assert out["samples"] == 3 and out["window"].startswith("nearest samples")
+    assert out["sm_mhz"] == 1200.0
+
+
+def test_no_lines_is_reported():
+    out = _sampler_with([], time.time()).stop()
+    assert out["reasons"] == ["no samples"]
