@@ -9,7 +9,6 @@ current torch stream, torch.distributed/NCCL for the one exchange step the path 
 The sharding logic is backend-agnostic: tests drive it on CPU with gloo and a stand-in backend; on the
 GPU box the backend is GpuBackend and the process group is NCCL over NVLink.
 """
-import numpy as np
 import torch
 
 from . import matcher as M

@@ -1,6 +1,5 @@
 """The oracle pinned against the reference's own known-answer vectors and against
 frozen cv2.BFMatcher outputs (tests/golden/make_golden.py).  CPU only."""
-import glob
 import os
 
 import numpy as np
