@@ -36,7 +36,7 @@ namespace {
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
-constexpr int kTailBytes = 2048;         // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (2 x 128 x 4 B)
+constexpr int kTailBytes = 3072;         // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B)
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
@@ -408,6 +408,26 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
     }
 }
 
+// The same for a 64-column batch (two chunks; the alternating-tile epilogue keeps only 64 accumulators in registers).
+template <int KT, int EH>
+__device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int col0, RowState<KT> &st, int k,
+                                          int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
+    const float m0 = min32(r0), m1 = min32(r1);
+    if (fminf(m0, m1) < st.thr) {   // inactive rows carry thr = -inf
+        if (kth_smallest<KT>(st, k) == INFINITY) {
+            if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, out_v, cap);
+            if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, out_v, cap);
+        } else {
+            tk_insert<KT>(st, m0);
+            tk_insert<KT>(st, m1);
+            retighten<KT, EH>(st, k);
+            const float thr = st.thr;
+            if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
+            if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
+        }
+    }
+}
+
 // PAIR: CTA-pair mode (tcgen05.mma cta_group::2, M = 256 across two SMs, each CTA holds half of every train tile).
 // EH:   epilogue column halves.  1 = four epilogue warps, a thread owns a whole row; 2 = eight warps (two per
 //       scheduler), warp w drains TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of every tile.
@@ -419,17 +439,28 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
 //       of 192 MMA cycles are in flight instead of two of 384, and a slow epilogue warp only holds up its own half.
 //       Column c of half h is train row h*64 + c of the tile for c < 64 (CTA 0's stage rows) and 128 + h*64 + (c - 64)
 //       beyond (CTA 1's).
-template <int KT, bool PAIR, int EH, bool SPLITN, bool DBG>
-__global__ void __launch_bounds__(64 + 128 * EH + (SPLITN ? 32 : 0), 1)
+// ALT:  (split-N only) sixteen epilogue warps, each bound to ONE accumulator buffer: warp (buffer, half, lane quarter) drains
+//       the 128 columns of its half of every SECOND tile, in two 64-column batches (64 accumulators in registers, so that
+//       20 warps fit the register file).  An epilogue warp's per-tile chain -- barrier test, TMEM-load latency, hand-back,
+//       min pass, loop -- is what bounded the split-N kernel (every warp touched every tile: ~1000 cycles per tile against
+//       384 MMA cycles); here a warp has two tile periods for it.  Four private candidate lists per row and train split.
+template <int KT, bool PAIR, int EH, bool SPLITN, bool ALT, bool DBG>
+__global__ void __launch_bounds__(ALT ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
                      const TcParams p) {
     const int dflags = DBG ? p.debug_flags : 0;
     float *const dump = DBG ? p.dump : nullptr;
-    constexpr int kEpiWarps = 4 * EH;
-    constexpr int kEpiThreads = 128 * EH;
-    constexpr int kIssuer2 = 2 + kEpiWarps;          // SPLITN: the warp that issues the second column half
+    constexpr int kEpiWarps = 4 * EH * (ALT ? 2 : 1);
+    constexpr int kEpiThreads = 32 * kEpiWarps;
+    constexpr int kListsPerSplit = EH * (ALT ? 2 : 1);   // private candidate lists per row and train split
+    // Warp roles.  ALT: warps 0..3 are the service warpgroup (TMA producer, the two MMA issuers, one idle warp) and the
+    // sixteen epilogue warps form warpgroups 1..4, so that the register file can be re-divided per warpgroup
+    // (setmaxnreg): 640 threads start with 96 registers each, the service warpgroup drops to 56, the epilogue rises to 112.
+    constexpr int kEpiWarp0 = ALT ? 4 : 2;           // first epilogue warp (TMEM lane quarter = warp & 3 either way)
+    constexpr int kIssuer2 = ALT ? 2 : 2 + kEpiWarps;   // SPLITN: the warp that issues the second column half
     constexpr uint32_t kAcc = SPLITN ? 4u : 2u;      // accumulator hand-off units: buffers, or (buffer, half) pairs
     static_assert(!SPLITN || (PAIR && EH == 2), "split-N is a pair-mode, two-column-half kernel");
+    static_assert(!ALT || SPLITN, "the alternating-tile epilogue is a split-N kernel");
     constexpr int kColsPerWarp = B200M_TILE_N / EH;
     // Everything in shared memory is addressed through the shared window (32-bit addresses).  The operand tiles need
     // 1024-byte alignment (128B-swizzle atoms of 8 rows); the dynamic segment starts at a 1024-aligned window offset as
@@ -448,7 +479,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t bar_tfull0 = bar_a + 8u;
     const uint32_t bar_tempty0 = bar_tfull0 + 8u * kAcc;                  // SPLITN: index buf * 2 + half
     const uint32_t tmem_slot = bar_tempty0 + 8u * kAcc;
-    const uint32_t s_thr = tmem_slot + 8u;                               // [2][128] f32: published thresholds per column half
+    const uint32_t s_thr = (tmem_slot + 8u + 15u) & ~15u;                // published thresholds: [2][128] f32 per column half; ALT: [128][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -496,6 +527,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint16_t cmask = (uint16_t) ((1u << p.cluster) - 1u);
 
     if (warp == 0) {
+        if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
         // ===== TMA producer: the whole warp walks the ring (warp-uniform control flow keeps addresses and barrier
         // handles in uniform registers), one elected lane issues =====
         const int q_row = p.q_row0 + qtile * B200M_TILE_M;
@@ -558,6 +590,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
         }
     } else if (warp == 1 || (SPLITN && warp == kIssuer2)) {
+        if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
         // ===== MMA issuer.  One MMA (K = 16) is 128 tensor-pipe cycles, so the issue loop has to stay far below that
         // per instruction: warp-uniform control flow, ring position kept as counters (no divisions), descriptors
         // advanced by adding to their low word, the four K steps of an atom unrolled. =====
@@ -709,11 +742,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             }   // general issue loop
         }
-    } else if (warp < 2 + kEpiWarps) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+        if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         // ===== epilogue: a thread owns one TMEM lane (query row) and kColsPerWarp columns of every tile.  With EH = 2
         // the two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = ((warp - kEpiWarp0) >> 2) & 1;
+        const int bsel = ALT ? (warp - kEpiWarp0) >> 3 : 0;   // ALT: the accumulator buffer (tile parity) this warp is bound to
         const int row_in_tile = quarter * 32 + lane;
         const int local = qtile * B200M_TILE_M + row_in_tile;
         const bool active = local < p.n_rows;
@@ -722,8 +757,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
         st.thr = active ? INFINITY : -INFINITY;
         st.cnt = 0;
-        st.s_thr_own = s_thr + 4u * (uint32_t) (half * B200M_TILE_M + row_in_tile);
-        const uint32_t s_thr_peer = s_thr + 4u * (uint32_t) ((half ^ 1) * B200M_TILE_M + row_in_tile);
+        st.s_thr_own = ALT ? s_thr + 4u * (uint32_t) (row_in_tile * 4 + bsel * 2 + half)
+                           : s_thr + 4u * (uint32_t) (half * B200M_TILE_M + row_in_tile);
+        const uint32_t s_thr_peer = ALT ? s_thr + 16u * (uint32_t) row_in_tile   // the row's four published thresholds
+                                        : s_thr + 4u * (uint32_t) ((half ^ 1) * B200M_TILE_M + row_in_tile);
         sts_f32(st.s_thr_own, st.thr);
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
@@ -735,15 +772,15 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
         // every epilogue thread owns a private candidate list: [split][column half][row][cap]
-        const size_t list_row = (size_t) (split * EH + half) * p.n_rows + (active ? local : 0);
+        const size_t list_row = (size_t) (split * kListsPerSplit + bsel * 2 + half) * p.n_rows + (active ? local : 0);
         int32_t *const out = p.cand_idx + list_row * p.cap;
         float *const out_v = EH == 1 ? p.cand_val + list_row * p.cap : nullptr;
         const int k = p.k, cap = p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         // SPLITN: this warp's hand-off barriers are those of its column half (index buf * 2 + half)
         const uint32_t acc_stride = SPLITN ? 16u : 8u;
-        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u);
-        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u);
+        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + (ALT ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + (ALT ? 16u * (uint32_t) bsel : 0u);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(tempty_mine, 0) : tempty_mine;
         // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
         // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
@@ -751,6 +788,52 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // chain of every tile.
         uint32_t e_tfull = tfull_mine, e_tempty = tempty_dst0, e_tmem = lane_base, e_peer = s_thr_peer;
         asm volatile("" : "+r"(e_tfull), "+r"(e_tempty), "+r"(e_tmem), "+r"(e_peer));
+        if constexpr (ALT) {
+            // ===== alternating-tile epilogue: this warp owns accumulator buffer `bsel`, i.e. tiles bsel, bsel + 2, ... =====
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = e_tmem + (uint32_t) bsel * (uint32_t) B200M_TILE_N;
+            // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c
+            int col_base = (t0 + bsel) * B200M_TILE_N + half * 64;
+            uint32_t par = 0;
+            for (int lt = bsel; lt < t1 - t0; lt += 2, col_base += 2 * B200M_TILE_N) {
+                mbar_wait(e_tfull, par);
+                par ^= 1u;
+                tc_fence_after();
+                if (!(dflags & 1)) {
+                    tmem_ld_32x32b_x32(taddr, r0);
+                    tmem_ld_32x32b_x32(taddr + 32u, r1);
+                    tmem_ld_wait();
+                }
+                {   // what the row's other three threads have learnt (own entry included: harmless)
+                    float t0_, t1_, t2_, t3_;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
+                    st.thr = fminf(st.thr, fminf(fminf(t0_, t1_), fminf(t2_, t3_)));
+                }
+                if (!(dflags & (1 | 32))) {
+                    if (dflags & 256) {   // timing experiment: fast path only
+                        if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                    } else {
+                        process64<KT, EH>(r0, r1, col_base, st, k, out, out_v, cap);
+                    }
+                }
+                if (!(dflags & 1)) {
+                    tmem_ld_32x32b_x32(taddr + 64u, r0);
+                    tmem_ld_32x32b_x32(taddr + 96u, r1);
+                    tmem_ld_wait();
+                }
+                // all 128 columns are in registers or done: the half goes back to its MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(e_tempty);
+                if (!(dflags & (1 | 32))) {
+                    if (dflags & 256) {
+                        if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                    } else {
+                        process64<KT, EH>(r0, r1, col_base + 128, st, k, out, out_v, cap);
+                    }
+                }
+            }
+        } else {
         uint32_t r0[32], r1[32], r2[32], r3[32];
         long long c_wait = 0, c_ld = 0, c_fast = 0, c_slow = 0;   // B200M_TC_DEBUG & 512: where this warp's cycles go
         int n_slow = 0;
@@ -834,11 +917,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             for (int i = 0; i < kTraceTiles && kTraceTile0 + i < t1 - t0; ++i)
                 printf("b200match trace epi cta %d warp %d tile %d: %lld %lld %lld %lld\n", blockIdx.x, warp, kTraceTile0 + i,
                        tr[i][0], tr[i][1], tr[i][2], tr[i][3]);
+        }   // !ALT
         if ((dflags & 256) && st.na == -1.f) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
         if (active && !dump) {
             p.cand_cnt[list_row] = st.cnt;
             if (EH == 1) p.cand_thr[list_row] = st.thr;
         }
+    } else if (ALT) {   // the idle warp of the service warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
@@ -905,12 +991,12 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
     return 0;
 }
 
-template <int KT, bool PAIR, int EH, bool SPLITN, bool DBG>
+template <int KT, bool PAIR, int EH, bool SPLITN, bool ALT, bool DBG>
 int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
-    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, SPLITN, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, SPLITN, ALT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(64 + 128 * EH + (SPLITN ? 32 : 0), 1, 1);
+    cfg.blockDim = dim3(ALT ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -920,7 +1006,7 @@ int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, SPLITN, DBG>, *mq, *mt, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, SPLITN, ALT, DBG>, *mq, *mt, p);
     if (e != cudaSuccess) {
         cudaGetLastError();   // do not leave the launch error behind for the next call
         return b200m_fail_msg(ctx, std::string("tc_candidates launch failed: ") + cudaGetErrorString(e) + " (grid " +
@@ -974,6 +1060,22 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     if (stages < 2) return b200m_fail_msg(ctx, "tc_candidates: descriptor too long for the shared-memory pipeline");
     p.stages = stages;
     p.n_ttiles = (int) (t.n_pad / B200M_TILE_N);
+    // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
+    // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and there a thread that owns its whole row
+    // also records the accumulator values so that the re-rank can prune by the row's final threshold.
+    int eh = p.ka <= 2 ? 2 : 1;
+    if (ctx->tc_debug & 64) eh = 1;
+    if (ctx->tc_debug & 128) eh = 2;
+    // One-atom descriptors (FPFH) in pair mode with the full 12-stage ring: fully unrolled issue loop (B200M_TC_LEAN=0
+    // falls back to the general loop).
+    p.lean = (pair && p.ka == 1 && stages == kMaxStages && ctx->tc_lean != 0) ? 1 : 0;
+    // split-N (two 128-column halves per accumulator, an issuer warp per half) for one-atom descriptors: C2 launch
+    // 4.18 -> 3.92 ms; B200M_TC_SPLITN=0 selects the single N = 256 MMA per tile (comparison)
+    const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
+    // ... with sixteen epilogue warps, each bound to one accumulator buffer (B200M_TC_ALT=0: eight warps, every warp on
+    // every tile)
+    const bool alt = splitn && ctx->tc_alt != 0;
+    const int lists_per_split = eh * (alt ? 2 : 1);
     int n_splits = 1;
     if (!dump) {
         // Train splits balance the waves of CTAs: a (cluster of) query tile(s) is a work unit that occupies its SMs for
@@ -983,6 +1085,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
         const long long units = (n_qtiles + cluster - 1) / cluster, slots = ctx->sm_count / cluster > 0 ? ctx->sm_count / cluster : 1;
         int max_splits = p.n_ttiles / 8 > 0 ? p.n_ttiles / 8 : 1;
         if (max_splits > kMaxLists) max_splits = kMaxLists;
+        if (max_splits * lists_per_split > 32) max_splits = 32 / lists_per_split;   // the re-rank reads at most 32 lists per row
         double best = 0;
         for (int sp = 1; sp <= max_splits; ++sp) {
             const long long waves = (units * sp + slots - 1) / slots;
@@ -999,26 +1102,20 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.dim = q.dim;
     p.bmax = ctx->prep.max_norm[1 - direction];
     p.q_norm16 = q_ops ? q_norm : q.norm16.as<float>();
-    // Short descriptors (FPFH: 3 MMAs per tile) are bound by the epilogue's latency chain: two epilogue warps per
-    // scheduler.  Long ones (SHOT: 23 MMAs per tile) hide a four-warp epilogue, and there a thread that owns its whole row
-    // also records the accumulator values so that the re-rank can prune by the row's final threshold.
-    int eh = p.ka <= 2 ? 2 : 1;
-    if (ctx->tc_debug & 64) eh = 1;
-    if (ctx->tc_debug & 128) eh = 2;
     // A list receives a column whenever it is under the running threshold: for columns in random order that is a
     // record process, E = k (ln(n / k) + 1) appends with variance about E, n = the columns the list's thread sees.
     // cap = E + 8 sqrt(E) + 16 puts an overflow beyond 8 sigma; overflowed rows (adversarial column orders) are
     // still answered exactly, by the CUDA-core fallback.
     int cap = cap_request;
     if (cap <= 0) {
-        const double n_list = (double) p.tiles_per_split * B200M_TILE_N / eh;
+        const double n_list = (double) p.tiles_per_split * B200M_TILE_N / lists_per_split;
         const double expect = k * (log(fmax(n_list / k, 2.0)) + 1.0);
         cap = (int) (expect + 8.0 * sqrt(expect) + 16.0);
         cap = (cap + 7) / 8 * 8;
     }
     if (cap < k) cap = k;
     p.cap = cap;
-    const int n_lists = n_splits * eh;
+    const int n_lists = n_splits * lists_per_split;
     CK(ctx->ws_cand_idx.reserve(sizeof(int32_t) * (size_t) n_lists * n_rows * (size_t) cap));
     CK(ctx->ws_cand_cnt.reserve(sizeof(int32_t) * (size_t) n_lists * n_rows));
     p.cand_idx = ctx->ws_cand_idx.as<int32_t>();
@@ -1031,12 +1128,6 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
         p.cand_val = ctx->ws_cand_val.as<float>();
         p.cand_thr = ctx->ws_cand_thr.as<float>();
     }
-    // One-atom descriptors (FPFH) in pair mode with the full 12-stage ring: fully unrolled issue loop (B200M_TC_LEAN=0
-    // falls back to the general loop).
-    p.lean = (pair && p.ka == 1 && stages == kMaxStages && ctx->tc_lean != 0) ? 1 : 0;
-    // split-N (two 128-column halves per accumulator, an issuer warp per half) for one-atom descriptors: C2 launch
-    // 4.18 -> 3.92 ms; B200M_TC_SPLITN=0 selects the single N = 256 MMA per tile (comparison)
-    const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
     *has_values_out = eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
@@ -1047,11 +1138,12 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     int rc;
     const bool dbg = dump != nullptr || ctx->tc_debug != 0;
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \
-    rc = pair ? (eh == 2 ? (splitn ? launch_tc<KT_, true, 2, true, DBG_>(ctx, mq, mt, p, grid, smem)          \
-                                   : launch_tc<KT_, true, 2, false, DBG_>(ctx, mq, mt, p, grid, smem))        \
-                         : launch_tc<KT_, true, 1, false, DBG_>(ctx, mq, mt, p, grid, smem))                  \
-              : (eh == 2 ? launch_tc<KT_, false, 2, false, DBG_>(ctx, mq, mt, p, grid, smem)                  \
-                         : launch_tc<KT_, false, 1, false, DBG_>(ctx, mq, mt, p, grid, smem))
+    rc = pair ? (eh == 2 ? (alt ? launch_tc<KT_, true, 2, true, true, DBG_>(ctx, mq, mt, p, grid, smem)            \
+                                : splitn ? launch_tc<KT_, true, 2, true, false, DBG_>(ctx, mq, mt, p, grid, smem)  \
+                                         : launch_tc<KT_, true, 2, false, false, DBG_>(ctx, mq, mt, p, grid, smem)) \
+                         : launch_tc<KT_, true, 1, false, false, DBG_>(ctx, mq, mt, p, grid, smem))                \
+              : (eh == 2 ? launch_tc<KT_, false, 2, false, false, DBG_>(ctx, mq, mt, p, grid, smem)                \
+                         : launch_tc<KT_, false, 1, false, false, DBG_>(ctx, mq, mt, p, grid, smem))
 #define B200M_TC_CASE(KT_)               \
     if (dbg) { B200M_TC_CASE2(KT_, true); } \
     else { B200M_TC_CASE2(KT_, false); }
