@@ -455,7 +455,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     constexpr int kListsPerSplit = EH * (ALT ? 2 : 1);   // private candidate lists per row and train split
     // Warp roles.  ALT: warps 0..3 are the service warpgroup (TMA producer, the two MMA issuers, one idle warp) and the
     // sixteen epilogue warps form warpgroups 1..4, so that the register file can be re-divided per warpgroup
-    // (setmaxnreg): 640 threads start with 96 registers each, the service warpgroup drops to 56, the epilogue rises to 112.
+    // (setmaxnreg): 640 threads start with 96 registers each, the service warpgroup drops to 64, the epilogue rises to 112 (640 x 96 + 128 x (64 - 96) + 512 x (112 - 96) = 65536).
     constexpr int kEpiWarp0 = ALT ? 4 : 2;           // first epilogue warp (TMEM lane quarter = warp & 3 either way)
     constexpr int kIssuer2 = ALT ? 2 : 2 + kEpiWarps;   // SPLITN: the warp that issues the second column half
     constexpr uint32_t kAcc = SPLITN ? 4u : 2u;      // accumulator hand-off units: buffers, or (buffer, half) pairs
@@ -526,8 +526,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t) ((1u << p.cluster) - 1u);
 
+    // setmaxnreg is a warpgroup-aligned instruction: all four warps of a warpgroup execute the SAME instruction, so the
+    // service warpgroup re-divides its registers before its warps part ways.
+    const bool is_service = ALT ? warp < 4 : (warp < 2 || (SPLITN && warp == kIssuer2));
+    if (is_service) {
+    if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
     if (warp == 0) {
-        if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
         // ===== TMA producer: the whole warp walks the ring (warp-uniform control flow keeps addresses and barrier
         // handles in uniform registers), one elected lane issues =====
         const int q_row = p.q_row0 + qtile * B200M_TILE_M;
@@ -590,7 +594,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
         }
     } else if (warp == 1 || (SPLITN && warp == kIssuer2)) {
-        if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
         // ===== MMA issuer.  One MMA (K = 16) is 128 tensor-pipe cycles, so the issue loop has to stay far below that
         // per instruction: warp-uniform control flow, ring position kept as counters (no divisions), descriptors
         // advanced by adding to their low word, the four K steps of an atom unrolled. =====
@@ -742,7 +745,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             }   // general issue loop
         }
-    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    }
+    } else {
         if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         // ===== epilogue: a thread owns one TMEM lane (query row) and kColsPerWarp columns of every tile.  With EH = 2
         // the two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
@@ -923,8 +927,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             p.cand_cnt[list_row] = st.cnt;
             if (EH == 1) p.cand_thr[list_row] = st.thr;
         }
-    } else if (ALT) {   // the idle warp of the service warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
