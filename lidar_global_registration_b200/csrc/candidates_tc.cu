@@ -455,7 +455,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     constexpr int kListsPerSplit = EH * (ALT ? 2 : 1);   // private candidate lists per row and train split
     // Warp roles.  ALT: warps 0..3 are the service warpgroup (TMA producer, the two MMA issuers, one idle warp) and the
     // sixteen epilogue warps form warpgroups 1..4, so that the register file can be re-divided per warpgroup
-    // (setmaxnreg): 640 threads start with 96 registers each, the service warpgroup drops to 64, the epilogue rises to 112 (640 x 96 + 128 x (64 - 96) + 512 x (112 - 96) = 65536).
+    // (setmaxnreg): 640 threads start with 96 registers each, the service warpgroup drops to 64, the epilogue rises to 104 -- the pool a CTA can re-divide is what it was launched with: 128 x 64 + 512 x 104 = 640 x 96.
     constexpr int kEpiWarp0 = ALT ? 4 : 2;           // first epilogue warp (TMEM lane quarter = warp & 3 either way)
     constexpr int kIssuer2 = ALT ? 2 : 2 + kEpiWarps;   // SPLITN: the warp that issues the second column half
     constexpr uint32_t kAcc = SPLITN ? 4u : 2u;      // accumulator hand-off units: buffers, or (buffer, half) pairs
@@ -747,7 +747,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
     }
     } else {
-        if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+        if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
         // ===== epilogue: a thread owns one TMEM lane (query row) and kColsPerWarp columns of every tile.  With EH = 2
         // the two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
         const int quarter = warp & 3;

@@ -67,6 +67,7 @@ struct b200m_ctx {
     void *tmap_cache = nullptr;
     void *multiscale = nullptr;   // MultiscaleState (multiscale.cu)
     void *cluster = nullptr;      // ClusterState (cluster.cu)
+    void *wide = nullptr;         // WideState (wide.cu)
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     double masked_min_pairs = 1e9;   // B200M_MASKED_MIN_PAIRS: b200m_match skips unreferenced target rows in the reverse pass
                                      // from this many (source, target) pairs on (below, the row selection's host round trip
@@ -172,8 +173,23 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
 bool tc_supported(const b200m_ctx *ctx, int dim, int k);
 void tc_release(b200m_ctx *ctx);
 
-// multiscale.cu
+// multiscale.cu: one table of per-scale k-lists filed under the query keypoints (match_multiscale's concatenation)
+struct MultiscaleState {
+    size_t n_query_kps = 0;
+    int n_scales = 0, k = 0;
+    DevBuf idx, dist, cnt, bad, qmap, tmap, xyz, oidx, odist, ocnt, kidx, kdist, kcnt;
+};
 void multiscale_release(b200m_ctx *ctx);
+void ms_free(MultiscaleState *ms);
+int ms_begin(b200m_ctx *ctx, MultiscaleState *ms, size_t n_query_kps, int n_scales, int k);
+int ms_add_device(b200m_ctx *ctx, MultiscaleState *ms, int scale, size_t n_rows, const int32_t *d_idx, const float *d_dist,
+                  const int32_t *d_count, const int32_t *d_query_map, const int32_t *d_train_map, size_t n_train_rows,
+                  int64_t train_index_offset, size_t n_train_kps);
+int ms_vote_device(b200m_ctx *ctx, MultiscaleState *ms, const float *d_train_xyz, size_t xyz_stride_bytes, float iss_radius,
+                   int32_t *d_idx, float *d_dist, int32_t *d_count);
+
+// wide.cu
+void wide_release(b200m_ctx *ctx);
 
 // cluster.cu
 void cluster_release(b200m_ctx *ctx);

@@ -75,7 +75,8 @@ __global__ void ms_vote_kernel(size_t n_query_kps, int n_scales, int k, const in
                 if (j2 < 0) continue;
                 const float *b = xyz + (size_t) j2 * xyz_stride_floats;
                 const float dx = __fsub_rn(ax, b[0]), dy = __fsub_rn(ay, b[1]), dz = __fsub_rn(az, b[2]);
-                const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                // Eigen's Vector3f::norm(): the unrolled fixed-size reduction adds x^2 + (y^2 + z^2)
+                const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz))));
                 if (d < limit) c = __fadd_rn(c, __fdiv_rn(iss_radius, fmaxf(d, iss_radius)));
             }
         }
@@ -100,36 +101,28 @@ __global__ void ms_vote_kernel(size_t n_query_kps, int n_scales, int k, const in
 
 }  // namespace
 
-struct MultiscaleState {
-    size_t n_query_kps = 0;
-    int n_scales = 0, k = 0;
-    DevBuf idx, dist, cnt, bad, qmap, tmap, xyz, oidx, odist, ocnt, kidx, kdist, kcnt;
-};
-
 static MultiscaleState *ms_state(b200m_ctx *ctx) {
     if (!ctx->multiscale) ctx->multiscale = new MultiscaleState();
     return static_cast<MultiscaleState *>(ctx->multiscale);
 }
 
-void multiscale_release(b200m_ctx *ctx) {
-    MultiscaleState *ms = static_cast<MultiscaleState *>(ctx->multiscale);
+void ms_free(MultiscaleState *ms) {
     if (!ms) return;
     DevBuf *b[] = {&ms->idx, &ms->dist, &ms->cnt, &ms->bad, &ms->qmap, &ms->tmap, &ms->xyz, &ms->oidx, &ms->odist, &ms->ocnt,
                    &ms->kidx, &ms->kdist, &ms->kcnt};
     for (DevBuf *x : b) x->release();
     delete ms;
+}
+
+void multiscale_release(b200m_ctx *ctx) {
+    ms_free(static_cast<MultiscaleState *>(ctx->multiscale));
     ctx->multiscale = nullptr;
 }
 
-extern "C" {
-
-int b200m_multiscale_begin(b200m_ctx *ctx, size_t n_query_kps, int n_scales, int k) {
-    if (!ctx) return b200m_fail_msg(nullptr, "null context");
-    CK(cudaSetDevice(ctx->device));
+int ms_begin(b200m_ctx *ctx, MultiscaleState *ms, size_t n_query_kps, int n_scales, int k) {
     if (n_scales < 1 || n_scales > 32) return b200m_fail_msg(ctx, "b200m_multiscale_begin: n_scales must be in [1, 32]");
     if (k < 1 || k > B200M_MAX_K || n_scales * k > kMaxVoteCands)
         return b200m_fail_msg(ctx, "b200m_multiscale_begin: k in [1, 32] and n_scales * k <= 128");
-    MultiscaleState *ms = ms_state(ctx);
     ms->n_query_kps = n_query_kps;
     ms->n_scales = n_scales;
     ms->k = k;
@@ -143,12 +136,9 @@ int b200m_multiscale_begin(b200m_ctx *ctx, size_t n_query_kps, int n_scales, int
     return 0;
 }
 
-int b200m_multiscale_add_device(b200m_ctx *ctx, int scale, size_t n_rows, const int32_t *d_idx, const float *d_dist,
-                                const int32_t *d_count, const int32_t *d_query_map, const int32_t *d_train_map,
-                                size_t n_train_rows, int64_t train_index_offset, size_t n_train_kps) {
-    if (!ctx) return b200m_fail_msg(nullptr, "null context");
-    CK(cudaSetDevice(ctx->device));
-    MultiscaleState *ms = static_cast<MultiscaleState *>(ctx->multiscale);
+int ms_add_device(b200m_ctx *ctx, MultiscaleState *ms, int scale, size_t n_rows, const int32_t *d_idx, const float *d_dist,
+                  const int32_t *d_count, const int32_t *d_query_map, const int32_t *d_train_map, size_t n_train_rows,
+                  int64_t train_index_offset, size_t n_train_kps) {
     if (!ms || ms->n_scales == 0) return b200m_fail_msg(ctx, "b200m_multiscale_add: call b200m_multiscale_begin first");
     if (scale < 0 || scale >= ms->n_scales) return b200m_fail_msg(ctx, "b200m_multiscale_add: scale out of range");
     if (n_rows == 0) return 0;
@@ -162,11 +152,8 @@ int b200m_multiscale_add_device(b200m_ctx *ctx, int scale, size_t n_rows, const 
     return 0;
 }
 
-int b200m_multiscale_vote_device(b200m_ctx *ctx, const float *d_train_xyz, size_t xyz_stride_bytes, float iss_radius,
-                                 int32_t *d_idx, float *d_dist, int32_t *d_count) {
-    if (!ctx) return b200m_fail_msg(nullptr, "null context");
-    CK(cudaSetDevice(ctx->device));
-    MultiscaleState *ms = static_cast<MultiscaleState *>(ctx->multiscale);
+int ms_vote_device(b200m_ctx *ctx, MultiscaleState *ms, const float *d_train_xyz, size_t xyz_stride_bytes, float iss_radius,
+                   int32_t *d_idx, float *d_dist, int32_t *d_count) {
     if (!ms || ms->n_scales == 0) return b200m_fail_msg(ctx, "b200m_multiscale_vote: call b200m_multiscale_begin first");
     if (xyz_stride_bytes % 4 != 0 || xyz_stride_bytes < 12)
         return b200m_fail_msg(ctx, "b200m_multiscale_vote: xyz stride must be a multiple of 4 and >= 12 bytes");
@@ -178,6 +165,31 @@ int b200m_multiscale_vote_device(b200m_ctx *ctx, const float *d_train_xyz, size_
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
     return 0;
+}
+
+extern "C" {
+
+int b200m_multiscale_begin(b200m_ctx *ctx, size_t n_query_kps, int n_scales, int k) {
+    if (!ctx) return b200m_fail_msg(nullptr, "null context");
+    CK(cudaSetDevice(ctx->device));
+    return ms_begin(ctx, ms_state(ctx), n_query_kps, n_scales, k);
+}
+
+int b200m_multiscale_add_device(b200m_ctx *ctx, int scale, size_t n_rows, const int32_t *d_idx, const float *d_dist,
+                                const int32_t *d_count, const int32_t *d_query_map, const int32_t *d_train_map,
+                                size_t n_train_rows, int64_t train_index_offset, size_t n_train_kps) {
+    if (!ctx) return b200m_fail_msg(nullptr, "null context");
+    CK(cudaSetDevice(ctx->device));
+    return ms_add_device(ctx, static_cast<MultiscaleState *>(ctx->multiscale), scale, n_rows, d_idx, d_dist, d_count, d_query_map,
+                         d_train_map, n_train_rows, train_index_offset, n_train_kps);
+}
+
+int b200m_multiscale_vote_device(b200m_ctx *ctx, const float *d_train_xyz, size_t xyz_stride_bytes, float iss_radius,
+                                 int32_t *d_idx, float *d_dist, int32_t *d_count) {
+    if (!ctx) return b200m_fail_msg(nullptr, "null context");
+    CK(cudaSetDevice(ctx->device));
+    return ms_vote_device(ctx, static_cast<MultiscaleState *>(ctx->multiscale), d_train_xyz, xyz_stride_bytes, iss_radius, d_idx,
+                          d_dist, d_count);
 }
 
 // ---- host-buffer forms: what match_multiscale's loop body and tail become ---------------------------

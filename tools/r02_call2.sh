@@ -15,13 +15,8 @@ done
 for sp in 1 2 3 4 6 8; do
   B200M_TC_SPLITS=$sp timeout 300 python tools/cand_time.py c2 10 2>&1 | tail -1 | tee -a $O/cand_ab.log
 done
-for sp in 1 4 8; do
-  B200M_TC_SPLITS=$sp timeout 300 python tools/cand_time.py c3 3 2>&1 | tail -1 | tee -a $O/cand_ab.log
-done
 timeout 600 python tools/fullsize_parity.py c2 4096 2>&1 | tee $O/fullsize_parity_c2.log | tail -2
 timeout 900 python tools/fullsize_parity.py c4 4096 2>&1 | tee $O/fullsize_parity_c4.log | tail -2
 python tools/profile_target.py c2 1 > $O/plain_c2.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_candidates -c 1 -f -o $O/prof_c2_cand python tools/profile_target.py c2 1 > $O/ncu_c2.log 2>&1
-python tools/profile_target.py c3 1 > $O/plain_c3.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_candidates -c 2 -f -o $O/prof_c3_cand python tools/profile_target.py c3 1 > $O/ncu_c3.log 2>&1
 ls -la $O/*.ncu-rep
