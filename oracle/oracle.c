@@ -427,7 +427,11 @@ ORC_API void orc_spatial_vote(size_t nq, int k, int32_t *idx, float *dist, int32
                 const float *p1 = train_xyz + 3 * (size_t) oi[m1];
                 const float *p2 = train_xyz + 3 * (size_t) oi[m2];
                 float dx = p1[0] - p2[0], dy = p1[1] - p2[1], dz = p1[2] - p2[2];
-                float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                /* Eigen's Vector3f::norm(): the unrolled fixed-size reduction adds x^2 + (y^2 + z^2); separate roundings
+                 * (whether the reference's build contracts these into FMAs depends on PCL's exported -march flags:
+                 * unpinned) */
+                float yz = dy * dy + dz * dz;
+                float d = sqrtf(dx * dx + yz);
                 if (d < 32 * iss_radius) c += iss_radius / fmaxf(d, iss_radius);
             }
             if (c > best_count || (c == best_count && od[m1] < best_dist)) {
