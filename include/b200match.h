@@ -234,6 +234,34 @@ B200M_API int b200m_cluster_filter_device(b200m_ctx *ctx, const b200m_params *p,
 B200M_API int b200m_knn3d_device(b200m_ctx *ctx, const float *d_xyz, size_t n, size_t xyz_stride_bytes, int k,
                                  int32_t *d_nbr);
 
+/* ---- the matcher classes at the WIDE seam: FeatureBasedMatcherImpl<FeatureT>::match_impl -------------------------
+ * (include/matching.h:395-411 OneSidedMatcher, :428-453 LeftToRightMatcher, :492-517 ClusterMatcher), composed as
+ * the reference composes it: match_multiscale in both directions (per-scale kNN with k = p->k = randomness, remap
+ * to keypoint ids, concatenation, spatial vote -> at most ONE match per keypoint, :264-354; the reverse direction is
+ * the reference's inverse_tn call), printDebugInfo's average over the VOTED forward lists, then the matcher's filter
+ * loop over the voted lists.  p->mode: ONE_SIDED, MUTUAL or CLUSTER.
+ * scales[s] (ascending log2 radius, the scales common to both clouds): the two clouds' descriptor rows of that scale
+ * (kps_features_multiscale[s]: host pointers, rows `stride_bytes` apart, `dim` leading floats) and the row -> keypoint
+ * id maps (kps_indices_multiscale[s]; NULL = identity).  src/tgt_kps_xyz: st_src_.kps / st_tgt_.kps coordinates, one
+ * row per keypoint, `xyz_stride_bytes` apart; iss_radius_src/tgt: Storage::iss_radius of the two clouds (the vote over
+ * the forward lists uses the TARGET keypoints and iss_radius_tgt).  cluster_k: AlignmentParameters::cluster_k (CLUSTER
+ * mode only).  Outputs as b200m_match's: records in ascending index_query (keypoint ids; finalize's map to cloud
+ * indices stays with the caller), at most n_src_kps of them. */
+typedef struct {
+    const float *src_desc;   /* source cloud, this scale: first descriptor value of row 0 */
+    size_t n_src;
+    const int32_t *src_map;  /* [n_src] row -> source keypoint id, or NULL */
+    const float *tgt_desc;
+    size_t n_tgt;
+    const int32_t *tgt_map;  /* [n_tgt] row -> target keypoint id, or NULL */
+} b200m_scale;
+B200M_API int b200m_match_multiscale(b200m_ctx *ctx, const b200m_params *p, const b200m_scale *scales, int n_scales,
+                                     size_t stride_bytes, int dim, const float *src_kps_xyz, size_t n_src_kps,
+                                     const float *tgt_kps_xyz, size_t n_tgt_kps, size_t xyz_stride_bytes,
+                                     float iss_radius_src, float iss_radius_tgt, int cluster_k, const float *thr_src,
+                                     const float *thr_tgt, b200m_corr *out, size_t cap, size_t *n_out,
+                                     float *avg_first_dist);
+
 B200M_API int b200m_version(void);
 
 /* ---- test hooks (used by tests/ only; not part of the reference-facing surface) ----

@@ -153,6 +153,7 @@ void b200m_destroy(b200m_ctx *ctx) {
     tc_release(ctx);
     multiscale_release(ctx);
     cluster_release(ctx);
+    wide_release(ctx);
     if (ctx->pool) {
         if (ctx->pool->created)
             for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventDestroy(ctx->pool->ev[i]);
@@ -612,7 +613,8 @@ int b200m_filter_device(b200m_ctx *ctx, const b200m_params *p, size_t row_begin,
     int launches = 0;
     StatTimer t(ctx, &ctx->stats.ms_filter);
     CK(launch_filter(p->mode, p->k, p->ratio_thr, p->distance_thr, row_begin, n_rows, d_fidx, d_fdist, d_fcount, d_ridx,
-                     d_rdist, d_rcount, n_rev_rows, d_thr_src, d_thr_tgt, ctx->side[0].index_offset, d_out, cap, d_n_out,
+                     d_rdist, d_rcount, n_rev_rows, d_thr_src, d_thr_tgt, ctx->side[0].index_offset, ctx->side[1].index_offset, d_out, cap,
+                     d_n_out,
                      d_avg, ctx->ws_scan.p, ctx->ws_scan.cap, ctx->stream, &launches));
     ctx->stats.launches += launches;
     t.stop();

@@ -394,11 +394,13 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
             if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + hi, st, k, out, out_v, cap);
             if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + hi + 32, st, k, out, out_v, cap);
         } else {
+            const float T_before = kth_smallest<KT>(st, k);
             tk_insert<KT>(st, m0);
             tk_insert<KT>(st, m1);
             tk_insert<KT>(st, m2);
             tk_insert<KT>(st, m3);
-            retighten<KT, EH>(st, k);
+            // a hit inside the certificate's margin (T <= v < thr(T)) leaves the k-th smallest where it was
+            if (kth_smallest<KT>(st, k) < T_before) retighten<KT, EH>(st, k);
             const float thr = st.thr;
             if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
             if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
@@ -418,9 +420,10 @@ __device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32
             if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, out_v, cap);
             if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, out_v, cap);
         } else {
+            const float T_before = kth_smallest<KT>(st, k);
             tk_insert<KT>(st, m0);
             tk_insert<KT>(st, m1);
-            retighten<KT, EH>(st, k);
+            if (kth_smallest<KT>(st, k) < T_before) retighten<KT, EH>(st, k);
             const float thr = st.thr;
             if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
             if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
@@ -439,17 +442,22 @@ __device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32
 //       of 192 MMA cycles are in flight instead of two of 384, and a slow epilogue warp only holds up its own half.
 //       Column c of half h is train row h*64 + c of the tile for c < 64 (CTA 0's stage rows) and 128 + h*64 + (c - 64)
 //       beyond (CTA 1's).
-// ALT:  (split-N only) sixteen epilogue warps, each bound to ONE accumulator buffer: warp (buffer, half, lane quarter) drains
-//       the 128 columns of its half of every SECOND tile, in two 64-column batches (64 accumulators in registers, so that
-//       20 warps fit the register file).  An epilogue warp's per-tile chain -- barrier test, TMEM-load latency, hand-back,
-//       min pass, loop -- is what bounded the split-N kernel (every warp touched every tile: ~1000 cycles per tile against
-//       384 MMA cycles); here a warp has two tile periods for it.  Four private candidate lists per row and train split.
-template <int KT, bool PAIR, int EH, bool SPLITN, bool ALT, bool DBG>
-__global__ void __launch_bounds__(ALT ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1)
+// EPI:  (split-N only) 1 or 2 = sixteen epilogue warps holding 64 accumulators each (20 warps x 96 registers fit the
+//       register file; four private candidate lists per row and train split).
+//       1 ("alternating tiles"): a warp is bound to ONE accumulator buffer and drains the 128 columns of its half of every
+//         second tile in two 64-column batches; the half goes back to the issuer after the second batch has been loaded,
+//         i.e. the filtering of the first batch sits on the hand-off chain (measured: drain-only 2.44 ms per C2 launch,
+//         fast path only 2.78 ms, full kernel 3.91 ms -- the append / threshold path of the first batch stalls the chain).
+//       2 ("quarter columns"): a warp owns 64 columns of EVERY tile; the half of the accumulator (N = 128 MMA) goes back
+//         as soon as both of its 64-column warps have their values in registers, all filtering happens off the chain.
+template <int KT, bool PAIR, int EH, bool SPLITN, int EPI, bool DBG>
+__global__ void __launch_bounds__(EPI ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
                      const TcParams p) {
     const int dflags = DBG ? p.debug_flags : 0;
     float *const dump = DBG ? p.dump : nullptr;
+    constexpr bool ALT = EPI != 0;   // the sixteen-warp layouts (warp roles, register re-division, four lists per row)
+    constexpr bool QE = EPI == 2;
     constexpr int kEpiWarps = 4 * EH * (ALT ? 2 : 1);
     constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr int kListsPerSplit = EH * (ALT ? 2 : 1);   // private candidate lists per row and train split
@@ -500,7 +508,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_init(bar_tfull0 + 8u * b, 1);
             // one arrival per epilogue WARP (a per-thread count serialises hundreds of barrier updates per tile);
             // pair mode: both CTAs' epilogue warps report to the leader, whose MMA thread owns the accumulators
-            mbar_init(bar_tempty0 + 8u * b, SPLITN ? 8u : PAIR ? 2u * kEpiWarps : (uint32_t) kEpiWarps);
+            mbar_init(bar_tempty0 + 8u * b, QE ? 16u : SPLITN ? 8u : PAIR ? 2u * kEpiWarps : (uint32_t) kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -752,7 +760,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // the two threads of a row share its candidate list (shared-memory counter) and exchange thresholds. =====
         const int quarter = warp & 3;
         const int half = ((warp - kEpiWarp0) >> 2) & 1;
-        const int bsel = ALT ? (warp - kEpiWarp0) >> 3 : 0;   // ALT: the accumulator buffer (tile parity) this warp is bound to
+        // EPI 1: the accumulator buffer (tile parity) this warp is bound to; EPI 2: which 64 columns of its 128-column half
+        const int bsel = ALT ? (warp - kEpiWarp0) >> 3 : 0;
         const int row_in_tile = quarter * 32 + lane;
         const int local = qtile * B200M_TILE_M + row_in_tile;
         const bool active = local < p.n_rows;
@@ -783,8 +792,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         // SPLITN: this warp's hand-off barriers are those of its column half (index buf * 2 + half)
         const uint32_t acc_stride = SPLITN ? 16u : 8u;
-        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + (ALT ? 16u * (uint32_t) bsel : 0u);
-        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + (ALT ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + (EPI == 1 ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + (EPI == 1 ? 16u * (uint32_t) bsel : 0u);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(tempty_mine, 0) : tempty_mine;
         // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
         // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
@@ -792,7 +801,39 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // chain of every tile.
         uint32_t e_tfull = tfull_mine, e_tempty = tempty_dst0, e_tmem = lane_base, e_peer = s_thr_peer;
         asm volatile("" : "+r"(e_tfull), "+r"(e_tempty), "+r"(e_tmem), "+r"(e_peer));
-        if constexpr (ALT) {
+        if constexpr (QE) {
+            // ===== quarter-column epilogue: 64 columns of every tile; hand back first, filter afterwards =====
+            uint32_t r0[32], r1[32];
+            const uint32_t tcol = e_tmem + (uint32_t) bsel * 64u;
+            // train rows of the warp's columns: TMEM columns 0..63 of a half are tile rows half*64 + c (CTA 0's stage rows),
+            // columns 64..127 are rows 128 + half*64 + c (CTA 1's)
+            int col_base = t0 * B200M_TILE_N + bsel * 128 + half * 64;
+            for (int lt = 0; lt < t1 - t0; ++lt, col_base += B200M_TILE_N) {
+                const uint32_t buf = (uint32_t) lt & 1u;
+                mbar_wait(e_tfull + 16u * buf, ((uint32_t) lt >> 1) & 1u);
+                tc_fence_after();
+                if (!(dflags & 1)) {
+                    const uint32_t taddr = tcol + buf * (uint32_t) B200M_TILE_N;
+                    tmem_ld_32x32b_x32(taddr, r0);
+                    tmem_ld_32x32b_x32(taddr + 32u, r1);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(e_tempty + 16u * buf);
+                {   // what the row's other three threads have learnt (own entry included: harmless)
+                    float t0_, t1_, t2_, t3_;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
+                    st.thr = fminf(st.thr, fminf(fminf(t0_, t1_), fminf(t2_, t3_)));
+                }
+                if (dflags & (1 | 32)) continue;
+                if (dflags & 256) {   // timing experiment: fast path only
+                    if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                    continue;
+                }
+                process64<KT, EH>(r0, r1, col_base, st, k, out, out_v, cap);
+            }
+        } else if constexpr (ALT) {
             // ===== alternating-tile epilogue: this warp owns accumulator buffer `bsel`, i.e. tiles bsel, bsel + 2, ... =====
             uint32_t r0[32], r1[32];
             const uint32_t taddr = e_tmem + (uint32_t) bsel * (uint32_t) B200M_TILE_N;
@@ -993,12 +1034,12 @@ int get_tmap(b200m_ctx *ctx, int side, bool as_query, int cluster, const CUtenso
     return 0;
 }
 
-template <int KT, bool PAIR, int EH, bool SPLITN, bool ALT, bool DBG>
+template <int KT, bool PAIR, int EH, bool SPLITN, int EPI, bool DBG>
 int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, const TcParams &p, dim3 grid, size_t smem) {
-    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, SPLITN, ALT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute(tc_candidates_kernel<KT, PAIR, EH, SPLITN, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(ALT ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1, 1);
+    cfg.blockDim = dim3(EPI ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -1008,7 +1049,7 @@ int launch_tc(b200m_ctx *ctx, const CUtensorMap *mq, const CUtensorMap *mt, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, SPLITN, ALT, DBG>, *mq, *mt, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_candidates_kernel<KT, PAIR, EH, SPLITN, EPI, DBG>, *mq, *mt, p);
     if (e != cudaSuccess) {
         cudaGetLastError();   // do not leave the launch error behind for the next call
         return b200m_fail_msg(ctx, std::string("tc_candidates launch failed: ") + cudaGetErrorString(e) + " (grid " +
@@ -1074,9 +1115,10 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // split-N (two 128-column halves per accumulator, an issuer warp per half) for one-atom descriptors: C2 launch
     // 4.18 -> 3.92 ms; B200M_TC_SPLITN=0 selects the single N = 256 MMA per tile (comparison)
     const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
-    // ... with sixteen epilogue warps, each bound to one accumulator buffer (B200M_TC_ALT=0: eight warps, every warp on
-    // every tile)
-    const bool alt = splitn && ctx->tc_alt != 0;
+    // ... with sixteen epilogue warps of 64 accumulators each: B200M_TC_ALT=2 (default) quarter columns of every tile,
+    // hand-back before filtering; =1 alternating tiles; =0 eight warps of 128 accumulators, every warp on every tile
+    const int epi = splitn ? (ctx->tc_alt == 1 ? 1 : ctx->tc_alt != 0 ? 2 : 0) : 0;
+    const bool alt = epi != 0;
     const int lists_per_split = eh * (alt ? 2 : 1);
     int n_splits = 1;
     if (!dump) {
@@ -1140,12 +1182,13 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     int rc;
     const bool dbg = dump != nullptr || ctx->tc_debug != 0;
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \
-    rc = pair ? (eh == 2 ? (alt ? launch_tc<KT_, true, 2, true, true, DBG_>(ctx, mq, mt, p, grid, smem)            \
-                                : splitn ? launch_tc<KT_, true, 2, true, false, DBG_>(ctx, mq, mt, p, grid, smem)  \
-                                         : launch_tc<KT_, true, 2, false, false, DBG_>(ctx, mq, mt, p, grid, smem)) \
-                         : launch_tc<KT_, true, 1, false, false, DBG_>(ctx, mq, mt, p, grid, smem))                \
-              : (eh == 2 ? launch_tc<KT_, false, 2, false, false, DBG_>(ctx, mq, mt, p, grid, smem)                \
-                         : launch_tc<KT_, false, 1, false, false, DBG_>(ctx, mq, mt, p, grid, smem))
+    rc = pair ? (eh == 2 ? (epi == 2 ? launch_tc<KT_, true, 2, true, 2, DBG_>(ctx, mq, mt, p, grid, smem)        \
+                            : epi == 1 ? launch_tc<KT_, true, 2, true, 1, DBG_>(ctx, mq, mt, p, grid, smem)      \
+                            : splitn ? launch_tc<KT_, true, 2, true, 0, DBG_>(ctx, mq, mt, p, grid, smem)        \
+                                     : launch_tc<KT_, true, 2, false, 0, DBG_>(ctx, mq, mt, p, grid, smem))      \
+                         : launch_tc<KT_, true, 1, false, 0, DBG_>(ctx, mq, mt, p, grid, smem))                  \
+              : (eh == 2 ? launch_tc<KT_, false, 2, false, 0, DBG_>(ctx, mq, mt, p, grid, smem)                  \
+                         : launch_tc<KT_, false, 1, false, 0, DBG_>(ctx, mq, mt, p, grid, smem))
 #define B200M_TC_CASE(KT_)               \
     if (dbg) { B200M_TC_CASE2(KT_, true); } \
     else { B200M_TC_CASE2(KT_, false); }

@@ -163,6 +163,8 @@ int b200m_cluster_filter_device(b200m_ctx *ctx, const b200m_params *p, int clust
     if (!p || p->k < 1 || p->k > B200M_MAX_K) return b200m_fail_msg(ctx, "b200m_cluster_filter: params.k must be in [1, 32]");
     if (cluster_k < 1 || cluster_k > kMaxClusterK) return b200m_fail_msg(ctx, "b200m_cluster_filter: cluster_k must be in [1, 64]");
     if (!d_n_out) return b200m_fail_msg(ctx, "b200m_cluster_filter: null n_out");
+    if (ctx->side[0].index_offset || ctx->side[1].index_offset)   // the neighbourhood tables are addressed by the reported indices
+        return b200m_fail_msg(ctx, "b200m_cluster_filter: descriptor sets uploaded with a non-zero index_offset are not supported");
     const int k = p->k;
     ClusterState *cs = cl_state(ctx);
     cudaStream_t st = ctx->stream;
@@ -186,7 +188,8 @@ int b200m_cluster_filter_device(b200m_ctx *ctx, const b200m_params *p, int clust
     CK(ctx->ws_scan.reserve(filter_scan_ws_bytes(n_src, k)));
     int launches = 1;
     CK(launch_filter(B200M_MODE_CLUSTER, k, p->ratio_thr, p->distance_thr, 0, n_src, d_fidx, d_fdist, d_fcount, nullptr, nullptr,
-                     nullptr, 0, d_thr_src, d_thr_tgt, ctx->side[0].index_offset, d_out, cap, d_n_out, d_avg, ctx->ws_scan.p,
+                     nullptr, 0, d_thr_src, d_thr_tgt, ctx->side[0].index_offset, ctx->side[1].index_offset, d_out, cap, d_n_out, d_avg,
+                     ctx->ws_scan.p,
                      ctx->ws_scan.cap, st, &launches, cs->cdist.as<float>()));
     ctx->stats.launches += launches;
     t.stop();

@@ -34,7 +34,7 @@ struct FilterArgs {
     const int32_t *ridx; const float *rdist; const int32_t *rcount;
     const float *thr_src; const float *thr_tgt;
     const float *cdist;   // cluster mode: per (row, slot) max cluster distance, negative = rejected (cluster.cu)
-    long long src_offset;
+    long long src_offset, tgt_offset;   // index_offset of the two sides: reported indices carry them, table rows do not
 };
 
 __device__ __forceinline__ bool eval_elem(const FilterArgs &a, size_t e, b200m_corr &c) {
@@ -44,8 +44,10 @@ __device__ __forceinline__ bool eval_elem(const FilterArgs &a, size_t e, b200m_c
     if (slot >= fc) return false;
     const int32_t *fi = a.fidx + local * a.k;
     const float *fd = a.fdist + local * a.k;
-    const long long i_glob = (long long) (a.row_begin + local) + a.src_offset;
+    const size_t i_loc = a.row_begin + local;
+    const long long i_glob = (long long) i_loc + a.src_offset;
     int32_t j = fi[slot];
+    const long long j_loc = (long long) j - a.tgt_offset;   // row of the reverse table / threshold array
     float d = fd[slot];
     if (a.mode == B200M_MODE_RATIO || a.mode == B200M_MODE_RATIO_MUTUAL) {
         if (fc < 2) return false;
@@ -57,13 +59,13 @@ __device__ __forceinline__ bool eval_elem(const FilterArgs &a, size_t e, b200m_c
         d = cd;
     }
     if (a.mode == B200M_MODE_MUTUAL || a.mode == B200M_MODE_RATIO_MUTUAL) {
-        if (j < 0 || (size_t) j >= a.n_rev_rows) return false;
-        const int rc = a.rcount[j];
-        const int32_t *ri = a.ridx + (size_t) j * a.k;
+        if (j_loc < 0 || (size_t) j_loc >= a.n_rev_rows) return false;
+        const int rc = a.rcount[j_loc];
+        const int32_t *ri = a.ridx + (size_t) j_loc * a.k;
         bool hit = false;
         for (int m = 0; m < rc; ++m) {
             if ((long long) ri[m] == i_glob) {
-                d = a.rdist[(size_t) j * a.k + m];
+                d = a.rdist[(size_t) j_loc * a.k + m];
                 hit = true;
                 break;
             }
@@ -72,7 +74,7 @@ __device__ __forceinline__ bool eval_elem(const FilterArgs &a, size_t e, b200m_c
     }
     float thr = a.distance_thr;
     if (a.thr_src && a.thr_tgt) {
-        float t = fmaxf(a.thr_src[i_glob], a.thr_tgt[j]);
+        float t = fmaxf(a.thr_src[i_loc], j_loc >= 0 ? a.thr_tgt[j_loc] : a.distance_thr);
         thr = fminf(t, a.distance_thr);
     }
     c.index_query = (int32_t) i_glob;
@@ -236,7 +238,7 @@ size_t filter_scan_ws_bytes(size_t n_rows, int k) {
 cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, size_t row_begin, size_t n_rows,
                           const int32_t *fidx, const float *fdist, const int32_t *fcount,
                           const int32_t *ridx, const float *rdist, const int32_t *rcount, size_t n_rev_rows,
-                          const float *thr_src, const float *thr_tgt, int64_t src_offset,
+                          const float *thr_src, const float *thr_tgt, int64_t src_offset, int64_t tgt_offset,
                           b200m_corr *out, size_t cap, unsigned long long *n_out, float *avg,
                           void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches, const float *cdist) {
     FilterArgs a;
@@ -247,7 +249,7 @@ cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, 
     a.row_begin = row_begin; a.n_rows = n_rows; a.n_rev_rows = n_rev_rows;
     a.fidx = fidx; a.fdist = fdist; a.fcount = fcount;
     a.ridx = ridx; a.rdist = rdist; a.rcount = rcount;
-    a.thr_src = thr_src; a.thr_tgt = thr_tgt; a.src_offset = src_offset;
+    a.thr_src = thr_src; a.thr_tgt = thr_tgt; a.src_offset = src_offset; a.tgt_offset = tgt_offset;
     size_t n_elems = n_rows * (size_t) a.kk;
     size_t nb = n_filter_blocks(n_rows, a.kk);
     if (filter_scan_ws_bytes(n_rows, k) > scan_ws_bytes) return cudaErrorInvalidValue;

@@ -74,7 +74,7 @@ struct b200m_ctx {
                                      // costs more than it saves)
     int tc_splits = 0;     // B200M_TC_SPLITS: 0 = chosen per launch (wave balance); > 0 forces the number of train splits
     int tc_splitn = 1;     // split-N candidate kernel for one-atom descriptors (B200M_TC_SPLITN=0: one N = 256 MMA per tile)
-    int tc_alt = 1;        // alternating-tile epilogue of the split-N kernel (B200M_TC_ALT=0: every epilogue warp on every tile)
+    int tc_alt = 2;        // B200M_TC_ALT: epilogue layout of the split-N kernel (2 quarter columns, 1 alternating tiles, 0 eight warps)
     int tc_lean = 1;       // B200M_TC_LEAN=0: general MMA issue loop also for one-atom descriptors (comparison)
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
     int tc_pair = 1;       // 1 = CTA-pair (cta_group::2) candidate kernel; 0 = cta_group::1 + multicast (B200M_TC_MODE=mcast)
@@ -151,7 +151,7 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
 cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, size_t row_begin, size_t n_rows,
                           const int32_t *fidx, const float *fdist, const int32_t *fcount,
                           const int32_t *ridx, const float *rdist, const int32_t *rcount, size_t n_rev_rows,
-                          const float *thr_src, const float *thr_tgt, int64_t src_offset,
+                          const float *thr_src, const float *thr_tgt, int64_t src_offset, int64_t tgt_offset,
                           b200m_corr *out, size_t cap, unsigned long long *n_out, float *avg,
                           void *scan_ws, size_t scan_ws_bytes, cudaStream_t st, int *n_launches,
                           const float *cdist = nullptr /* B200M_MODE_CLUSTER: [n_rows][k] from cluster.cu */);

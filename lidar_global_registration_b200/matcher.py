@@ -44,6 +44,11 @@ class _Params(C.Structure):
                 ("precision", C.c_int32), ("cand_cap", C.c_int32)]
 
 
+class _Scale(C.Structure):
+    _fields_ = [("src_desc", C.c_void_p), ("n_src", C.c_size_t), ("src_map", C.c_void_p),
+                ("tgt_desc", C.c_void_p), ("n_tgt", C.c_size_t), ("tgt_map", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("ms_pack", C.c_double), ("ms_prepare", C.c_double), ("ms_candidates", C.c_double),
                 ("ms_rerank", C.c_double), ("ms_fallback", C.c_double), ("ms_filter", C.c_double),
@@ -60,7 +65,8 @@ EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_strea
            "b200m_knn", "b200m_knn_device", "b200m_match", "b200m_filter_device", "b200m_merge_device",
            "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile", "b200m_multiscale_begin",
            "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device", "b200m_match_cluster",
-           "b200m_cluster_filter_device", "b200m_knn3d_device", "b200m_knn_local", "b200m_knn_local_device", "b200m_mark_referenced_device", "b200m_knn_masked_device"]
+           "b200m_cluster_filter_device", "b200m_knn3d_device", "b200m_knn_local", "b200m_knn_local_device", "b200m_mark_referenced_device", "b200m_knn_masked_device",
+           "b200m_match_multiscale"]
 
 _lib = None
 
@@ -106,6 +112,8 @@ def load_library():
     L.b200m_knn_masked_device.argtypes = [vp, C.POINTER(_Params), C.c_int, sz, sz, vp, vp, vp, vp]
     L.b200m_knn_local.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
     L.b200m_knn_local_device.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
+    L.b200m_match_multiscale.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Scale), C.c_int, sz, C.c_int, fp, sz, fp, sz, sz,
+                                         C.c_float, C.c_float, C.c_int, fp, fp, vp, sz, C.POINTER(sz), C.POINTER(C.c_float)]
     L.b200m_version.restype = C.c_int
     L.b200m_debug_operands.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, C.POINTER(C.c_float), C.POINTER(i32),
                                        C.POINTER(i64)]
@@ -312,6 +320,52 @@ class Context:
                                              out.ctypes.data, out.shape[0], C.byref(n_out), C.byref(avg)))
         return out[:n_out.value], float(avg.value)
 
+    # -- the matcher classes at the wide seam (match_impl: match_multiscale both ways + filter) ----
+    def match_wide(self, k, mode, src_scales, tgt_scales, src_kps_xyz, tgt_kps_xyz, iss_radius_src, iss_radius_tgt, dim=None,
+                   cluster_k=MATCHING_CLUSTER_K, distance_thr=FLT_MAX, thr_src=None, thr_tgt=None, precision=PREC_TC_F16,
+                   cand_cap=0):
+        """OneSided / LeftToRight / ClusterMatcher::match_impl (include/matching.h:395-411, :428-453, :492-517) over
+        precomputed per-scale descriptors: `src_scales` / `tgt_scales` are lists, one entry per common scale, of
+        (features [n_s, >= dim] float32, kps_indices_multiscale [n_s] int32 or None).  Returns (correspondences over
+        keypoint ids, average first-NN distance of the voted forward lists)."""
+        if len(src_scales) != len(tgt_scales) or not src_scales:
+            raise B200MatchError("match_wide: need the same, non-zero number of scales on both sides")
+        sx = np.ascontiguousarray(src_kps_xyz, np.float32)
+        tx = np.ascontiguousarray(tgt_kps_xyz, np.float32)
+        if sx.ndim != 2 or tx.ndim != 2 or sx.shape[1] < 3 or sx.shape[1] != tx.shape[1]:
+            raise B200MatchError("keypoint coordinates must be [n, >= 3] float32 with the same row length on both sides")
+        keep, arr = [], (_Scale * len(src_scales))()
+        width = None
+        for s, ((sf, smap), (tf, tmap)) in enumerate(zip(src_scales, tgt_scales)):
+            sf = np.ascontiguousarray(sf, np.float32)
+            tf = np.ascontiguousarray(tf, np.float32)
+            if sf.ndim != 2 or tf.ndim != 2 or sf.shape[1] != tf.shape[1] or (width is not None and sf.shape[1] != width):
+                raise B200MatchError("match_wide: every scale's descriptor rows must have the same length on both sides")
+            width = sf.shape[1]
+            sm = None if smap is None else np.ascontiguousarray(smap, np.int32)
+            tm = None if tmap is None else np.ascontiguousarray(tmap, np.int32)
+            if (sm is not None and sm.shape[0] != sf.shape[0]) or (tm is not None and tm.shape[0] != tf.shape[0]):
+                raise B200MatchError("match_wide: index map length != number of descriptor rows of the scale")
+            keep += [sf, tf, sm, tm]
+            arr[s] = _Scale(sf.ctypes.data, sf.shape[0], None if sm is None else sm.ctypes.data,
+                            tf.ctypes.data, tf.shape[0], None if tm is None else tm.ctypes.data)
+        d = int(dim or width)
+        if d > width:
+            raise B200MatchError("dim exceeds the row length")
+        ts = None if thr_src is None else np.ascontiguousarray(thr_src, np.float32)
+        tt = None if thr_tgt is None else np.ascontiguousarray(thr_tgt, np.float32)
+        if (ts is not None and ts.shape[0] != sx.shape[0]) or (tt is not None and tt.shape[0] != tx.shape[0]):
+            raise B200MatchError("threshold arrays must have one entry per keypoint")
+        out = np.empty(max(sx.shape[0], 1), CORR_DTYPE)
+        p = self._params(k, mode, distance_thr=distance_thr, precision=precision, cand_cap=cand_cap)
+        n_out, avg = C.c_size_t(0), C.c_float(0)
+        self._ck(self._L.b200m_match_multiscale(
+            self._h, C.byref(p), arr, len(src_scales), width * 4, d, sx.ctypes.data, sx.shape[0], tx.ctypes.data, tx.shape[0],
+            sx.strides[0] if sx.shape[0] > 1 else 4 * sx.shape[1], float(iss_radius_src), float(iss_radius_tgt), int(cluster_k),
+            None if ts is None else ts.ctypes.data, None if tt is None else tt.ctypes.data, out.ctypes.data, out.shape[0],
+            C.byref(n_out), C.byref(avg)))
+        return out[:n_out.value], float(avg.value)
+
     # -- multi-scale merge + spatial vote (match_multiscale, include/matching.h:264-354) ----
     def multiscale_begin(self, n_query_kps, n_scales, k):
         self._ms = (int(n_query_kps), int(k))
@@ -425,18 +479,35 @@ def match_multiscale(query_scales, train_scales, n_query_kps, train_kps_xyz, iss
 
 # ---- the reference's matcher classes --------------------------------------------------------
 class FeatureBasedMatcher:
-    """FeatureBasedMatcher (include/matching.h:25-42) at the descriptor seam: constructed over two
-    descriptor sets (the reference's `initialize` -- feature extraction -- is out of scope)."""
+    """FeatureBasedMatcherImpl<FeatureT> (include/matching.h:96-161) at the descriptor seam: constructed over the two
+    clouds' per-scale keypoint descriptors (the reference's `initialize` -- downsampling, normals, feature extraction --
+    is out of scope).  match() = match_impl + finalize, and match_impl is composed as in the reference: match_multiscale
+    (per-scale kNN with k = randomness, spatial vote -> at most one match per keypoint) in one or both directions, then
+    the matcher's filter over the VOTED lists.
+
+    src_features / tgt_features: one float32 array [n, >= dim] (a single scale) or a list of them (kps_features_multiscale,
+    ascending scale); kps_indices_multiscale_src/tgt: the per-scale row -> keypoint id maps (None = identity);
+    kps_xyz_src/tgt + iss_radius_src/tgt: keypoint coordinates and Storage::iss_radius, needed by the vote whenever a
+    keypoint can have more than one candidate (randomness * scales > 1) and by the cluster filter;
+    kps_indices_src/tgt: keypoint id -> cloud index (finalize)."""
     mode = None
     name = "FeatureBasedMatcher"
 
     def __init__(self, src_features, tgt_features, parameters, dim=None, thresholds_src=None, thresholds_tgt=None,
-                 kps_indices_src=None, kps_indices_tgt=None, device=0):
+                 kps_indices_src=None, kps_indices_tgt=None, device=0, kps_xyz_src=None, kps_xyz_tgt=None,
+                 iss_radius_src=None, iss_radius_tgt=None, kps_indices_multiscale_src=None, kps_indices_multiscale_tgt=None):
         self.parameters = parameters
-        self.src, self.tgt = src_features, tgt_features
-        self.dim = dim or np.asarray(src_features).shape[1]
+        self.src = list(src_features) if isinstance(src_features, (list, tuple)) else [src_features]
+        self.tgt = list(tgt_features) if isinstance(tgt_features, (list, tuple)) else [tgt_features]
+        if len(self.src) != len(self.tgt) or not self.src:
+            raise B200MatchError("the two clouds need the same, non-zero number of scales")
+        self.dim = dim or np.asarray(self.src[0]).shape[1]
         self.thr_src, self.thr_tgt = thresholds_src, thresholds_tgt
         self.kps_src, self.kps_tgt = kps_indices_src, kps_indices_tgt
+        self.xyz_src, self.xyz_tgt = kps_xyz_src, kps_xyz_tgt
+        self.iss_src, self.iss_tgt = iss_radius_src, iss_radius_tgt
+        self.maps_src = kps_indices_multiscale_src or [None] * len(self.src)
+        self.maps_tgt = kps_indices_multiscale_tgt or [None] * len(self.tgt)
         self.device = device
         self.average_distance_ = FLT_MAX      # include/matching.h:41
 
@@ -449,14 +520,28 @@ class FeatureBasedMatcher:
     def _k(self):
         return self.parameters.randomness
 
+    def _vote_is_identity(self):
+        # one candidate per keypoint: the vote keeps it (its own term of the count is 1), include/matching.h:327-352
+        return len(self.src) == 1 and self._k() == 1 and self.maps_src[0] is None and self.maps_tgt[0] is None
+
+    def _match_impl(self, ctx):
+        p = self.parameters
+        if self.xyz_src is None or self.xyz_tgt is None or self.iss_src is None or self.iss_tgt is None:
+            if not self._vote_is_identity() or self.mode == MODE_CLUSTER:
+                raise B200MatchError(
+                    "%s: randomness * scales > 1 (or the cluster filter) needs kps_xyz_src/tgt and iss_radius_src/tgt -- "
+                    "match_multiscale's spatial vote keeps one match per keypoint (reference include/matching.h:327-352)" % self.name)
+            ctx.upload(0, self.src[0], self.dim)
+            ctx.upload(1, self.tgt[0], self.dim)
+            return ctx.match(1, self.mode, p.ratio_thr, p.distance_thr, self.thr_src, self.thr_tgt, p.precision, p.cand_cap)
+        return ctx.match_wide(self._k(), self.mode, list(zip(self.src, self.maps_src)), list(zip(self.tgt, self.maps_tgt)),
+                              self.xyz_src, self.xyz_tgt, self.iss_src, self.iss_tgt, self.dim, p.cluster_k, p.distance_thr,
+                              self.thr_src, self.thr_tgt, p.precision, p.cand_cap)
+
     def match(self):
         """match() (include/matching.h:148-161): match_impl + finalize (:356-362)."""
-        p = self.parameters
         with Context(self.device) as ctx:
-            ctx.upload(0, self.src, self.dim)
-            ctx.upload(1, self.tgt, self.dim)
-            corrs, avg = ctx.match(self._k(), self.mode, p.ratio_thr, p.distance_thr, self.thr_src, self.thr_tgt,
-                                   p.precision, p.cand_cap)
+            corrs, avg = self._match_impl(ctx)
         corrs = corrs.copy()
         self.average_distance_ = avg
         if self.kps_src is not None:
@@ -467,46 +552,45 @@ class FeatureBasedMatcher:
 
 
 class OneSidedMatcher(FeatureBasedMatcher):
+    """include/matching.h:385-416"""
     mode, name = MODE_ONE_SIDED, "OneSidedMatcher"
 
 
 class LeftToRightMatcher(FeatureBasedMatcher):
+    """include/matching.h:418-458"""
     mode, name = MODE_MUTUAL, "LeftToRightMatcher"
 
 
 class ClusterMatcher(FeatureBasedMatcher):
-    """ClusterMatcher (include/matching.h:480-551), the reference's default matching_id: needs the keypoint
-    coordinates of both sides (st_src_.kps / st_tgt_.kps) next to the descriptors."""
+    """ClusterMatcher (include/matching.h:480-551), the reference's default matching_id: always needs the keypoint
+    coordinates of both sides (st_src_.kps / st_tgt_.kps); iss radii default to 1 when the vote is the identity."""
     mode, name = MODE_CLUSTER, "ClusterMatcher"
 
-    def __init__(self, src_features, tgt_features, parameters, kps_xyz_src=None, kps_xyz_tgt=None, **kw):
+    def __init__(self, src_features, tgt_features, parameters, **kw):
         super().__init__(src_features, tgt_features, parameters, **kw)
-        if kps_xyz_src is None or kps_xyz_tgt is None:
+        if self.xyz_src is None or self.xyz_tgt is None:
             raise B200MatchError("ClusterMatcher needs kps_xyz_src and kps_xyz_tgt (keypoint coordinates of both sides)")
-        self.xyz_src, self.xyz_tgt = kps_xyz_src, kps_xyz_tgt
-
-    def match(self):
-        p = self.parameters
-        with Context(self.device) as ctx:
-            ctx.upload(0, self.src, self.dim)
-            ctx.upload(1, self.tgt, self.dim)
-            corrs, avg = ctx.match_cluster(self._k(), p.cluster_k, self.xyz_src, self.xyz_tgt, p.distance_thr, self.thr_src,
-                                           self.thr_tgt, p.precision)
-        corrs = corrs.copy()
-        self.average_distance_ = avg
-        if self.kps_src is not None:
-            corrs["index_query"] = np.asarray(self.kps_src, np.int32)[corrs["index_query"]]
-        if self.kps_tgt is not None:
-            corrs["index_match"] = np.asarray(self.kps_tgt, np.int32)[corrs["index_match"]]
-        return corrs
+        if self.iss_src is None or self.iss_tgt is None:
+            if not self._vote_is_identity():
+                raise B200MatchError("ClusterMatcher: randomness * scales > 1 needs iss_radius_src/tgt for the spatial vote")
+            self.iss_src = self.iss_tgt = 1.0
 
 
 class RatioMatcher(FeatureBasedMatcher):
-    """A stub in the reference (include/matching.h:470-473); semantics defined in DESIGN.md."""
+    """A stub in the reference (include/matching.h:470-473: match_impl returns {}); semantics defined in DESIGN.md on the
+    raw k-lists of a single scale (parity unpinned -- there is no reference behaviour)."""
     mode, name = MODE_RATIO, "RatioMatcher"
 
     def _k(self):
         return max(self.parameters.ratio_k, 2)
+
+    def _match_impl(self, ctx):
+        p = self.parameters
+        if len(self.src) != 1:
+            raise B200MatchError("RatioMatcher is defined on a single scale")
+        ctx.upload(0, self.src[0], self.dim)
+        ctx.upload(1, self.tgt[0], self.dim)
+        return ctx.match(self._k(), self.mode, p.ratio_thr, p.distance_thr, self.thr_src, self.thr_tgt, p.precision, p.cand_cap)
 
 
 def get_feature_based_matcher_from_parameters(src_features, tgt_features, parameters, **kw):

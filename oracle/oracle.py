@@ -282,6 +282,60 @@ def finalize(corrs, kps_src, kps_tgt):
     return out
 
 
+def match_multiscale(query_scales, train_scales, n_query_kps, train_xyz, iss_radius, k):
+    """FeatureBasedMatcherImpl::match_multiscale (include/matching.h:264-354): per scale an exact kNN (k = randomness) over
+    that scale's descriptor rows, row numbers renamed to keypoint ids through kps_indices_multiscale (:313-321), candidates
+    concatenated per query keypoint in scale order, then the spatial vote (:327-352).  `*_scales`: lists of
+    (descriptors [n_s, dim], row -> keypoint id map [n_s] or None).  Returns one-entry lists (idx [n,1], dist [n,1], count [n])."""
+    comb_i = [[] for _ in range(n_query_kps)]
+    comb_d = [[] for _ in range(n_query_kps)]
+    for (qf, qmap), (tf, tmap) in zip(query_scales, train_scales):
+        if qf.shape[0] == 0:
+            continue
+        ei, ed, ec = knn(qf, tf, k)
+        for r in range(qf.shape[0]):
+            kp = r if qmap is None else int(qmap[r])
+            for m in range(ec[r]):
+                j = int(ei[r, m])
+                comb_i[kp].append(j if tmap is None else int(tmap[j]))
+                comb_d[kp].append(ed[r, m])
+    width = max(max((len(c) for c in comb_i), default=0), 1)
+    ci = np.full((n_query_kps, width), -1, np.int32)
+    cd = np.zeros((n_query_kps, width), np.float32)
+    cc = np.zeros(n_query_kps, np.int32)
+    for i in range(n_query_kps):
+        cc[i] = len(comb_i[i])
+        ci[i, :cc[i]] = comb_i[i]
+        cd[i, :cc[i]] = comb_d[i]
+    xyz = np.ascontiguousarray(np.asarray(train_xyz, np.float32)[:, :3])
+    if xyz.shape[0] == 0:
+        return ci[:, :1].copy(), cd[:, :1].copy(), np.zeros(n_query_kps, np.int32)
+    vi, vd, vc = spatial_vote(ci, cd, cc, xyz, iss_radius)
+    return np.ascontiguousarray(vi[:, :1]), np.ascontiguousarray(vd[:, :1]), vc
+
+
+def match_wide(mode, src_scales, tgt_scales, src_xyz, tgt_xyz, iss_radius_src, iss_radius_tgt, k, cluster_k=40,
+               distance_thr=np.float32(3.4e38), thr_q=None, thr_t=None):
+    """match_impl of OneSidedMatcher / LeftToRightMatcher / ClusterMatcher (include/matching.h:395-411, :428-453, :492-517)
+    as the reference composes it: match_multiscale both ways (the reverse call is the reference's inverse_tn one), the
+    average over the voted forward lists (printDebugInfo), then the matcher's loop over the voted lists.
+    mode in {'one_sided', 'mutual', 'cluster'}.  Returns (corrs, avg_first_distance)."""
+    n_s, n_t = np.asarray(src_xyz).shape[0], np.asarray(tgt_xyz).shape[0]
+    fi, fd, fc = match_multiscale(src_scales, tgt_scales, n_s, tgt_xyz, iss_radius_tgt, k)
+    avg = average_distance(fd, fc)
+    if mode == "one_sided":
+        return filter_one_sided(fi, fd, fc, distance_thr, thr_q, thr_t), avg
+    ri, rd, rc = match_multiscale(tgt_scales, src_scales, n_t, src_xyz, iss_radius_src, k)
+    if mode == "mutual":
+        return filter_mutual(fi, fc, ri, rd, rc, distance_thr, thr_q, thr_t), avg
+    if mode == "cluster":
+        if n_s == 0 or n_t == 0:
+            return np.empty(0, CORR_DTYPE), avg
+        return filter_cluster(fi, fc, ri, rc, knn3d(src_xyz, cluster_k), knn3d(tgt_xyz, cluster_k), distance_thr,
+                              thr_q=thr_q, thr_t=thr_t), avg
+    raise ValueError(mode)
+
+
 def match(query, train, k, mode, ratio_thr=1.1, distance_thr=np.float32(3.4e38), thr_q=None, thr_t=None):
     """Whole matcher call at the k-list seam: mode in {'one_sided','mutual','ratio'}.
     Returns (corrs, avg_first_distance)."""

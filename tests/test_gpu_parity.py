@@ -242,12 +242,17 @@ def test_reference_style_interface(golden_dir):
     rng = np.random.default_rng(1)
     ks = rng.permutation(10 * src.shape[0])[:src.shape[0]].astype(np.int32)
     kt = rng.permutation(10 * tgt.shape[0])[:tgt.shape[0]].astype(np.int32)
-    m = M.get_feature_based_matcher_from_parameters(src, tgt, params, dim=dim, kps_indices_src=ks, kps_indices_tgt=kt)
+    # randomness = 1, one scale: match_multiscale's vote is the identity, no keypoint coordinates needed
+    p1 = M.AlignmentParameters(randomness=1, matching_id=M.MATCHING_LEFT_TO_RIGHT)
+    m = M.get_feature_based_matcher_from_parameters(src, tgt, p1, dim=dim, kps_indices_src=ks, kps_indices_tgt=kt)
     assert m.get_class_name() == "LeftToRightMatcher" and m.get_average_distance() == M.FLT_MAX
     corrs = m.match()
-    exp, eavg = orc.match(_dense(src, dim), _dense(tgt, dim), k, "mutual", distance_thr=np.float32(M.FLT_MAX))
+    exp, eavg = orc.match(_dense(src, dim), _dense(tgt, dim), 1, "mutual", distance_thr=np.float32(M.FLT_MAX))
     exp = orc.finalize(exp, ks, kt)
     assert corrs.tobytes() == exp.tobytes() and m.get_average_distance() == eavg
+    # randomness > 1 feeds the spatial vote (include/matching.h:327-352): the classes refuse to run without coordinates
+    with pytest.raises(M.B200MatchError):
+        M.get_feature_based_matcher_from_parameters(src, tgt, params, dim=dim).match()
     with pytest.raises(M.B200MatchError):
         M.get_feature_based_matcher_from_parameters(src, tgt, M.AlignmentParameters(matching_id="cluster"))
 
@@ -398,6 +403,53 @@ def test_match_multiscale_vote_equals_oracle(desc, k, n_scales):
         assert np.any(gi != first)
 
 
+@pytest.mark.parametrize("masked", [False, True], ids=["full-reverse", "masked-reverse"])
+@pytest.mark.parametrize("mode", ["one_sided", "mutual", "cluster"])
+@pytest.mark.parametrize("desc,k,n_scales", [("fpfh", 1, 1), ("fpfh", 2, 1), ("shot", 2, 2), ("rops", 3, 3), ("fpfh", 5, 2)])
+def test_matcher_classes_at_the_wide_seam_equal_oracle(monkeypatch, desc, k, n_scales, mode, masked):
+    """match_impl of OneSided / LeftToRight / ClusterMatcher as the reference composes it (include/matching.h:395-411,
+    :428-453, :492-517): match_multiscale in BOTH directions (the reverse one is the reference's inverse_tn call) -- per-scale
+    kNN, remap, concatenation, spatial vote -- the average over the voted forward lists, then the filter loop over the voted
+    lists; records and average == the oracle composed the same way, byte for byte."""
+    monkeypatch.setenv("B200M_MASKED_MIN_PAIRS", "1" if masked else "1e30")
+    rng = np.random.default_rng(31 + 7 * k + n_scales)
+    n_sk, n_tk = 800, 950
+    sx = np.zeros((n_sk, 4), np.float32)
+    tx = np.zeros((n_tk, 4), np.float32)
+    sx[:, :3] = rng.random((n_sk, 3)) * 4
+    tx[:, :3] = rng.random((n_tk, 3)) * 4
+    tx[: n_tk // 4, :3] = tx[0, :3] + 0.02 * rng.standard_normal((n_tk // 4, 3)).astype(np.float32)   # tight clusters:
+    sx[: n_sk // 4, :3] = sx[0, :3] + 0.02 * rng.standard_normal((n_sk // 4, 3)).astype(np.float32)   # the vote matters
+    iss_s, iss_t = np.float32(0.06), np.float32(0.05)
+    s_sc, t_sc, dim = [], [], None
+    for s in range(n_scales):
+        smap = None if (s == 0 and n_scales == 1 and k == 1) else np.sort(rng.choice(n_sk, n_sk - 50 * s, replace=False)).astype(np.int32)
+        tmap = None if (s == 0 and n_scales == 1 and k == 1) else np.sort(rng.choice(n_tk, n_tk - 40 * s, replace=False)).astype(np.int32)
+        src, tgt, dim = synth.make_pair(desc, n_sk if smap is None else smap.shape[0], n_tk if tmap is None else tmap.shape[0],
+                                        seed=200 + s, nan_frac=0.01)
+        s_sc.append((np.ascontiguousarray(_dense(src, dim)), smap))
+        t_sc.append((np.ascontiguousarray(_dense(tgt, dim)), tmap))
+    thr_s, thr_t = rng.random(n_sk).astype(np.float32), rng.random(n_tk).astype(np.float32)
+    dthr = np.float32(0.7)
+    exp, eavg = orc.match_wide(mode, s_sc, t_sc, sx[:, :3], tx[:, :3], iss_s, iss_t, k, 40, dthr, thr_s, thr_t)
+    gmode = {"one_sided": M.MODE_ONE_SIDED, "mutual": M.MODE_MUTUAL, "cluster": M.MODE_CLUSTER}[mode]
+    with M.Context(0) as ctx:
+        got, avg = ctx.match_wide(k, gmode, s_sc, t_sc, sx, tx, iss_s, iss_t, dim, 40, dthr, thr_s, thr_t)
+    assert len(exp) > 0 and got.tobytes() == exp.tobytes() and avg == eavg
+    assert np.all(np.diff(got["index_query"]) > 0)       # at most one correspondence per source keypoint, ascending
+    # the reference-shaped classes, finalize included
+    ks = rng.permutation(5 * n_sk)[:n_sk].astype(np.int32)
+    kt = rng.permutation(5 * n_tk)[:n_tk].astype(np.int32)
+    params = M.AlignmentParameters(randomness=k, distance_thr=float(dthr), cluster_k=40,
+                                   matching_id={"one_sided": M.MATCHING_ONE_SIDED, "mutual": M.MATCHING_LEFT_TO_RIGHT,
+                                                "cluster": M.MATCHING_CLUSTER}[mode])
+    m = M.get_feature_based_matcher_from_parameters(
+        [a for a, _ in s_sc], [a for a, _ in t_sc], params, dim=dim, thresholds_src=thr_s, thresholds_tgt=thr_t,
+        kps_indices_src=ks, kps_indices_tgt=kt, kps_xyz_src=sx, kps_xyz_tgt=tx, iss_radius_src=iss_s, iss_radius_tgt=iss_t,
+        kps_indices_multiscale_src=[m_ for _, m_ in s_sc], kps_indices_multiscale_tgt=[m_ for _, m_ in t_sc])
+    assert m.match().tobytes() == orc.finalize(exp, ks, kt).tobytes() and m.get_average_distance() == eavg
+
+
 @pytest.mark.parametrize("desc,nq,nt,k,ck", [("fpfh", 1500, 1700, 1, 40), ("shot", 600, 500, 2, 40), ("rops", 400, 450, 3, 10),
                                              ("fpfh", 30, 25, 1, 40)])
 def test_cluster_matcher_equals_oracle(desc, nq, nt, k, ck):
@@ -431,11 +483,17 @@ def test_cluster_matcher_equals_oracle(desc, nq, nt, k, ck):
         assert len(exp) < fcnt.sum()          # the filter keeps some pairs and rejects some
     assert got.tobytes() == exp.tobytes()
     assert avg == orc.average_distance(fdist, fcnt)
-    # the reference-shaped class
+    # the reference-shaped class goes through match_multiscale's vote first (at most one match per keypoint)
     params = M.AlignmentParameters(randomness=k, matching_id=M.MATCHING_CLUSTER, cluster_k=ck, distance_thr=float(dthr))
     m = M.get_feature_based_matcher_from_parameters(src, tgt, params, dim=dim, kps_xyz_src=sx, kps_xyz_tgt=tx,
-                                                    thresholds_src=thr_s, thresholds_tgt=thr_t)
-    assert m.get_class_name() == "ClusterMatcher" and m.match().tobytes() == exp.tobytes()
+                                                    thresholds_src=thr_s, thresholds_tgt=thr_t, iss_radius_src=0.3,
+                                                    iss_radius_tgt=0.25)
+    exp_w, avg_w = orc.match_wide("cluster", [(_dense(src, dim), None)], [(_dense(tgt, dim), None)], sx[:, :3], tx[:, :3],
+                                  np.float32(0.3), np.float32(0.25), k, ck, dthr, thr_s, thr_t)
+    assert m.get_class_name() == "ClusterMatcher" and m.match().tobytes() == exp_w.tobytes()
+    assert m.get_average_distance() == avg_w
+    if k == 1:
+        assert exp_w.tobytes() == exp.tobytes()      # one candidate per keypoint: the vote is the identity
 
 
 @pytest.mark.parametrize("desc,nq,nt,k,radius", [("fpfh", 900, 1200, 2, 1.5), ("shot", 300, 500, 5, 3.0), ("rops", 250, 300, 1, 0.4),
