@@ -5,8 +5,13 @@
 //                                  reference include/matching.h:368-383, :562-678
 //   MultivaluedCorrespondence      reference include/common.h:192-195
 //   Correspondence                 reference include/common.h:120-127
-//   FeatureBasedMatcher, OneSidedMatcher / LeftToRightMatcher / RatioMatcher  (match(), getAverageDistance(),
-//   getClassName())                reference include/matching.h:25-42, :385-478
+//   FeatureBasedMatcher, FeatureBasedMatcherImpl<FeatureT>::Storage, OneSidedMatcher / LeftToRightMatcher /
+//   RatioMatcher / ClusterMatcher  (match(), getAverageDistance(), getClassName())
+//                                  reference include/matching.h:25-42, :96-161, :385-551
+// The matcher classes run match_impl as the reference composes it -- match_multiscale (per-scale kNN, spatial vote ->
+// at most one match per keypoint) in one or both directions, then the filter over the voted lists -- in ONE library
+// call (b200m_match_multiscale); the narrow-seam functions share one context per host thread and device, so calling
+// them per scale and per direction does not pay for streams and device allocations again.
 //
 // With -DB200MATCH_WITH_PCL the feature types are PCL's (pcl::FPFHSignature33, pcl::SHOT352,
 // pcl::Histogram<135>) and clouds are pcl::PointCloud<FeatureT>::ConstPtr exactly as in the reference; without
@@ -14,7 +19,10 @@
 // is a std::vector<FeatureT>.  Errors surface as std::runtime_error -- the convention of the reference's
 // rassert (include/utils.h:9).  There is no CPU fallback anywhere below.
 #pragma once
+#include <algorithm>
+#include <array>
 #include <limits>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -75,8 +83,9 @@ struct AlignmentParameters {
     int cluster_k = 40;             // :146  MATCHING_CLUSTER_K (include/common.h:53)
     int randomness = 1;             // :147  k
     float distance_thr = std::numeric_limits<float>::max();   // :139
-    std::string matching_id = "lr"; // :149  one_sided | lr | ratio
+    std::string matching_id = "lr"; // :149  one_sided | lr | ratio | cluster
     float ratio_thr = 1.1f;         // MATCHING_RATIO_THRESHOLD, include/common.h:50
+    float match_search_radius = std::numeric_limits<float>::max();   // :160  matchLocal's 3-D gate
     int device = 0;
     int precision = B200M_PREC_TC_F16;
 };
@@ -104,6 +113,16 @@ private:
     b200m_ctx *ctx_ = nullptr;
 };
 
+// One context per host thread and device, created on first use and kept: the reference calls matchBF / matchFLANN /
+// matchLocal once per scale and direction (include/matching.h:297-311), and a context owns its stream and every device
+// buffer (grow-only), so only the first call pays for them.
+inline Context &shared_context(int device) {
+    thread_local std::map<int, std::unique_ptr<Context>> pool;
+    auto &slot = pool[device];
+    if (!slot) slot.reset(new Context(device));
+    return *slot;
+}
+
 inline b200m_params make_params(const AlignmentParameters &p, int mode, int k) {
     b200m_params q;
     q.k = k;
@@ -120,7 +139,7 @@ template <typename FeatureT>
 std::vector<MultivaluedCorrespondence> matchBF(const FeatureCloud<FeatureT> &query_features,
                                                const FeatureCloud<FeatureT> &train_features,
                                                const AlignmentParameters &parameters) {
-    Context ctx(parameters.device);
+    Context &ctx = shared_context(parameters.device);
     ctx.upload<FeatureT>(0, query_features);
     ctx.upload<FeatureT>(1, train_features);
     const size_t nq = cloud_size<FeatureT>(query_features);
@@ -147,12 +166,50 @@ std::vector<MultivaluedCorrespondence> matchFLANN(const FeatureCloud<FeatureT> &
 }
 
 // matchLocal<FeatureT> with match_search_radius = inf (reference include/matching.h:637-678 as called by
-// tests/flann_bf_matcher.h:66-72).  The spatially gated variant is a next-row item.
+// tests/flann_bf_matcher.h:66-72): plain brute force.
 template <typename FeatureT>
 std::vector<MultivaluedCorrespondence> matchLocal(const FeatureCloud<FeatureT> &query_features,
                                                   const FeatureCloud<FeatureT> &train_features,
                                                   const AlignmentParameters &parameters) {
     return matchBF<FeatureT>(query_features, train_features, parameters);
+}
+
+// matchLocal<FeatureT> as match_multiscale calls it when AlignmentParameters::guess is set (reference
+// include/matching.h:378-383, :637-678): the query keypoints are moved by `guess` (row-major 4x4, the reference's
+// Eigen::Matrix4f; pcl::transformPointCloudWithNormals, :644), and only train rows whose keypoint lies within
+// parameters.match_search_radius of the moved query keypoint compete (radiusSearch on the train keypoint tree, :659).
+// query_kps / train_kps: one keypoint per descriptor row, `kps_stride_bytes` apart (pcl::PointNormal rows: 48).
+// In a PCL build pass the cloud already transformed by PCL and the identity as `guess` to keep PCL's own arithmetic.
+template <typename FeatureT>
+std::vector<MultivaluedCorrespondence> matchLocal(const float *query_kps, const float *train_kps, size_t kps_stride_bytes,
+                                                  const FeatureCloud<FeatureT> &query_features,
+                                                  const FeatureCloud<FeatureT> &train_features,
+                                                  const AlignmentParameters &parameters, const std::array<float, 16> &guess) {
+    Context &ctx = shared_context(parameters.device);
+    ctx.upload<FeatureT>(0, query_features);
+    ctx.upload<FeatureT>(1, train_features);
+    const size_t nq = cloud_size<FeatureT>(query_features), fl = kps_stride_bytes / 4;
+    const int k = parameters.randomness;
+    std::vector<float> moved(nq * 3);
+    for (size_t i = 0; i < nq; ++i) {   // Eigen's affine product: x' = m00 x + m01 y + m02 z + m03 (float)
+        const float *q = query_kps + i * fl;
+        for (int r = 0; r < 3; ++r)
+            moved[3 * i + r] = guess[4 * r] * q[0] + guess[4 * r + 1] * q[1] + guess[4 * r + 2] * q[2] + guess[4 * r + 3];
+    }
+    std::vector<float> train_xyz(cloud_size<FeatureT>(train_features) * 3);
+    for (size_t j = 0; j < train_xyz.size() / 3; ++j)
+        for (int r = 0; r < 3; ++r) train_xyz[3 * j + r] = train_kps[j * fl + r];
+    std::vector<int32_t> idx(nq * k), cnt(nq);
+    std::vector<float> dist(nq * k);
+    b200m_params p = make_params(parameters, B200M_MODE_KNN_ONLY, k);
+    ctx.check(b200m_knn_local(ctx.get(), &p, 0, moved.data(), train_xyz.data(), 12, parameters.match_search_radius, idx.data(),
+                              dist.data(), cnt.data()));
+    std::vector<MultivaluedCorrespondence> out(nq);
+    for (size_t i = 0; i < nq; ++i) {
+        out[i].match_indices.assign(idx.begin() + i * k, idx.begin() + i * k + cnt[i]);
+        out[i].distances.assign(dist.begin() + i * k, dist.begin() + i * k + cnt[i]);
+    }
+    return out;
 }
 
 // match_multiscale (reference include/matching.h:264-354) over precomputed per-scale descriptors: one exact kNN per
@@ -174,7 +231,7 @@ std::vector<MultivaluedCorrespondence> match_multiscale(const std::vector<Featur
     const size_t n_scales = query_features.size();
     if (n_scales == 0 || train_features.size() != n_scales || query_indices.size() != n_scales || train_indices.size() != n_scales)
         throw std::runtime_error("match_multiscale: one descriptor cloud and one index map per scale and side are needed");
-    Context ctx(parameters.device);
+    Context &ctx = shared_context(parameters.device);
     const int k = parameters.randomness;
     ctx.check(b200m_multiscale_begin(ctx.get(), n_query_kps, (int) n_scales, k));
     b200m_params p = make_params(parameters, B200M_MODE_KNN_ONLY, k);
@@ -217,41 +274,108 @@ protected:
 template <typename FeatureT>
 class FeatureBasedMatcherImpl : public FeatureBasedMatcher {
 public:
-    // thresholds_*: calculateSmoothedDensities outputs (may be empty); kps_indices_*: keypoint-local -> cloud-global
-    // index maps applied by finalize (reference include/matching.h:356-362); may be empty.
-    FeatureBasedMatcherImpl(FeatureCloud<FeatureT> src, FeatureCloud<FeatureT> tgt, AlignmentParameters parameters,
-                            std::vector<float> thresholds_src = {}, std::vector<float> thresholds_tgt = {},
-                            std::vector<int> kps_indices_src = {}, std::vector<int> kps_indices_tgt = {})
-        : src_(std::move(src)), tgt_(std::move(tgt)), parameters_(std::move(parameters)),
-          thr_src_(std::move(thresholds_src)), thr_tgt_(std::move(thresholds_tgt)),
-          kps_src_(std::move(kps_indices_src)), kps_tgt_(std::move(kps_indices_tgt)) {}
+    // The fields of FeatureBasedMatcherImpl<FeatureT>::Storage (reference include/matching.h:114-127) that match_impl
+    // reads; `initialize` (downsampling, normals, feature estimation: :163-262) stays with the caller and fills them.
+    struct Storage {
+        const float *kps_xyz = nullptr;            // kps: keypoint coordinates, one row per keypoint
+        size_t n_kps = 0;                          // kps->size()
+        size_t kps_stride_bytes = 16;              // sizeof(PointN) (pcl::PointNormal: 48; pcl::PointXYZ: 16)
+        std::vector<int> kps_indices;              // keypoint id -> index in pcd (finalize, :356-362); empty = identity
+        std::vector<std::vector<int>> kps_indices_multiscale;          // [scale][row] -> keypoint id; empty = identity (one scale)
+        std::vector<FeatureCloud<FeatureT>> kps_features_multiscale;   // [scale] descriptors of that scale's keypoints
+        int min_log2_radius = 0, max_log2_radius = 0;                  // scales present: max - min + 1 entries above
+        float iss_radius = 1.f;
+        std::vector<float> thresholds;             // calculateSmoothedDensities(kps) (src/common.cpp:531-547); may be empty
+    };
 
+    // single-scale convenience: one descriptor per keypoint, identity maps
+    static Storage makeStorage(FeatureCloud<FeatureT> features, const float *kps_xyz = nullptr, size_t kps_stride_bytes = 16,
+                               float iss_radius = 1.f, std::vector<float> thresholds = {}, std::vector<int> kps_indices = {}) {
+        Storage st;
+        st.n_kps = cloud_size<FeatureT>(features);
+        st.kps_features_multiscale.push_back(std::move(features));
+        st.kps_xyz = kps_xyz;
+        st.kps_stride_bytes = kps_stride_bytes;
+        st.iss_radius = iss_radius;
+        st.thresholds = std::move(thresholds);
+        st.kps_indices = std::move(kps_indices);
+        return st;
+    }
+
+    FeatureBasedMatcherImpl(Storage src, Storage tgt, AlignmentParameters parameters)
+        : st_src_(std::move(src)), st_tgt_(std::move(tgt)), parameters_(std::move(parameters)) {}
+
+    // match() (reference include/matching.h:148-161): match_impl + finalize
     CorrespondencesPtr match() override {
-        Context ctx(parameters_.device);
-        ctx.upload<FeatureT>(0, src_);
-        ctx.upload<FeatureT>(1, tgt_);
-        const int k = mode() == B200M_MODE_RATIO ? (parameters_.ratio_k < 2 ? 2 : parameters_.ratio_k) : parameters_.randomness;
-        b200m_params p = make_params(parameters_, mode(), k);
-        const size_t nq = cloud_size<FeatureT>(src_);
-        auto out = std::make_shared<Correspondences>(nq * (mode() == B200M_MODE_MUTUAL ? k : 1));
-        size_t n = 0;
-        const bool thr = !thr_src_.empty() && !thr_tgt_.empty();
-        ctx.check(b200m_match(ctx.get(), &p, thr ? thr_src_.data() : nullptr, thr ? thr_tgt_.data() : nullptr,
-                              reinterpret_cast<b200m_corr *>(out->data()), out->size(), &n, &average_distance_));
-        out->resize(n);
-        for (auto &c : *out) {   // finalize
-            if (!kps_src_.empty()) c.index_query = kps_src_[c.index_query];
-            if (!kps_tgt_.empty()) c.index_match = kps_tgt_[c.index_match];
+        auto correspondences = match_impl();
+        for (auto &c : *correspondences) {   // finalize (:356-362)
+            if (!st_src_.kps_indices.empty()) c.index_query = st_src_.kps_indices[c.index_query];
+            if (!st_tgt_.kps_indices.empty()) c.index_match = st_tgt_.kps_indices[c.index_match];
         }
-        return out;
+        return correspondences;
     }
 
 protected:
     virtual int mode() const = 0;
-    FeatureCloud<FeatureT> src_, tgt_;
+
+    // match_impl of the three implemented matchers: both match_multiscale calls, the vote, printDebugInfo's average
+    // and the filter loop in one device-resident call
+    virtual CorrespondencesPtr match_impl() {
+        // the scales common to both clouds (reference :268-270)
+        const int lo = std::max(st_src_.min_log2_radius, st_tgt_.min_log2_radius);
+        const int hi = std::min(st_src_.max_log2_radius, st_tgt_.max_log2_radius);
+        if (hi < lo) throw std::runtime_error("the two clouds have no scale in common");
+        std::vector<b200m_scale> scales;
+        static_assert(sizeof(int) == sizeof(int32_t), "index maps are passed as int32");
+        for (int r = lo; r <= hi; ++r) {
+            const size_t is = (size_t) (r - st_src_.min_log2_radius), it = (size_t) (r - st_tgt_.min_log2_radius);
+            if (is >= st_src_.kps_features_multiscale.size() || it >= st_tgt_.kps_features_multiscale.size())
+                throw std::runtime_error("kps_features_multiscale has fewer entries than scales");
+            b200m_scale sc{};
+            sc.src_desc = reinterpret_cast<const float *>(cloud_data<FeatureT>(st_src_.kps_features_multiscale[is]));
+            sc.n_src = cloud_size<FeatureT>(st_src_.kps_features_multiscale[is]);
+            sc.tgt_desc = reinterpret_cast<const float *>(cloud_data<FeatureT>(st_tgt_.kps_features_multiscale[it]));
+            sc.n_tgt = cloud_size<FeatureT>(st_tgt_.kps_features_multiscale[it]);
+            if (is < st_src_.kps_indices_multiscale.size()) {
+                if (st_src_.kps_indices_multiscale[is].size() != sc.n_src) throw std::runtime_error("kps_indices_multiscale: length != descriptors of the scale");
+                sc.src_map = reinterpret_cast<const int32_t *>(st_src_.kps_indices_multiscale[is].data());
+            }
+            if (it < st_tgt_.kps_indices_multiscale.size()) {
+                if (st_tgt_.kps_indices_multiscale[it].size() != sc.n_tgt) throw std::runtime_error("kps_indices_multiscale: length != descriptors of the scale");
+                sc.tgt_map = reinterpret_cast<const int32_t *>(st_tgt_.kps_indices_multiscale[it].data());
+            }
+            scales.push_back(sc);
+        }
+        // one candidate per keypoint (randomness 1, one scale): the vote is the identity and needs no coordinates
+        std::vector<float> zeros;
+        const float *sx = st_src_.kps_xyz, *tx = st_tgt_.kps_xyz;
+        size_t stride = st_src_.kps_stride_bytes;
+        if (!sx || !tx) {
+            if (parameters_.randomness != 1 || scales.size() != 1 || mode() == B200M_MODE_CLUSTER)
+                throw std::runtime_error("randomness * scales > 1 (or the cluster filter) needs the keypoint coordinates of both clouds: "
+                                         "match_multiscale's spatial vote keeps one match per keypoint (include/matching.h:327-352)");
+            zeros.assign(4 * std::max(st_src_.n_kps, st_tgt_.n_kps) + 4, 0.f);
+            sx = tx = zeros.data();
+            stride = 16;
+        } else if (st_src_.kps_stride_bytes != st_tgt_.kps_stride_bytes) {
+            throw std::runtime_error("both keypoint clouds must have the same point stride");
+        }
+        const bool thr = !st_src_.thresholds.empty() && !st_tgt_.thresholds.empty();
+        b200m_params p = make_params(parameters_, mode(), parameters_.randomness);
+        auto out = std::make_shared<Correspondences>(st_src_.n_kps);
+        size_t n = 0;
+        Context &ctx = shared_context(parameters_.device);
+        ctx.check(b200m_match_multiscale(ctx.get(), &p, scales.data(), (int) scales.size(), sizeof(FeatureT), feature_dim<FeatureT>(),
+                                         sx, st_src_.n_kps, tx, st_tgt_.n_kps, stride, st_src_.iss_radius, st_tgt_.iss_radius,
+                                         parameters_.cluster_k, thr ? st_src_.thresholds.data() : nullptr,
+                                         thr ? st_tgt_.thresholds.data() : nullptr, reinterpret_cast<b200m_corr *>(out->data()),
+                                         out->size(), &n, &average_distance_));
+        out->resize(n);
+        return out;
+    }
+
+    Storage st_src_, st_tgt_;
     AlignmentParameters parameters_;
-    std::vector<float> thr_src_, thr_tgt_;
-    std::vector<int> kps_src_, kps_tgt_;
 };
 
 template <typename FeatureT>
@@ -272,66 +396,57 @@ protected:
     int mode() const override { return B200M_MODE_MUTUAL; }
 };
 
+// ClusterMatcher (reference include/matching.h:480-551, the default matching_id): both Storages need kps_xyz.
 template <typename FeatureT>
-class RatioMatcher : public FeatureBasedMatcherImpl<FeatureT> {   // reference include/matching.h:460-478 (stub there)
+class ClusterMatcher : public FeatureBasedMatcherImpl<FeatureT> {
+public:
+    using FeatureBasedMatcherImpl<FeatureT>::FeatureBasedMatcherImpl;
+    std::string getClassName() override { return "ClusterMatcher"; }
+protected:
+    int mode() const override { return B200M_MODE_CLUSTER; }
+};
+
+// RatioMatcher: a stub in the reference (include/matching.h:460-478, match_impl returns {}); defined here on the raw
+// k-lists of a single scale (parity unpinned: there is no reference behaviour).
+template <typename FeatureT>
+class RatioMatcher : public FeatureBasedMatcherImpl<FeatureT> {
 public:
     using FeatureBasedMatcherImpl<FeatureT>::FeatureBasedMatcherImpl;
     std::string getClassName() override { return "RatioMatcher"; }
 protected:
     int mode() const override { return B200M_MODE_RATIO; }
-};
-
-// ClusterMatcher (reference include/matching.h:480-551, the default matching_id): needs the keypoint coordinates of
-// both sides (st_src_.kps / st_tgt_.kps), one row per descriptor, `xyz_stride_bytes` apart (pcl::PointXYZ / PointN rows).
-template <typename FeatureT>
-class ClusterMatcher : public FeatureBasedMatcherImpl<FeatureT> {
-public:
-    ClusterMatcher(FeatureCloud<FeatureT> src, FeatureCloud<FeatureT> tgt, AlignmentParameters parameters,
-                   const float *src_kps_xyz, const float *tgt_kps_xyz, size_t xyz_stride_bytes,
-                   std::vector<float> thresholds_src = {}, std::vector<float> thresholds_tgt = {},
-                   std::vector<int> kps_indices_src = {}, std::vector<int> kps_indices_tgt = {})
-        : FeatureBasedMatcherImpl<FeatureT>(std::move(src), std::move(tgt), std::move(parameters), std::move(thresholds_src),
-                                            std::move(thresholds_tgt), std::move(kps_indices_src), std::move(kps_indices_tgt)),
-          sx_(src_kps_xyz), tx_(tgt_kps_xyz), stride_(xyz_stride_bytes) {}
-    std::string getClassName() override { return "ClusterMatcher"; }
-
-    CorrespondencesPtr match() override {
-        Context ctx(this->parameters_.device);
-        ctx.template upload<FeatureT>(0, this->src_);
-        ctx.template upload<FeatureT>(1, this->tgt_);
-        const int k = this->parameters_.randomness;
-        b200m_params p = make_params(this->parameters_, B200M_MODE_CLUSTER, k);
-        auto out = std::make_shared<Correspondences>(cloud_size<FeatureT>(this->src_) * k);
+    CorrespondencesPtr match_impl() override {
+        if (this->st_src_.kps_features_multiscale.size() != 1 || this->st_tgt_.kps_features_multiscale.size() != 1)
+            throw std::runtime_error("RatioMatcher is defined on a single scale");
+        Context &ctx = shared_context(this->parameters_.device);
+        ctx.template upload<FeatureT>(0, this->st_src_.kps_features_multiscale[0]);
+        ctx.template upload<FeatureT>(1, this->st_tgt_.kps_features_multiscale[0]);
+        const int k = this->parameters_.ratio_k < 2 ? 2 : this->parameters_.ratio_k;
+        b200m_params p = make_params(this->parameters_, B200M_MODE_RATIO, k);
+        auto out = std::make_shared<Correspondences>(this->st_src_.n_kps);
         size_t n = 0;
-        const bool thr = !this->thr_src_.empty() && !this->thr_tgt_.empty();
-        ctx.check(b200m_match_cluster(ctx.get(), &p, this->parameters_.cluster_k, sx_, tx_, stride_,
-                                      thr ? this->thr_src_.data() : nullptr, thr ? this->thr_tgt_.data() : nullptr,
-                                      reinterpret_cast<b200m_corr *>(out->data()), out->size(), &n, &this->average_distance_));
+        const bool thr = !this->st_src_.thresholds.empty() && !this->st_tgt_.thresholds.empty();
+        ctx.check(b200m_match(ctx.get(), &p, thr ? this->st_src_.thresholds.data() : nullptr,
+                              thr ? this->st_tgt_.thresholds.data() : nullptr, reinterpret_cast<b200m_corr *>(out->data()),
+                              out->size(), &n, &this->average_distance_));
         out->resize(n);
-        for (auto &c : *out) {   // finalize
-            if (!this->kps_src_.empty()) c.index_query = this->kps_src_[c.index_query];
-            if (!this->kps_tgt_.empty()) c.index_match = this->kps_tgt_[c.index_match];
-        }
         return out;
     }
-
-protected:
-    int mode() const override { return B200M_MODE_CLUSTER; }
-    const float *sx_, *tx_;
-    size_t stride_;
 };
 
-// getFeatureBasedMatcherFromParameters (reference src/matching.cpp:21-76) for one feature type.  ("cluster" needs the
-// keypoint coordinates: construct b200match::ClusterMatcher<FeatureT> directly.)
-template <typename FeatureT, typename... Args>
-FeatureBasedMatcher::Ptr getFeatureBasedMatcherFromParameters(const FeatureCloud<FeatureT> &src, const FeatureCloud<FeatureT> &tgt,
-                                                              const AlignmentParameters &parameters, Args &&...rest) {
+// getFeatureBasedMatcherFromParameters (reference src/matching.cpp:21-76) for one feature type.
+template <typename FeatureT>
+FeatureBasedMatcher::Ptr getFeatureBasedMatcherFromParameters(typename FeatureBasedMatcherImpl<FeatureT>::Storage src,
+                                                              typename FeatureBasedMatcherImpl<FeatureT>::Storage tgt,
+                                                              const AlignmentParameters &parameters) {
     if (parameters.matching_id == "one_sided")
-        return std::make_shared<OneSidedMatcher<FeatureT>>(src, tgt, parameters, std::forward<Args>(rest)...);
+        return std::make_shared<OneSidedMatcher<FeatureT>>(std::move(src), std::move(tgt), parameters);
     if (parameters.matching_id == "lr")
-        return std::make_shared<LeftToRightMatcher<FeatureT>>(src, tgt, parameters, std::forward<Args>(rest)...);
+        return std::make_shared<LeftToRightMatcher<FeatureT>>(std::move(src), std::move(tgt), parameters);
     if (parameters.matching_id == "ratio")
-        return std::make_shared<RatioMatcher<FeatureT>>(src, tgt, parameters, std::forward<Args>(rest)...);
+        return std::make_shared<RatioMatcher<FeatureT>>(std::move(src), std::move(tgt), parameters);
+    if (parameters.matching_id == "cluster")
+        return std::make_shared<ClusterMatcher<FeatureT>>(std::move(src), std::move(tgt), parameters);
     throw std::runtime_error("Matching method " + parameters.matching_id + " isn't supported by the B200 matcher");
 }
 

@@ -260,6 +260,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 template <int KT>
 struct RowState {
     float tk[KT];   // k smallest accumulator values this thread has seen (of distinct columns), ascending
+    float T;        // tk[k - 1], cached: the k-th smallest (+inf until k values are known)
     float thr;      // effective append threshold: min(own threshold, the partner thread's published one)
     float na, eta, slop, gfac;
     int cnt;              // entries appended to this thread's own list (may run past cap: overflow)
@@ -300,9 +301,20 @@ __device__ __forceinline__ void tk_insert(RowState<KT> &st, float v) {
 }
 template <int KT, int EH>
 __device__ __forceinline__ void retighten(RowState<KT> &st, int k) {
-    const float thr_own = cand_threshold(kth_smallest<KT>(st, k), st.na, st.eta, st.slop, st.gfac);
+    st.T = kth_smallest<KT>(st, k);
+    const float thr_own = cand_threshold(st.T, st.na, st.eta, st.slop, st.gfac);
     st.thr = fminf(st.thr, thr_own);
     if (EH == 2) sts_f32(st.s_thr_own, thr_own);
+}
+// A chunk minimum enters the k-smallest list only if it can move the k-th smallest; the threshold is re-derived only
+// when it did (a hit inside the certificate's margin, T <= v < thr(T), changes nothing).
+template <int KT>
+__device__ __forceinline__ void tk_offer(RowState<KT> &st, float m) {
+    if (m < st.T) tk_insert<KT>(st, m);
+}
+template <int KT, int EH>
+__device__ __forceinline__ void retighten_if_moved(RowState<KT> &st, int k) {
+    if (kth_smallest<KT>(st, k) < st.T) retighten<KT, EH>(st, k);
 }
 
 #define F(i) __uint_as_float(r[i])
@@ -388,19 +400,17 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
                                            int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
     const float m0 = min32(r0), m1 = min32(r1), m2 = min32(r2), m3 = min32(r3);
     if (fminf(min3(m0, m1, m2), m3) < st.thr) {   // inactive rows carry thr = -inf
-        if (kth_smallest<KT>(st, k) == INFINITY) {
+        if (st.T == INFINITY) {
             if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, out_v, cap);
             if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, out_v, cap);
             if (m2 < st.thr) warmup_chunk<KT, EH>(r2, col0 + hi, st, k, out, out_v, cap);
             if (m3 < st.thr) warmup_chunk<KT, EH>(r3, col0 + hi + 32, st, k, out, out_v, cap);
         } else {
-            const float T_before = kth_smallest<KT>(st, k);
-            tk_insert<KT>(st, m0);
-            tk_insert<KT>(st, m1);
-            tk_insert<KT>(st, m2);
-            tk_insert<KT>(st, m3);
-            // a hit inside the certificate's margin (T <= v < thr(T)) leaves the k-th smallest where it was
-            if (kth_smallest<KT>(st, k) < T_before) retighten<KT, EH>(st, k);
+            tk_offer<KT>(st, m0);
+            tk_offer<KT>(st, m1);
+            tk_offer<KT>(st, m2);
+            tk_offer<KT>(st, m3);
+            retighten_if_moved<KT, EH>(st, k);
             const float thr = st.thr;
             if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
             if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
@@ -410,25 +420,72 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
     }
 }
 
-// The same for a 64-column batch (two chunks; the alternating-tile epilogue keeps only 64 accumulators in registers).
-template <int KT, int EH>
-__device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int col0, RowState<KT> &st, int k,
-                                          int32_t *__restrict__ out, float *__restrict__ out_v, int cap) {
-    const float m0 = min32(r0), m1 = min32(r1);
-    if (fminf(m0, m1) < st.thr) {   // inactive rows carry thr = -inf
-        if (kth_smallest<KT>(st, k) == INFINITY) {
-            if (m0 < st.thr) warmup_chunk<KT, EH>(r0, col0, st, k, out, out_v, cap);
-            if (m1 < st.thr) warmup_chunk<KT, EH>(r1, col0 + 32, st, k, out, out_v, cap);
-        } else {
-            const float T_before = kth_smallest<KT>(st, k);
-            tk_insert<KT>(st, m0);
-            tk_insert<KT>(st, m1);
-            if (kth_smallest<KT>(st, k) < T_before) retighten<KT, EH>(st, k);
-            const float thr = st.thr;
-            if (m0 < thr) append_chunk<EH>(r0, col0, thr, st.cnt, out, out_v, cap);
-            if (m1 < thr) append_chunk<EH>(r1, col0 + 32, thr, st.cnt, out, out_v, cap);
+// ---- 64-column batches (the sixteen-warp epilogues: EH = 2, no accumulator values recorded) ----
+// The work of a batch is split into what needs the accumulator VALUES (scan64: the minima and, on a hit, bit masks of the
+// columns under the threshold -- two-level: eight-column group minima first, so that a typical hit costs 16 + 8 compares
+// instead of 64) and what does not (apply64: appends from the masks, k-smallest list, threshold).  The alternating-tile
+// epilogue runs only scan64 of its first batch before the accumulators go back to the MMA issuer.
+struct Hit64 {
+    uint32_t mask0, mask1;   // columns of the two 32-column chunks under the threshold at scan time
+    float m0, m1;            // chunk minima
+};
+#define F(i) __uint_as_float(r[i])
+__device__ __forceinline__ uint32_t mask_below(const uint32_t (&r)[32], float thr) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float pg = fminf(min3(min3(F(8 * g), F(8 * g + 1), F(8 * g + 2)), F(8 * g + 3), F(8 * g + 4)),
+                               min3(F(8 * g + 5), F(8 * g + 6), F(8 * g + 7)));
+        if (pg < thr) {
+#pragma unroll
+            for (int i = 8 * g; i < 8 * g + 8; ++i) mask |= (F(i) < thr) ? (1u << i) : 0u;
         }
     }
+    return mask;
+}
+#undef F
+__device__ __forceinline__ void append_mask(uint32_t mask, int col0, int &cnt, int32_t *__restrict__ out, int cap) {
+    while (mask) {
+        const int i = __ffs((int) mask) - 1;
+        mask &= mask - 1;
+        const int slot = cnt++;
+        if (slot < cap) out[slot] = col0 + i;
+    }
+}
+// needs the values.  Returns true when apply64 has work to do.  A row that has not yet seen k columns (its first
+// tile) goes through the warm-up path right here, values in hand.
+template <int KT>
+__device__ __forceinline__ bool scan64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int col0, RowState<KT> &st, int k,
+                                       int32_t *__restrict__ out, int cap, Hit64 &h) {
+    h.m0 = min32(r0);
+    h.m1 = min32(r1);
+    h.mask0 = h.mask1 = 0u;
+    if (!(fminf(h.m0, h.m1) < st.thr)) return false;   // inactive rows carry thr = -inf
+    if (st.T == INFINITY) {
+        if (h.m0 < st.thr) warmup_chunk<KT, 2>(r0, col0, st, k, out, nullptr, cap);
+        if (h.m1 < st.thr) warmup_chunk<KT, 2>(r1, col0 + 32, st, k, out, nullptr, cap);
+        st.T = kth_smallest<KT>(st, k);
+        return false;
+    }
+    if (h.m0 < st.thr) h.mask0 = mask_below(r0, st.thr);
+    if (h.m1 < st.thr) h.mask1 = mask_below(r1, st.thr);
+    return true;
+}
+// needs only the masks and minima: may run after the accumulators have gone back (the masks were taken with a threshold
+// at least as loose as the current one, so the list stays a superset)
+template <int KT>
+__device__ __forceinline__ void apply64(const Hit64 &h, int col0, RowState<KT> &st, int k, int32_t *__restrict__ out, int cap) {
+    append_mask(h.mask0, col0, st.cnt, out, cap);
+    append_mask(h.mask1, col0 + 32, st.cnt, out, cap);
+    tk_offer<KT>(st, h.m0);
+    tk_offer<KT>(st, h.m1);
+    retighten_if_moved<KT, 2>(st, k);
+}
+template <int KT>
+__device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int col0, RowState<KT> &st, int k,
+                                          int32_t *__restrict__ out, int cap) {
+    Hit64 h;
+    if (scan64<KT>(r0, r1, col0, st, k, out, cap, h)) apply64<KT>(h, col0, st, k, out, cap);
 }
 
 // PAIR: CTA-pair mode (tcgen05.mma cta_group::2, M = 256 across two SMs, each CTA holds half of every train tile).
@@ -769,6 +826,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int s = 0; s < KT; ++s) st.tk[s] = INFINITY;
         st.thr = active ? INFINITY : -INFINITY;
+        st.T = INFINITY;
         st.cnt = 0;
         st.s_thr_own = ALT ? s_thr + 4u * (uint32_t) (row_in_tile * 4 + bsel * 2 + half)
                            : s_thr + 4u * (uint32_t) (half * B200M_TILE_M + row_in_tile);
@@ -831,10 +889,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
                     continue;
                 }
-                process64<KT, EH>(r0, r1, col_base, st, k, out, out_v, cap);
+                process64<KT>(r0, r1, col_base, st, k, out, cap);
             }
         } else if constexpr (ALT) {
-            // ===== alternating-tile epilogue: this warp owns accumulator buffer `bsel`, i.e. tiles bsel, bsel + 2, ... =====
+            // ===== alternating-tile epilogue: this warp owns accumulator buffer `bsel`, i.e. tiles bsel, bsel + 2, ...
+            // Of the first 64-column batch only what needs the values (minima, hit masks) runs before the second batch is
+            // loaded and the half goes back to its MMA issuer; appends and threshold upkeep of both batches run after. =====
             uint32_t r0[32], r1[32];
             const uint32_t taddr = e_tmem + (uint32_t) bsel * (uint32_t) B200M_TILE_N;
             // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c
@@ -844,39 +904,39 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 mbar_wait(e_tfull, par);
                 par ^= 1u;
                 tc_fence_after();
+                Hit64 h0;
+                bool hit0 = false;
                 if (!(dflags & 1)) {
                     tmem_ld_32x32b_x32(taddr, r0);
                     tmem_ld_32x32b_x32(taddr + 32u, r1);
                     tmem_ld_wait();
+                    if (!(dflags & 32)) {
+                        if (dflags & 256) {   // timing experiment: fast path only
+                            if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                        } else {
+                            hit0 = scan64<KT>(r0, r1, col_base, st, k, out, cap, h0);
+                        }
+                    }
+                    tmem_ld_32x32b_x32(taddr + 64u, r0);
+                    tmem_ld_32x32b_x32(taddr + 96u, r1);
+                    tmem_ld_wait();
                 }
+                // all 128 columns are in registers or reduced to masks: the half goes back to its MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(e_tempty);
+                if (dflags & (1 | 32)) continue;
+                if (dflags & 256) {
+                    if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                    continue;
+                }
+                if (hit0) apply64<KT>(h0, col_base, st, k, out, cap);
                 {   // what the row's other three threads have learnt (own entry included: harmless)
                     float t0_, t1_, t2_, t3_;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
                     st.thr = fminf(st.thr, fminf(fminf(t0_, t1_), fminf(t2_, t3_)));
                 }
-                if (!(dflags & (1 | 32))) {
-                    if (dflags & 256) {   // timing experiment: fast path only
-                        if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
-                    } else {
-                        process64<KT, EH>(r0, r1, col_base, st, k, out, out_v, cap);
-                    }
-                }
-                if (!(dflags & 1)) {
-                    tmem_ld_32x32b_x32(taddr + 64u, r0);
-                    tmem_ld_32x32b_x32(taddr + 96u, r1);
-                    tmem_ld_wait();
-                }
-                // all 128 columns are in registers or done: the half goes back to its MMA issuer
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(e_tempty);
-                if (!(dflags & (1 | 32))) {
-                    if (dflags & 256) {
-                        if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
-                    } else {
-                        process64<KT, EH>(r0, r1, col_base + 128, st, k, out, out_v, cap);
-                    }
-                }
+                process64<KT>(r0, r1, col_base + 128, st, k, out, cap);
             }
         } else {
         uint32_t r0[32], r1[32], r2[32], r3[32];

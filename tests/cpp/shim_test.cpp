@@ -51,22 +51,8 @@ static int run(char **argv) {
             fprintf(out, "\n");
         }
     }
-    for (const char *id : {"one_sided", "lr", "ratio"}) {
-        if (!strcmp(id, "ratio") && parameters.randomness < 2) continue;
-        parameters.matching_id = id;
-        auto matcher = getFeatureBasedMatcherFromParameters<FeatureT>(src, tgt, parameters);
-        auto corrs = matcher->match();
-        fprintf(out, "matcher %s %s %zu %.9g\n", id, matcher->getClassName().c_str(), corrs->size(), matcher->getAverageDistance());
-        for (const auto &c : *corrs) fprintf(out, "corr %s %d %d %.9g\n", id, c.index_query, c.index_match, c.distance);
-    }
-    try {   // the factory has no keypoints to hand to the cluster filter
-        parameters.matching_id = "cluster";
-        getFeatureBasedMatcherFromParameters<FeatureT>(src, tgt, parameters);
-        abort();
-    } catch (const std::runtime_error &) {
-    }
-    // ClusterMatcher and match_multiscale over keypoints laid out on a deterministic lattice (the pytest driver builds
-    // the same coordinates): pcl::PointXYZ-like rows of 4 floats
+    // keypoints laid out on a deterministic lattice (the pytest driver builds the same coordinates): pcl::PointXYZ-like
+    // rows of 4 floats
     auto lattice = [](size_t n, float step) {
         std::vector<float> xyz(4 * n, 0.f);
         for (size_t i = 0; i < n; ++i) {
@@ -77,14 +63,29 @@ static int run(char **argv) {
         return xyz;
     };
     const auto sx = lattice(ns, 0.5f), tx = lattice(nt, 0.25f);
-    {
-        parameters.cluster_k = 12;
-        ClusterMatcher<FeatureT> cm(src, tgt, parameters, sx.data(), tx.data(), 16);
-        auto corrs = cm.match();
-        fprintf(out, "matcher cluster %s %zu %.9g\n", cm.getClassName().c_str(), corrs->size(), cm.getAverageDistance());
-        for (const auto &c : *corrs) fprintf(out, "corr cluster %d %d %.9g\n", c.index_query, c.index_match, c.distance);
+    using Impl = FeatureBasedMatcherImpl<FeatureT>;
+    // the matcher classes, one scale: match_multiscale both ways + vote + filter (reference include/matching.h:395-517)
+    parameters.cluster_k = 12;
+    for (const char *id : {"one_sided", "lr", "cluster", "ratio"}) {
+        if (!strcmp(id, "ratio") && parameters.randomness < 2) continue;
+        parameters.matching_id = id;
+        auto matcher = getFeatureBasedMatcherFromParameters<FeatureT>(Impl::makeStorage(src, sx.data(), 16, 0.3f),
+                                                                      Impl::makeStorage(tgt, tx.data(), 16, 0.2f), parameters);
+        auto corrs = matcher->match();
+        fprintf(out, "matcher %s %s %zu %.9g\n", id, matcher->getClassName().c_str(), corrs->size(), matcher->getAverageDistance());
+        for (const auto &c : *corrs) fprintf(out, "corr %s %d %d %.9g\n", id, c.index_query, c.index_match, c.distance);
     }
-    {   // two "scales": all keypoints, then every second one on both sides
+    try {   // more than one candidate per keypoint and no coordinates for the vote
+        parameters.matching_id = "lr";
+        AlignmentParameters p2 = parameters;
+        p2.randomness = 2;
+        getFeatureBasedMatcherFromParameters<FeatureT>(Impl::makeStorage(src), Impl::makeStorage(tgt), p2)->match();
+        abort();
+    } catch (const std::runtime_error &) {
+    }
+    // two "scales" (all keypoints, then every second one on both sides): the narrow-seam match_multiscale and the
+    // LeftToRightMatcher over the same Storage contents, finalize included
+    {
         std::vector<FeatureCloud<FeatureT>> qf{src, {}}, tf{tgt, {}};
         std::vector<std::vector<int>> qi(2), ti(2);
         for (size_t i = 0; i < ns; ++i) qi[0].push_back((int) i);
@@ -96,6 +97,30 @@ static int run(char **argv) {
         for (size_t i = 0; i < ns; ++i) {
             fprintf(out, "ms %zu %zu", i, mv[i].match_indices.size());
             for (size_t m = 0; m < mv[i].match_indices.size(); ++m) fprintf(out, " %d %.9g", mv[i].match_indices[m], mv[i].distances[m]);
+            fprintf(out, "\n");
+        }
+        typename Impl::Storage ss, st;
+        ss.kps_xyz = sx.data(); ss.n_kps = ns; ss.iss_radius = 0.3f; ss.kps_features_multiscale = qf; ss.kps_indices_multiscale = qi;
+        st.kps_xyz = tx.data(); st.n_kps = nt; st.iss_radius = 0.2f; st.kps_features_multiscale = tf; st.kps_indices_multiscale = ti;
+        ss.min_log2_radius = st.min_log2_radius = -3;
+        ss.max_log2_radius = st.max_log2_radius = -2;
+        for (size_t i = 0; i < ns; ++i) ss.kps_indices.push_back((int) (3 * i + 1));   // keypoint id -> cloud index
+        for (size_t i = 0; i < nt; ++i) st.kps_indices.push_back((int) (2 * i + 5));
+        parameters.matching_id = "lr";
+        auto matcher = getFeatureBasedMatcherFromParameters<FeatureT>(ss, st, parameters);
+        auto corrs = matcher->match();
+        fprintf(out, "matcher lr2 %s %zu %.9g\n", matcher->getClassName().c_str(), corrs->size(), matcher->getAverageDistance());
+        for (const auto &c : *corrs) fprintf(out, "corr lr2 %d %d %.9g\n", c.index_query, c.index_match, c.distance);
+    }
+    // matchLocal as match_multiscale calls it with a guess (reference include/matching.h:297-304, :637-678)
+    {
+        parameters.match_search_radius = 1.75f;
+        const std::array<float, 16> guess{1.f, 0.f, 0.f, 0.25f, 0.f, 1.f, 0.f, -0.5f, 0.f, 0.f, 1.f, 0.125f, 0.f, 0.f, 0.f, 1.f};
+        auto loc = matchLocal<FeatureT>(sx.data(), tx.data(), 16, src, tgt, parameters, guess);
+        if (loc.size() != ns) abort();
+        for (size_t i = 0; i < ns; ++i) {
+            fprintf(out, "local %zu %zu", i, loc[i].match_indices.size());
+            for (size_t m = 0; m < loc[i].match_indices.size(); ++m) fprintf(out, " %d %.9g", loc[i].match_indices[m], loc[i].distances[m]);
             fprintf(out, "\n");
         }
     }

@@ -44,8 +44,8 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
     assert r.returncode == 0, r.stderr
     s_d, t_d = src[:, :dim], tgt[:, :dim]
     exp = {0: orc.knn(s_d, t_d, k), 1: orc.knn(t_d, s_d, k)}
-    got_corr = {"one_sided": [], "lr": [], "ratio": [], "cluster": []}
-    got_ms = {}
+    got_corr = {"one_sided": [], "lr": [], "ratio": [], "cluster": [], "lr2": []}
+    got_ms, got_local = {}, {}
     heads = {}
     n_knn = 0
     for line in open(op):
@@ -63,39 +63,47 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
             got_corr[w[1]].append((int(w[2]), int(w[3]), np.float32(w[4])))
         elif w[0] == "ms":
             got_ms[int(w[1])] = [(int(a), np.float32(b)) for a, b in zip(w[3::2], w[4::2])]
+        elif w[0] == "local":
+            got_local[int(w[1])] = [(int(a), np.float32(b)) for a, b in zip(w[3::2], w[4::2])]
     assert n_knn == ns + nt
     fmax = np.float32(np.finfo(np.float32).max)
-    for mid, mode, cls in (("one_sided", "one_sided", "OneSidedMatcher"), ("lr", "mutual", "LeftToRightMatcher"),
-                           ("ratio", "ratio", "RatioMatcher")):
-        if mid == "ratio" and k < 2:
-            continue
-        e, eavg = orc.match(s_d, t_d, max(k, 2) if mid == "ratio" else k, mode, 1.1, fmax)
-        assert heads[mid][0] == cls and heads[mid][1] == len(e) and heads[mid][2] == np.float32(eavg)
-        assert got_corr[mid] == [(int(a), int(b), np.float32(c)) for a, b, c in zip(e["index_query"], e["index_match"], e["distance"])]
 
-    # ClusterMatcher and match_multiscale over the same keypoint lattice shim_test.cpp builds
+    # the same keypoint lattice shim_test.cpp builds
     def lattice(n, step):
         i = np.arange(n)
         return np.stack([step * (i % 17), step * ((i // 17) % 13), step * (i // 221)], 1).astype(np.float32)
     sx, tx = lattice(ns, np.float32(0.5)), lattice(nt, np.float32(0.25))
-    f = orc.knn(s_d, t_d, k)
-    r = orc.knn(t_d, s_d, k)
-    e = orc.filter_cluster(f[0], f[2], r[0], r[2], orc.knn3d(sx, 12), orc.knn3d(tx, 12), fmax)
-    assert heads["cluster"][0] == "ClusterMatcher" and heads["cluster"][1] == len(e)
-    assert got_corr["cluster"] == [(int(a), int(b), np.float32(c)) for a, b, c in zip(e["index_query"], e["index_match"], e["distance"])]
-    q2, t2 = np.arange(0, ns, 2), np.arange(0, nt, 2)
-    f2 = orc.knn(np.ascontiguousarray(s_d[q2]), np.ascontiguousarray(t_d[t2]), k)
-    ci = np.full((ns, 2 * k), -1, np.int32)
-    cd = np.zeros((ns, 2 * k), np.float32)
-    cc = np.zeros(ns, np.int32)
-    for i in range(ns):
-        ent = [(int(f[0][i, m]), f[1][i, m]) for m in range(f[2][i])]
-        if i % 2 == 0:
-            ent += [(int(t2[f2[0][i // 2, m]]), f2[1][i // 2, m]) for m in range(f2[2][i // 2])]
-        cc[i] = len(ent)
-        for m, (a, b) in enumerate(ent):
-            ci[i, m], cd[i, m] = a, b
-    vi, vd, vc = orc.spatial_vote(ci, cd, cc, tx, np.float32(0.3))
+    iss_s, iss_t = np.float32(0.3), np.float32(0.2)
+
+    def triples(e):
+        return [(int(a), int(b), np.float32(c)) for a, b, c in zip(e["index_query"], e["index_match"], e["distance"])]
+    # matcher classes: match_impl as the reference composes it (match_multiscale both ways + vote + filter)
+    one = ([(np.ascontiguousarray(s_d), None)], [(np.ascontiguousarray(t_d), None)])
+    for mid, mode, cls in (("one_sided", "one_sided", "OneSidedMatcher"), ("lr", "mutual", "LeftToRightMatcher"),
+                           ("cluster", "cluster", "ClusterMatcher")):
+        e, eavg = orc.match_wide(mode, one[0], one[1], sx, tx, iss_s, iss_t, k, 12, fmax)
+        assert heads[mid][0] == cls and heads[mid][1] == len(e) and heads[mid][2] == np.float32(eavg)
+        assert got_corr[mid] == triples(e)
+    if k >= 2:   # the ratio filter stays on the raw k-lists (a stub in the reference)
+        e, eavg = orc.match(s_d, t_d, k, "ratio", 1.1, fmax)
+        assert heads["ratio"][0] == "RatioMatcher" and heads["ratio"][1] == len(e) and heads["ratio"][2] == np.float32(eavg)
+        assert got_corr["ratio"] == triples(e)
+    # two scales: the narrow-seam match_multiscale and the LeftToRightMatcher over the same Storage, finalize included
+    q2, t2 = np.arange(0, ns, 2).astype(np.int32), np.arange(0, nt, 2).astype(np.int32)
+    s_sc = [(np.ascontiguousarray(s_d), np.arange(ns, dtype=np.int32)), (np.ascontiguousarray(s_d[q2]), q2)]
+    t_sc = [(np.ascontiguousarray(t_d), np.arange(nt, dtype=np.int32)), (np.ascontiguousarray(t_d[t2]), t2)]
+    vi, vd, vc = orc.match_multiscale(s_sc, t_sc, ns, tx, np.float32(0.3), k)
     assert len(got_ms) == ns
     for i in range(ns):
         assert got_ms[i] == ([(int(vi[i, 0]), np.float32(vd[i, 0]))] if vc[i] else [])
+    e, eavg = orc.match_wide("mutual", s_sc, t_sc, sx, tx, iss_s, iss_t, k, 12, fmax)
+    e = orc.finalize(e, (3 * np.arange(ns) + 1).astype(np.int32), (2 * np.arange(nt) + 5).astype(np.int32))
+    assert heads["lr2"][0] == "LeftToRightMatcher" and heads["lr2"][1] == len(e) and heads["lr2"][2] == np.float32(eavg)
+    assert got_corr["lr2"] == triples(e)
+    # the gated matchLocal: query keypoints moved by the guess (a translation), radius 1.75
+    g = np.array([0.25, -0.5, 0.125], np.float32)
+    moved = ((np.float32(1) * sx + np.float32(0)) + g).astype(np.float32)   # 1*x + 0*y + 0*z + t in float32
+    li, ld, lc = orc.match_local(s_d, t_d, k, moved, tx, np.float32(1.75))
+    assert len(got_local) == ns and lc.min() < k   # the gate bites somewhere
+    for i in range(ns):
+        assert got_local[i] == [(int(li[i, m]), np.float32(ld[i, m])) for m in range(lc[i])]
