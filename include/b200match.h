@@ -64,7 +64,13 @@ typedef struct {
     int32_t precision;    /* B200M_PREC_* */
     int32_t cand_cap;     /* candidate slots per query row and train split in the tensor-core pass
                              (0 = default chosen from k; rows that overflow go through the exact row kernel) */
+    int32_t n_gpus;       /* multi-GPU calls: 0 = every rank of the communicator / group (the only value accepted besides
+                             the communicator's size; kept for the reference-side config) */
+    int32_t shard;        /* multi-GPU calls: B200M_SHARD_QUERY (source rows split, target replicated) or
+                             B200M_SHARD_TARGET (target rows split, per-query top-k merge) */
 } b200m_params;
+
+enum { B200M_SHARD_QUERY = 0, B200M_SHARD_TARGET = 1 };
 
 /* per-call device timings and counters, filled by the *_device calls when
  * profiling is on (b200m_set_profiling); times are CUDA-event milliseconds on the
@@ -233,6 +239,58 @@ B200M_API int b200m_cluster_filter_device(b200m_ctx *ctx, const b200m_params *p,
                                           size_t cap, unsigned long long *d_n_out, float *d_avg);
 B200M_API int b200m_knn3d_device(b200m_ctx *ctx, const float *d_xyz, size_t n, size_t xyz_stride_bytes, int k,
                                  int32_t *d_nbr);
+
+/* ---- multi-GPU: the partitioning of SURVEY 8e inside the library (NCCL over NVLink, bound at run time) ----------------
+ * Rank r of W owns rows [r*R, min(n, (r+1)*R)), R = ceil(n / W) (b200m_shard_rows).
+ *
+ * (1) One process per GPU: create a context per process, exchange a B200M_UNIQUE_ID_BYTES id made by
+ *     b200m_comm_unique_id on one rank (any transport: MPI, torch.distributed, a file), b200m_comm_attach on every rank,
+ *     then call the *_sharded entry points COLLECTIVELY (every rank, same arguments, same order):
+ *       b200m_upload_replicated      every rank holds the whole HOST set: rank r copies 1/W of it over PCIe, the slices are
+ *                                    all-gathered over NVLink, the pack kernel runs on the full set (or use
+ *                                    b200m_upload[_device] per rank when the set is already resident)
+ *       b200m_match_sharded[_device] the whole matcher call, query-sharded / target-replicated: forward kNN of this rank's
+ *                                    source rows, reverse kNN of this rank's (referenced) target rows, ONE all-gather of the
+ *                                    reverse table, filter of this rank's rows.  Output = this rank's slice, ascending
+ *                                    index_query; the slices in rank order are the single-GPU output.  The average is the
+ *                                    one over ALL source rows on every rank.
+ *       b200m_knn_target_sharded_device   side 1 = this rank's target shard (uploaded with index_offset = its first
+ *                                    global row), side 0 all queries: exact local top-k, all-gather, merge -> every rank
+ *                                    holds the full k-lists (BASELINE configs[4]; at most 8 ranks).
+ * (2) One process, several GPUs -- the reference's shape (one FeatureBasedMatcher::match() call in one address space,
+ *     src/correspondence_search.cpp:14-15): b200m_create_multi makes one context per device plus one host thread per
+ *     device inside the library; the b200m_group_* calls take and return WHOLE host arrays. */
+#define B200M_UNIQUE_ID_BYTES 128
+B200M_API int b200m_comm_unique_id(void *id_out, size_t bytes);
+B200M_API int b200m_comm_attach(b200m_ctx *ctx, int n_ranks, int rank, const void *unique_id);
+B200M_API int b200m_comm_rank(const b200m_ctx *ctx, int *rank, int *n_ranks);
+B200M_API int b200m_shard_rows(size_t n, int n_ranks, int rank, size_t *row_begin, size_t *row_end);
+B200M_API int b200m_upload_replicated(b200m_ctx *ctx, int side, const float *host_base, size_t n, size_t stride_bytes,
+                                      int dim);
+B200M_API int b200m_match_sharded(b200m_ctx *ctx, const b200m_params *p, const float *thr_src, const float *thr_tgt,
+                                  b200m_corr *out, size_t cap, size_t *n_out, float *avg_first_dist);
+B200M_API int b200m_match_sharded_device(b200m_ctx *ctx, const b200m_params *p, const float *d_thr_src,
+                                         const float *d_thr_tgt, b200m_corr *d_out, size_t cap,
+                                         unsigned long long *d_n_out, float *d_avg);
+B200M_API int b200m_knn_target_sharded_device(b200m_ctx *ctx, const b200m_params *p, int32_t *d_idx, float *d_dist,
+                                              int32_t *d_count);
+
+typedef struct b200m_group b200m_group;
+B200M_API int b200m_create_multi(b200m_group **group, const int *device_ids, int n);
+B200M_API void b200m_destroy_multi(b200m_group *group);
+B200M_API const char *b200m_group_last_error(const b200m_group *group); /* group may be NULL: last create error */
+B200M_API int b200m_group_size(const b200m_group *group);
+B200M_API b200m_ctx *b200m_group_ctx(b200m_group *group, int i);        /* e.g. for b200m_get_stats */
+/* replicated upload (query-sharded runs) / row-sharded upload with global index offsets (target-sharded runs) */
+B200M_API int b200m_group_upload(b200m_group *group, int side, const float *host_base, size_t n, size_t stride_bytes,
+                                 int dim);
+B200M_API int b200m_group_upload_sharded(b200m_group *group, int side, const float *host_base, size_t n,
+                                         size_t stride_bytes, int dim);
+/* == b200m_match / b200m_knn(direction 0, all rows) on the whole problem; p->shard picks the partition for the kNN
+ * (B200M_SHARD_TARGET needs the target uploaded with b200m_group_upload_sharded) */
+B200M_API int b200m_group_match(b200m_group *group, const b200m_params *p, const float *thr_src, const float *thr_tgt,
+                                b200m_corr *out, size_t cap, size_t *n_out, float *avg_first_dist);
+B200M_API int b200m_group_knn(b200m_group *group, const b200m_params *p, int32_t *idx, float *dist, int32_t *count);
 
 /* ---- the matcher classes at the WIDE seam: FeatureBasedMatcherImpl<FeatureT>::match_impl -------------------------
  * (include/matching.h:395-411 OneSidedMatcher, :428-453 LeftToRightMatcher, :492-517 ClusterMatcher), composed as

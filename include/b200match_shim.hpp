@@ -87,6 +87,8 @@ struct AlignmentParameters {
     float ratio_thr = 1.1f;         // MATCHING_RATIO_THRESHOLD, include/common.h:50
     float match_search_radius = std::numeric_limits<float>::max();   // :160  matchLocal's 3-D gate
     int device = 0;
+    std::vector<int> devices;       // more than one entry: the call is partitioned over these GPUs inside the library
+                                    // (b200m_create_multi: source rows sharded, target replicated, NCCL over NVLink)
     int precision = B200M_PREC_TC_F16;
 };
 
@@ -123,6 +125,35 @@ inline Context &shared_context(int device) {
     return *slot;
 }
 
+class Group {   // RAII b200m_group: one context + one host thread per device, inside the library
+public:
+    explicit Group(const std::vector<int> &devices) {
+        if (b200m_create_multi(&g_, devices.data(), (int) devices.size()) != 0) throw std::runtime_error(b200m_group_last_error(nullptr));
+    }
+    ~Group() { b200m_destroy_multi(g_); }
+    Group(const Group &) = delete;
+    Group &operator=(const Group &) = delete;
+    b200m_group *get() const { return g_; }
+    void check(int rc) const {
+        if (rc != 0) throw std::runtime_error(b200m_group_last_error(g_));
+    }
+    template <typename FeatureT>
+    void upload(int side, const FeatureCloud<FeatureT> &cloud) {
+        check(b200m_group_upload(g_, side, reinterpret_cast<const float *>(cloud_data<FeatureT>(cloud)), cloud_size<FeatureT>(cloud),
+                                 sizeof(FeatureT), feature_dim<FeatureT>()));
+    }
+
+private:
+    b200m_group *g_ = nullptr;
+};
+
+inline Group &shared_group(const std::vector<int> &devices) {
+    thread_local std::map<std::vector<int>, std::unique_ptr<Group>> pool;
+    auto &slot = pool[devices];
+    if (!slot) slot.reset(new Group(devices));
+    return *slot;
+}
+
 inline b200m_params make_params(const AlignmentParameters &p, int mode, int k) {
     b200m_params q;
     q.k = k;
@@ -131,6 +162,8 @@ inline b200m_params make_params(const AlignmentParameters &p, int mode, int k) {
     q.distance_thr = p.distance_thr;
     q.precision = p.precision;
     q.cand_cap = 0;
+    q.n_gpus = 0;
+    q.shard = B200M_SHARD_QUERY;
     return q;
 }
 
@@ -139,16 +172,23 @@ template <typename FeatureT>
 std::vector<MultivaluedCorrespondence> matchBF(const FeatureCloud<FeatureT> &query_features,
                                                const FeatureCloud<FeatureT> &train_features,
                                                const AlignmentParameters &parameters) {
-    Context &ctx = shared_context(parameters.device);
-    ctx.upload<FeatureT>(0, query_features);
-    ctx.upload<FeatureT>(1, train_features);
     const size_t nq = cloud_size<FeatureT>(query_features);
     const int k = parameters.randomness;
     std::vector<int32_t> idx(nq * k);
     std::vector<float> dist(nq * k);
     std::vector<int32_t> cnt(nq);
     b200m_params p = make_params(parameters, B200M_MODE_KNN_ONLY, k);
-    ctx.check(b200m_knn(ctx.get(), &p, 0, 0, 0, idx.data(), dist.data(), cnt.data()));
+    if (parameters.devices.size() > 1) {   // query rows sharded over the GPUs, train set replicated
+        Group &g = shared_group(parameters.devices);
+        g.upload<FeatureT>(0, query_features);
+        g.upload<FeatureT>(1, train_features);
+        g.check(b200m_group_knn(g.get(), &p, idx.data(), dist.data(), cnt.data()));
+    } else {
+        Context &ctx = shared_context(parameters.device);
+        ctx.upload<FeatureT>(0, query_features);
+        ctx.upload<FeatureT>(1, train_features);
+        ctx.check(b200m_knn(ctx.get(), &p, 0, 0, 0, idx.data(), dist.data(), cnt.data()));
+    }
     std::vector<MultivaluedCorrespondence> out(nq);
     for (size_t i = 0; i < nq; ++i) {
         out[i].match_indices.assign(idx.begin() + i * k, idx.begin() + i * k + cnt[i]);
@@ -364,6 +404,20 @@ protected:
         b200m_params p = make_params(parameters_, mode(), parameters_.randomness);
         auto out = std::make_shared<Correspondences>(st_src_.n_kps);
         size_t n = 0;
+        if (parameters_.devices.size() > 1) {
+            // several GPUs: the library partitions the k-list matcher call (b200m_group_match).  That IS match_impl when every
+            // keypoint has one candidate (randomness 1, one scale, identity maps: the vote keeps it); the voted multi-scale
+            // form runs on one GPU.
+            if (parameters_.randomness != 1 || scales.size() != 1 || scales[0].src_map || scales[0].tgt_map || mode() == B200M_MODE_CLUSTER)
+                throw std::runtime_error("multi-GPU matcher classes: randomness 1, one scale, one-sided / lr only");
+            Group &g = shared_group(parameters_.devices);
+            g.upload<FeatureT>(0, st_src_.kps_features_multiscale[(size_t) (lo - st_src_.min_log2_radius)]);
+            g.upload<FeatureT>(1, st_tgt_.kps_features_multiscale[(size_t) (lo - st_tgt_.min_log2_radius)]);
+            g.check(b200m_group_match(g.get(), &p, thr ? st_src_.thresholds.data() : nullptr, thr ? st_tgt_.thresholds.data() : nullptr,
+                                      reinterpret_cast<b200m_corr *>(out->data()), out->size(), &n, &average_distance_));
+            out->resize(n);
+            return out;
+        }
         Context &ctx = shared_context(parameters_.device);
         ctx.check(b200m_match_multiscale(ctx.get(), &p, scales.data(), (int) scales.size(), sizeof(FeatureT), feature_dim<FeatureT>(),
                                          sx, st_src_.n_kps, tx, st_tgt_.n_kps, stride, st_src_.iss_radius, st_tgt_.iss_radius,

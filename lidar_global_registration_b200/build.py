@@ -11,9 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200match.so")
-SOURCES = ["api.cu", "pack.cu", "exact.cu", "filter.cu", "candidates_tc.cu", "multiscale.cu", "cluster.cu", "wide.cu"]
+SOURCES = ["api.cu", "pack.cu", "exact.cu", "filter.cu", "candidates_tc.cu", "multiscale.cu", "cluster.cu", "wide.cu", "multi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-LINK_VERSION = "cudart-shared-1"
+LINK_VERSION = "cudart-shared-2-dl-pthread"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wall",
          "-diag-suppress", "177"]
@@ -79,7 +79,7 @@ def build(force=False, verbose=False):
     # stand-alone C++ users) instead of a private static copy -- two runtimes in one process can disagree about
     # the current device on multi-GPU ranks.
     cmd = [NVCC, "-shared", "-cudart", "shared", "-o", LIB] + objs + [
-        "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+        "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-ldl", "-lpthread"]
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:
         f.write(digest + "\n")

@@ -87,7 +87,7 @@ void StatTimer::stop() {
 
 extern "C" {
 
-int b200m_version(void) { return 100; }
+int b200m_version(void) { return 200; }
 
 int b200m_create(b200m_ctx **out, int device) {
     b200m_ctx *ctx = nullptr;
@@ -154,6 +154,7 @@ void b200m_destroy(b200m_ctx *ctx) {
     multiscale_release(ctx);
     cluster_release(ctx);
     wide_release(ctx);
+    comm_release(ctx);
     if (ctx->pool) {
         if (ctx->pool->created)
             for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventDestroy(ctx->pool->ev[i]);
@@ -334,8 +335,8 @@ __global__ void gather_query_rows_kernel(const int32_t *__restrict__ row_list, s
 
 // kNN of query rows [row_begin, row_begin + n_rows) of `direction`; with d_flags, only of the flagged (and valid) rows --
 // every other row gets an empty list.  Outputs are indexed by (row - row_begin).
-static int knn_core(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t n_rows,
-                    const uint8_t *d_flags, int32_t *d_idx, float *d_dist, int32_t *d_count) {
+int b200m_knn_rows(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t n_rows,
+                   const uint8_t *d_flags, int32_t *d_idx, float *d_dist, int32_t *d_count) {
     Side &q = ctx->side[direction], &t = ctx->side[1 - direction];
     const int k = p->k;
     cudaStream_t st = ctx->stream;
@@ -481,7 +482,7 @@ int b200m_knn_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_
     REQUIRE_CTX();
     if (check_knn_args(ctx, p, direction, row_begin, &row_end, d_idx, d_dist, d_count)) return 1;
     if (row_end == row_begin) return 0;
-    return knn_core(ctx, p, direction, row_begin, row_end - row_begin, nullptr, d_idx, d_dist, d_count);
+    return b200m_knn_rows(ctx, p, direction, row_begin, row_end - row_begin, nullptr, d_idx, d_dist, d_count);
 }
 
 int b200m_knn_masked_device(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t row_end,
@@ -490,7 +491,7 @@ int b200m_knn_masked_device(b200m_ctx *ctx, const b200m_params *p, int direction
     if (check_knn_args(ctx, p, direction, row_begin, &row_end, d_idx, d_dist, d_count)) return 1;
     if (row_end == row_begin) return 0;
     if (!d_row_flags) return b200m_fail_msg(ctx, "b200m_knn_masked: null row flags");
-    return knn_core(ctx, p, direction, row_begin, row_end - row_begin, d_row_flags, d_idx, d_dist, d_count);
+    return b200m_knn_rows(ctx, p, direction, row_begin, row_end - row_begin, d_row_flags, d_idx, d_dist, d_count);
 }
 
 int b200m_mark_referenced_device(b200m_ctx *ctx, int k, const int32_t *d_fidx, const int32_t *d_fcount, size_t n_rows,
@@ -673,7 +674,7 @@ int b200m_match(b200m_ctx *ctx, const b200m_params *p, const float *thr_src, con
                 return 1;
             d_flags = ctx->ws_row_flags.as<uint8_t>();
         }
-        if (knn_core(ctx, p, 1, 0, nt, d_flags, ctx->ws_ridx.as<int32_t>(), ctx->ws_rdist.as<float>(), ctx->ws_rcnt.as<int32_t>()))
+        if (b200m_knn_rows(ctx, p, 1, 0, nt, d_flags, ctx->ws_ridx.as<int32_t>(), ctx->ws_rdist.as<float>(), ctx->ws_rcnt.as<int32_t>()))
             return 1;
     }
     const float *d_thr_s = nullptr, *d_thr_t = nullptr;

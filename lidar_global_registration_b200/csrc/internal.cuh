@@ -68,6 +68,7 @@ struct b200m_ctx {
     void *multiscale = nullptr;   // MultiscaleState (multiscale.cu)
     void *cluster = nullptr;      // ClusterState (cluster.cu)
     void *wide = nullptr;         // WideState (wide.cu)
+    void *comm = nullptr;         // Comm (multi.cu): this context's rank in an NCCL communicator
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     double masked_min_pairs = 1e9;   // B200M_MASKED_MIN_PAIRS: b200m_match skips unreferenced target rows in the reverse pass
                                      // from this many (source, target) pairs on (below, the row selection's host round trip
@@ -190,6 +191,14 @@ int ms_vote_device(b200m_ctx *ctx, MultiscaleState *ms, const float *d_train_xyz
 
 // wide.cu
 void wide_release(b200m_ctx *ctx);
+
+// multi.cu
+void comm_release(b200m_ctx *ctx);
+
+// api.cu: kNN of query rows [row_begin, row_begin + n_rows) of `direction` on device buffers; with d_flags only the flagged
+// (and valid) rows are answered, the others get empty lists.  Outputs are indexed by (row - row_begin).
+extern "C" int b200m_knn_rows(b200m_ctx *ctx, const b200m_params *p, int direction, size_t row_begin, size_t n_rows, const uint8_t *d_flags,
+                   int32_t *d_idx, float *d_dist, int32_t *d_count);
 
 // cluster.cu
 void cluster_release(b200m_ctx *ctx);

@@ -1,13 +1,13 @@
-"""Device-resident and multi-GPU drivers of the matcher (torch tensors for HBM buffers, the
-current torch stream, torch.distributed/NCCL for the one exchange step the path has).
+"""Device-resident and multi-GPU drivers of the matcher on torch tensors (HBM buffers, the current torch stream).
 
     GpuBackend      one b200m context working on torch device buffers (no host copies)
-    ShardedMatcher  SURVEY 8e: query-sharded / target-replicated matcher (forward rows and reverse rows
-                    split across ranks, ONE all-gather of the reverse table for the mutual test), and the
-                    target-sharded kNN (per-rank exact top-k with global indices, all-gather, merge kernel).
-
-The sharding logic is backend-agnostic: tests drive it on CPU with gloo and a stand-in backend; on the
-GPU box the backend is GpuBackend and the process group is NCCL over NVLink.
+    ShardedMatcher  SURVEY 8e, one process per GPU: query-sharded / target-replicated matcher and the target-sharded kNN.
+                    With a GpuBackend this is a THIN caller of the library -- partitioning, the NCCL exchange step and
+                    the merge live in libb200match.so (csrc/multi.cu: b200m_match_sharded_device,
+                    b200m_knn_target_sharded_device, b200m_upload_replicated); torch.distributed only carries the
+                    128-byte communicator id to the ranks.  The same partitioning written out in Python over
+                    torch.distributed collectives is kept for backends without native sharding: the CPU tests drive it
+                    with gloo and a stand-in backend as an executable statement of the exchange protocol.
 """
 import torch
 
@@ -19,14 +19,16 @@ MASKED_REVERSE_MIN_PAIRS = 10 ** 9
 
 
 def shard_bounds(n, rank, world):
-    """Contiguous, balanced row ranges: rank r owns [lo, hi)."""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """The library's row partition (b200m_shard_rows): rank r owns [r*R, min(n, (r+1)*R)), R = ceil(n / world) -- the
+    all-gathered slots are then the row-major table of all rows."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
 
 
 class GpuBackend:
     """kNN / filter / merge on device buffers through the C-ABI *_device entry points."""
+    native_sharding = True    # partitioning + NCCL inside libb200match.so
 
     def __init__(self, device_index=0, precision=M.PREC_TC_F16, cand_cap=0):
         self.device = torch.device("cuda", device_index)
@@ -48,6 +50,18 @@ class GpuBackend:
     @property
     def n(self):
         return self.ctx.n
+
+    def attach_comm(self, rank, world, group=None):
+        """Give the context its rank in an NCCL communicator of its own: rank 0 makes the id, torch.distributed carries
+        the 128 bytes to the others (plumbing only)."""
+        import torch.distributed as dist
+        ident = torch.zeros(M.UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            ident = torch.frombuffer(bytearray(M.comm_unique_id()), dtype=torch.uint8).clone()
+        on_dev = dist.get_backend(group) == "nccl"
+        t = ident.to(self.device) if on_dev else ident
+        dist.broadcast(t, src=0, group=group)
+        self.ctx.comm_attach(world, rank, bytes(t.cpu().numpy().tobytes()))
 
     # -- descriptors ----------------------------------------------------------
     def upload_device(self, side, aos, dim, index_offset=0):
@@ -147,6 +161,9 @@ class ShardedMatcher:
     def __init__(self, backend, rank=0, world=1, group=None):
         self.b = backend
         self.rank, self.world, self.group = rank, world, group
+        self.native = world > 1 and getattr(backend, "native_sharding", False)
+        if self.native:
+            backend.attach_comm(rank, world, group)
 
     # -- collectives ------------------------------------------------------------
     def _all_gather_rows(self, t, n_total):
@@ -175,6 +192,13 @@ class ShardedMatcher:
         if self.world == 1:
             return self.b.upload_host(side, aos_host, dim, index_offset)
         n = aos_host.shape[0]
+        if self.native:
+            assert index_offset == 0
+            c = self.b.ctx
+            c._ck(c._L.b200m_upload_replicated(c._h, side, aos_host.data_ptr(), n, aos_host.stride(0) * 4, dim))
+            c.n[side], c.dim = n, dim
+            lo, hi = shard_bounds(n, self.rank, self.world)
+            return (hi - lo) * aos_host.stride(0) * 4
         lo, hi = shard_bounds(n, self.rank, self.world)
         shard = aos_host[lo:hi].to(self.b.device, non_blocking=True)
         full = self._all_gather_rows(shard, n)
@@ -188,6 +212,13 @@ class ShardedMatcher:
         single-GPU output (ascending index_query)."""
         nq, nt = self.b.n
         q0, q1 = shard_bounds(nq, self.rank, self.world)
+        if self.native:
+            cap = max((q1 - q0) * (k if mode == M.MODE_MUTUAL else 1), 1)
+            out = torch.empty((cap, 4), dtype=torch.int32, device=self.b.device)
+            n_out = torch.zeros((1,), dtype=torch.int64, device=self.b.device)
+            self.b.ctx.match_sharded_device(k, mode, out.data_ptr(), cap, n_out.data_ptr(), ratio_thr=ratio_thr,
+                                            distance_thr=distance_thr, precision=self.b.precision, cand_cap=self.b.cand_cap)
+            return out, n_out, None
         fwd = self.b.knn(k, 0, q0, q1)
         rev = None
         if mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL):
@@ -226,6 +257,13 @@ class ShardedMatcher:
         """The backend's side 1 holds THIS rank's target shard (uploaded with index_offset = shard start), side 0
         all queries.  Exact local top-k with global indices -> all-gather -> merge kernel (canonical tie rule)."""
         nq = self.b.n[0]
+        if self.native:
+            idx = torch.empty((nq, k), dtype=torch.int32, device=self.b.device)
+            dist_ = torch.empty((nq, k), dtype=torch.float32, device=self.b.device)
+            cnt = torch.empty((nq,), dtype=torch.int32, device=self.b.device)
+            self.b.ctx.knn_target_sharded_device(k, idx.data_ptr(), dist_.data_ptr(), cnt.data_ptr(), self.b.precision,
+                                                 self.b.cand_cap)
+            return idx, dist_, cnt
         local = self.b.knn(k, 0, 0, nq)
         if self.world == 1:
             return local

@@ -26,6 +26,8 @@ CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"),
 
 MODE_KNN_ONLY, MODE_ONE_SIDED, MODE_MUTUAL, MODE_RATIO, MODE_RATIO_MUTUAL, MODE_CLUSTER = 0, 1, 2, 3, 4, 5
 PREC_TC_F16, PREC_F32_EXACT = 0, 2
+SHARD_QUERY, SHARD_TARGET = 0, 1
+UNIQUE_ID_BYTES = 128
 
 # reference constants (include/common.h:50-51, :42, :45)
 MATCHING_RATIO_THRESHOLD = 1.1
@@ -41,7 +43,7 @@ class B200MatchError(RuntimeError):
 
 class _Params(C.Structure):
     _fields_ = [("k", C.c_int32), ("mode", C.c_int32), ("ratio_thr", C.c_float), ("distance_thr", C.c_float),
-                ("precision", C.c_int32), ("cand_cap", C.c_int32)]
+                ("precision", C.c_int32), ("cand_cap", C.c_int32), ("n_gpus", C.c_int32), ("shard", C.c_int32)]
 
 
 class _Scale(C.Structure):
@@ -66,7 +68,10 @@ EXPORTS = ["b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_strea
            "b200m_version", "b200m_debug_operands", "b200m_debug_tc_tile", "b200m_multiscale_begin",
            "b200m_multiscale_add", "b200m_multiscale_vote", "b200m_multiscale_add_device", "b200m_multiscale_vote_device", "b200m_match_cluster",
            "b200m_cluster_filter_device", "b200m_knn3d_device", "b200m_knn_local", "b200m_knn_local_device", "b200m_mark_referenced_device", "b200m_knn_masked_device",
-           "b200m_match_multiscale"]
+           "b200m_match_multiscale", "b200m_comm_unique_id", "b200m_comm_attach", "b200m_comm_rank", "b200m_shard_rows",
+           "b200m_upload_replicated", "b200m_match_sharded", "b200m_match_sharded_device", "b200m_knn_target_sharded_device",
+           "b200m_create_multi", "b200m_destroy_multi", "b200m_group_last_error", "b200m_group_size", "b200m_group_ctx",
+           "b200m_group_upload", "b200m_group_upload_sharded", "b200m_group_match", "b200m_group_knn"]
 
 _lib = None
 
@@ -114,6 +119,26 @@ def load_library():
     L.b200m_knn_local_device.argtypes = [vp, C.POINTER(_Params), C.c_int, fp, fp, sz, C.c_float, vp, vp, vp]
     L.b200m_match_multiscale.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Scale), C.c_int, sz, C.c_int, fp, sz, fp, sz, sz,
                                          C.c_float, C.c_float, C.c_int, fp, fp, vp, sz, C.POINTER(sz), C.POINTER(C.c_float)]
+    L.b200m_comm_unique_id.argtypes = [vp, sz]
+    L.b200m_comm_attach.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.b200m_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.b200m_shard_rows.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+    L.b200m_upload_replicated.argtypes = [vp, C.c_int, fp, sz, sz, C.c_int]
+    L.b200m_match_sharded.argtypes = [vp, C.POINTER(_Params), fp, fp, vp, sz, C.POINTER(sz), C.POINTER(C.c_float)]
+    L.b200m_match_sharded_device.argtypes = [vp, C.POINTER(_Params), fp, fp, vp, sz, vp, vp]
+    L.b200m_knn_target_sharded_device.argtypes = [vp, C.POINTER(_Params), vp, vp, vp]
+    L.b200m_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.b200m_destroy_multi.argtypes = [vp]
+    L.b200m_destroy_multi.restype = None
+    L.b200m_group_last_error.argtypes = [vp]
+    L.b200m_group_last_error.restype = C.c_char_p
+    L.b200m_group_size.argtypes = [vp]
+    L.b200m_group_ctx.argtypes = [vp, C.c_int]
+    L.b200m_group_ctx.restype = vp
+    L.b200m_group_upload.argtypes = [vp, C.c_int, fp, sz, sz, C.c_int]
+    L.b200m_group_upload_sharded.argtypes = [vp, C.c_int, fp, sz, sz, C.c_int]
+    L.b200m_group_match.argtypes = [vp, C.POINTER(_Params), fp, fp, vp, sz, C.POINTER(sz), C.POINTER(C.c_float)]
+    L.b200m_group_knn.argtypes = [vp, C.POINTER(_Params), vp, vp, vp]
     L.b200m_version.restype = C.c_int
     L.b200m_debug_operands.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, C.POINTER(C.c_float), C.POINTER(i32),
                                        C.POINTER(i64)]
@@ -159,6 +184,7 @@ class Context:
         self.device = int(device)
         self.n = [0, 0]
         self.dim = 0
+        self.rank, self.n_ranks = 0, 1
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -182,8 +208,10 @@ class Context:
             raise B200MatchError(self._L.b200m_last_error(self._h).decode())
 
     @staticmethod
-    def _params(k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, precision=PREC_TC_F16, cand_cap=0):
-        return _Params(int(k), int(mode), float(ratio_thr), float(distance_thr), int(precision), int(cand_cap))
+    def _params(k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, precision=PREC_TC_F16, cand_cap=0,
+                n_gpus=0, shard=SHARD_QUERY):
+        return _Params(int(k), int(mode), float(ratio_thr), float(distance_thr), int(precision), int(cand_cap), int(n_gpus),
+                       int(shard))
 
     # -- plumbing ------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
@@ -219,6 +247,46 @@ class Context:
         self._ck(self._L.b200m_upload_device(self._h, side, C.c_void_p(ptr), n, stride_bytes, dim, index_offset))
         self.n[side] = n
         self.dim = dim
+
+    # -- multi-GPU: one process per GPU ----------------------------------------
+    def comm_attach(self, n_ranks, rank, unique_id):
+        """ncclCommInitRank on this context's device; `unique_id` = the 128 bytes of comm_unique_id() made on one rank."""
+        buf = C.create_string_buffer(bytes(unique_id), UNIQUE_ID_BYTES)
+        self._ck(self._L.b200m_comm_attach(self._h, int(n_ranks), int(rank), buf))
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
+
+    def upload_replicated(self, side, rows, dim):
+        """Collective: every rank passes the same HOST set, copies 1/ranks of it over PCIe; NVLink all-gather; pack."""
+        a, stride = _as_rows(rows)
+        self._ck(self._L.b200m_upload_replicated(self._h, side, a.ctypes.data, a.shape[0], stride, dim))
+        self.n[side] = a.shape[0]
+        self.dim = dim
+
+    def match_sharded(self, k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, thr_src=None, thr_tgt=None,
+                      precision=PREC_TC_F16, cand_cap=0):
+        """Collective, query-sharded: returns (this rank's slice of the correspondences, average over ALL source rows)."""
+        lo, hi = shard_rows(self.n[0], self.n_ranks, self.rank)
+        out = np.empty(max((hi - lo) * (k if mode == MODE_MUTUAL else 1), 1), CORR_DTYPE)
+        ts = None if thr_src is None else np.ascontiguousarray(thr_src, np.float32)
+        tt = None if thr_tgt is None else np.ascontiguousarray(thr_tgt, np.float32)
+        p = self._params(k, mode, ratio_thr, distance_thr, precision, cand_cap)
+        n_out, avg = C.c_size_t(0), C.c_float(0)
+        self._ck(self._L.b200m_match_sharded(self._h, C.byref(p), None if ts is None else ts.ctypes.data,
+                                             None if tt is None else tt.ctypes.data, out.ctypes.data, out.shape[0],
+                                             C.byref(n_out), C.byref(avg)))
+        return out[:n_out.value], float(avg.value)
+
+    def match_sharded_device(self, k, mode, out_ptr, cap, n_out_ptr, avg_ptr=0, thr_src=0, thr_tgt=0,
+                             ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, precision=PREC_TC_F16, cand_cap=0):
+        p = self._params(k, mode, ratio_thr, distance_thr, precision, cand_cap)
+        v = C.c_void_p
+        self._ck(self._L.b200m_match_sharded_device(self._h, C.byref(p), v(thr_src), v(thr_tgt), v(out_ptr), cap, v(n_out_ptr),
+                                                    v(avg_ptr)))
+
+    def knn_target_sharded_device(self, k, idx_ptr, dist_ptr, cnt_ptr, precision=PREC_TC_F16, cand_cap=0):
+        p = self._params(k, MODE_KNN_ONLY, precision=precision, cand_cap=cand_cap, shard=SHARD_TARGET)
+        v = C.c_void_p
+        self._ck(self._L.b200m_knn_target_sharded_device(self._h, C.byref(p), v(idx_ptr), v(dist_ptr), v(cnt_ptr)))
 
     # -- raw k-lists ----------------------------------------------------------
     def knn(self, k, direction=0, row_begin=0, row_end=0, precision=PREC_TC_F16, cand_cap=0):
@@ -411,6 +479,80 @@ class Context:
         out = np.empty((128, 256), np.float32)
         self._ck(self._L.b200m_debug_tc_tile(self._h, direction, q_row0, t_tile, out.ctypes.data))
         return out
+
+
+def comm_unique_id():
+    """128 bytes naming a new NCCL communicator (make it on one rank, hand it to all: Context.comm_attach)."""
+    L = load_library()
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    if L.b200m_comm_unique_id(buf, UNIQUE_ID_BYTES) != 0:
+        raise B200MatchError(L.b200m_last_error(None).decode())
+    return buf.raw
+
+
+def shard_rows(n, n_ranks, rank):
+    """The library's row partition: rank r owns [r*R, min(n, (r+1)*R)), R = ceil(n / ranks) (pure host code)."""
+    L = load_library()
+    lo, hi = C.c_size_t(0), C.c_size_t(0)
+    if L.b200m_shard_rows(int(n), int(n_ranks), int(rank), C.byref(lo), C.byref(hi)) != 0:
+        raise B200MatchError("shard_rows: bad rank")
+    return lo.value, hi.value
+
+
+class Group:
+    """b200m_create_multi: ONE process, one context + one host thread per device inside the library; whole host arrays in
+    and out -- the shape of the reference's single FeatureBasedMatcher::match() call (src/correspondence_search.cpp:14-15)."""
+
+    def __init__(self, devices):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        if self._L.b200m_create_multi(C.byref(self._h), ids, len(devices)) != 0:
+            raise B200MatchError(self._L.b200m_group_last_error(None).decode())
+        self.devices = list(devices)
+        self.n = [0, 0]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.b200m_destroy_multi(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise B200MatchError(self._L.b200m_group_last_error(self._h).decode())
+
+    def upload(self, side, rows, dim, sharded=False):
+        a, stride = _as_rows(rows)
+        self._keep = getattr(self, "_keep", {})
+        self._keep[side] = a
+        fn = self._L.b200m_group_upload_sharded if sharded else self._L.b200m_group_upload
+        self._ck(fn(self._h, side, a.ctypes.data, a.shape[0], stride, dim))
+        self.n[side] = a.shape[0]
+
+    def match(self, k, mode, ratio_thr=MATCHING_RATIO_THRESHOLD, distance_thr=FLT_MAX, thr_src=None, thr_tgt=None,
+              precision=PREC_TC_F16):
+        out = np.empty(max(self.n[0] * (k if mode == MODE_MUTUAL else 1), 1), CORR_DTYPE)
+        ts = None if thr_src is None else np.ascontiguousarray(thr_src, np.float32)
+        tt = None if thr_tgt is None else np.ascontiguousarray(thr_tgt, np.float32)
+        p = Context._params(k, mode, ratio_thr, distance_thr, precision)
+        n_out, avg = C.c_size_t(0), C.c_float(0)
+        self._ck(self._L.b200m_group_match(self._h, C.byref(p), None if ts is None else ts.ctypes.data,
+                                           None if tt is None else tt.ctypes.data, out.ctypes.data, out.shape[0],
+                                           C.byref(n_out), C.byref(avg)))
+        return out[:n_out.value], float(avg.value)
+
+    def knn(self, k, shard=SHARD_QUERY, precision=PREC_TC_F16):
+        nq = self.n[0]
+        idx, dist, cnt = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32), np.empty((nq,), np.int32)
+        p = Context._params(k, MODE_KNN_ONLY, precision=precision, shard=shard)
+        self._ck(self._L.b200m_group_knn(self._h, C.byref(p), idx.ctypes.data, dist.ctypes.data, cnt.ctypes.data))
+        return idx, dist, cnt
 
 
 # ---- the reference's free functions ------------------------------------------------------

@@ -11,6 +11,8 @@
 
 using namespace b200match;
 
+static int g_devices = 1;
+
 template <typename FeatureT>
 static std::vector<FeatureT> load(const char *path, size_t n) {
     std::vector<FeatureT> v(n);
@@ -124,15 +126,37 @@ static int run(char **argv) {
             fprintf(out, "\n");
         }
     }
+    // several GPUs (optional 9th argument): the same calls partitioned inside the library must give the same answers
+    if (g_devices > 1) {
+        AlignmentParameters pm;
+        pm.randomness = std::stoi(argv[6]);
+        for (int d = 0; d < g_devices; ++d) pm.devices.push_back(d);
+        auto bf = matchBF<FeatureT>(src, tgt, pm);
+        if (bf.size() != ns) abort();
+        for (size_t i = 0; i < ns; ++i) {
+            fprintf(out, "mknn %zu %zu", i, bf[i].match_indices.size());
+            for (size_t m = 0; m < bf[i].match_indices.size(); ++m) fprintf(out, " %d %.9g", bf[i].match_indices[m], bf[i].distances[m]);
+            fprintf(out, "\n");
+        }
+        pm.randomness = 1;
+        for (const char *id : {"one_sided", "lr"}) {
+            pm.matching_id = id;
+            auto matcher = getFeatureBasedMatcherFromParameters<FeatureT>(Impl::makeStorage(src), Impl::makeStorage(tgt), pm);
+            auto corrs = matcher->match();
+            fprintf(out, "matcher m_%s %s %zu %.9g\n", id, matcher->getClassName().c_str(), corrs->size(), matcher->getAverageDistance());
+            for (const auto &c : *corrs) fprintf(out, "corr m_%s %d %d %.9g\n", id, c.index_query, c.index_match, c.distance);
+        }
+    }
     fclose(out);
     return 0;
 }
 
 int main(int argc, char **argv) {
-    if (argc != 8) {
-        std::cerr << "usage: shim_test <fpfh|shot|rops> src.bin n_src tgt.bin n_tgt k out.txt\n";
+    if (argc != 8 && argc != 9) {
+        std::cerr << "usage: shim_test <fpfh|shot|rops> src.bin n_src tgt.bin n_tgt k out.txt [n_gpus]\n";
         return 2;
     }
+    if (argc == 9) g_devices = std::stoi(argv[8]);
     try {
         if (!strcmp(argv[1], "fpfh")) return run<FPFHSignature33>(argv);
         if (!strcmp(argv[1], "shot")) return run<SHOT352>(argv);

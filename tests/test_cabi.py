@@ -35,7 +35,7 @@ def test_header_symbols_are_exported(lib):
 def test_struct_layouts_match_header():
     # b200m_corr == reference Correspondence (include/common.h:120-131): 16 bytes
     assert M.CORR_DTYPE.itemsize == 16
-    assert C.sizeof(M._Params) == 24
+    assert C.sizeof(M._Params) == 32     # k, mode, ratio_thr, distance_thr, precision, cand_cap, n_gpus, shard
     assert C.sizeof(M.Stats) == 6 * 8 + 7 * 8
 
 

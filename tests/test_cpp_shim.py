@@ -32,6 +32,11 @@ def test_shim_compiles_and_links():
     assert r.returncode == 2 and "usage" in r.stderr
 
 
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("desc,ns,nt,k", [("fpfh", 700, 900, 2), ("shot", 300, 420, 1), ("rops", 280, 300, 3)])
 def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
@@ -40,12 +45,14 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
     sp, tp, op = tmp_path / "s.bin", tmp_path / "t.bin", tmp_path / "o.txt"
     src.tofile(sp)
     tgt.tofile(tp)
-    r = subprocess.run([exe, desc, str(sp), str(ns), str(tp), str(nt), str(k), str(op)], capture_output=True, text=True)
+    n_gpus = min(_n_gpus(), 8)     # with several GPUs visible the program also runs its multi-GPU section (b200m_create_multi)
+    r = subprocess.run([exe, desc, str(sp), str(ns), str(tp), str(nt), str(k), str(op)] + ([str(n_gpus)] if n_gpus > 1 else []),
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     s_d, t_d = src[:, :dim], tgt[:, :dim]
     exp = {0: orc.knn(s_d, t_d, k), 1: orc.knn(t_d, s_d, k)}
-    got_corr = {"one_sided": [], "lr": [], "ratio": [], "cluster": [], "lr2": []}
-    got_ms, got_local = {}, {}
+    got_corr = {"one_sided": [], "lr": [], "ratio": [], "cluster": [], "lr2": [], "m_one_sided": [], "m_lr": []}
+    got_ms, got_local, got_mknn = {}, {}, {}
     heads = {}
     n_knn = 0
     for line in open(op):
@@ -63,6 +70,8 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
             got_corr[w[1]].append((int(w[2]), int(w[3]), np.float32(w[4])))
         elif w[0] == "ms":
             got_ms[int(w[1])] = [(int(a), np.float32(b)) for a, b in zip(w[3::2], w[4::2])]
+        elif w[0] == "mknn":
+            got_mknn[int(w[1])] = [(int(a), np.float32(b)) for a, b in zip(w[3::2], w[4::2])]
         elif w[0] == "local":
             got_local[int(w[1])] = [(int(a), np.float32(b)) for a, b in zip(w[3::2], w[4::2])]
     assert n_knn == ns + nt
@@ -107,3 +116,12 @@ def test_cpp_shim_matches_oracle(tmp_path, desc, ns, nt, k):
     assert len(got_local) == ns and lc.min() < k   # the gate bites somewhere
     for i in range(ns):
         assert got_local[i] == [(int(li[i, m]), np.float32(ld[i, m])) for m in range(lc[i])]
+    if n_gpus > 1:   # the multi-GPU section: same answers as one GPU / the oracle
+        idx, dist, cnt = exp[0]
+        assert len(got_mknn) == ns
+        for i in range(ns):
+            assert got_mknn[i] == [(int(idx[i, m]), np.float32(dist[i, m])) for m in range(cnt[i])]
+        for mid, mode in (("m_one_sided", "one_sided"), ("m_lr", "mutual")):
+            e, eavg = orc.match(s_d, t_d, 1, mode, 1.1, fmax)
+            assert heads[mid][1] == len(e) and heads[mid][2] == np.float32(eavg)
+            assert got_corr[mid] == triples(e)

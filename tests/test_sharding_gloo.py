@@ -145,11 +145,17 @@ def test_sharded_matcher_two_ranks_gloo(desc, ns, nt, k):
             assert np.array_equal(a, b)
 
 
-def test_shard_bounds_cover_and_balance():
-    for n in (0, 1, 7, 8, 500000, 500001):
+def test_shard_bounds_cover_and_match_the_library():
+    """Contiguous cover of [0, n); every rank but the last non-empty one holds ceil(n / world) rows (so that all-gathered
+    slots are the row-major table of all rows); identical to the library's own partition (b200m_shard_rows: host code)."""
+    from lidar_global_registration_b200 import build as b200_build
+    from lidar_global_registration_b200 import matcher as M
+    b200_build.build()
+    for n in (0, 1, 7, 8, 10, 500000, 500001):
         for w in (1, 2, 3, 8):
             b = [D.shard_bounds(n, r, w) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
-            sizes = [hi - lo for lo, hi in b]
-            assert max(sizes) - min(sizes) <= 1
+            per = -(-n // w)
+            assert all(hi - lo == per for lo, hi in b if hi < n)
+            assert b == [M.shard_rows(n, w, r) for r in range(w)]
