@@ -900,10 +900,19 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c
             int col_base = (t0 + bsel) * B200M_TILE_N + half * 64;
             uint32_t par = 0;
+            // B200M_TC_DEBUG & 512: where this warp's cycles go -- [phase: first 64 tiles / the rest][wait for the accumulators,
+            // values in registers + first scan (on the hand-off chain), everything after the hand-back], and how many
+            // batches took the hit path in some lane
+            const bool prof = DBG && (dflags & 512) != 0;
+            long long cyc[2][3] = {{0, 0, 0}, {0, 0, 0}};
+            int hits[2][2] = {{0, 0}, {0, 0}};
             for (int lt = bsel; lt < t1 - t0; lt += 2, col_base += 2 * B200M_TILE_N) {
+                const int ph = lt < 64 ? 0 : 1;
+                long long c0 = prof ? clock64() : 0;
                 mbar_wait(e_tfull, par);
                 par ^= 1u;
                 tc_fence_after();
+                if (prof) { const long long c1 = clock64(); cyc[ph][0] += c1 - c0; c0 = c1; }
                 Hit64 h0;
                 bool hit0 = false;
                 if (!(dflags & 1)) {
@@ -925,6 +934,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(e_tempty);
+                if (prof) {
+                    const long long c1 = clock64();
+                    cyc[ph][1] += c1 - c0;
+                    c0 = c1;
+                    if (__any_sync(0xffffffffu, hit0)) ++hits[ph][0];
+                }
                 if (dflags & (1 | 32)) continue;
                 if (dflags & 256) {
                     if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
@@ -936,8 +951,21 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
                     st.thr = fminf(st.thr, fminf(fminf(t0_, t1_), fminf(t2_, t3_)));
                 }
-                process64<KT>(r0, r1, col_base + 128, st, k, out, cap);
+                if (prof) {
+                    Hit64 h1;
+                    const bool hit1 = scan64<KT>(r0, r1, col_base + 128, st, k, out, cap, h1);
+                    if (hit1) apply64<KT>(h1, col_base + 128, st, k, out, cap);
+                    if (__any_sync(0xffffffffu, hit1)) ++hits[ph][1];
+                    cyc[ph][2] += clock64() - c0;
+                } else {
+                    process64<KT>(r0, r1, col_base + 128, st, k, out, cap);
+                }
             }
+            if (prof && lane == 0 && blockIdx.x < 2 && blockIdx.y == 0)
+                printf("b200match epi-prof cta %d warp %2d (buf %d half %d) tiles<64: wait %lld chain %lld after %lld hits %d/%d | rest: "
+                       "wait %lld chain %lld after %lld hits %d/%d of %d batches each\n", blockIdx.x, warp, bsel, half, cyc[0][0],
+                       cyc[0][1], cyc[0][2], hits[0][0], hits[0][1], cyc[1][0], cyc[1][1], cyc[1][2], hits[1][0], hits[1][1],
+                       (t1 - t0 - 64) / 2);
         } else {
         uint32_t r0[32], r1[32], r2[32], r3[32];
         long long c_wait = 0, c_ld = 0, c_fast = 0, c_slow = 0;   // B200M_TC_DEBUG & 512: where this warp's cycles go
