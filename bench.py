@@ -38,12 +38,28 @@ WORKLOADS = {
     "c5": ("shot", 500000, 1000000, 2, "knn_target_sharded",
            "SHOT-352 kNN k=2, 500k queries x (1M target rows per GPU), target-sharded + NCCL top-k merge (BASELINE configs[4])"),
 }
-METRIC = "descriptor queries/sec (k=2 + mutual)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE candidate-kernel launch, from the ncu --set full capture of the
-# same workload on 1 GPU (profiles/r01b_ncu_c3_cand.txt, profiles/r01c_ncu_c2_cand.txt).  The kernel is tensor bound; the traffic is the FP16 train
-# operand array streaming through L2 once per wave of query tiles (algorithmic operand bytes: 0.77 GB for c3).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c3": 19.784716e9 + 219.15264e6, "c2": 61.222400e6 + 21.200384e6}
-NCU_TRAFFIC_SOURCE = {"c3": "profiles/r01b_ncu_c3_cand.txt", "c2": "profiles/r01c_ncu_c2_cand.txt"}
+METRICS = {
+    "c1": "descriptor queries/sec (FPFH-33 k=1 + mutual)",
+    "c2": "descriptor queries/sec (FPFH-33 k=2 + ratio)",
+    "c3": "descriptor queries/sec (k=2 + mutual)",          # BASELINE.json's metric string, quoted on configs[2]
+    "c3s": "descriptor queries/sec (k=2 + mutual, reduced size)",
+    "c4": "descriptor queries/sec (FPFH-33 k=5 + mutual)",
+    "c5": "descriptor queries/sec (SHOT-352 k=2 kNN, target-sharded)",
+}
+
+
+def ncu_traffic(wl):
+    """dram__bytes_read.sum + dram__bytes_write.sum per candidate-kernel launch, read at run time from the committed ncu
+    --set full summary of the same workload on 1 GPU (profiles/ncu_traffic.json names the summary file per workload;
+    tools/ncu_traffic.py regenerates it from the .ncu-rep).  None when there is no capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        e = json.load(open(p)).get(wl)
+    except Exception:
+        return None, None
+    if not e:
+        return None, None
+    return float(e["bytes_per_launch"]), "%s (%s)" % (e["source"], e.get("note", "ncu --set full, 1 GPU"))
 
 
 def peaks():
@@ -192,14 +208,32 @@ def run_reference(args, wl):
             rates.append(r)
             secs_all.append(secs)
     value = float(np.mean(rates))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRICS[wl], "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs_all)),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg, "timing": "wall clock around the CPU matcher call, bounded query sample per step"},
+            "config": workload_config(wl, max(args.gpus, 1)),
+            "timing": "wall clock around the CPU matcher call, bounded query sample per step",
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+DIMS = {"fpfh": (33, 132), "shot": (352, 1444), "rops": (135, 540)}   # descriptor length, sizeof(FeatureT) as PCL lays it out
+
+
+def workload_config(wl, world):
+    """`config` of a workload: identical on both arms (the driver compares them), nothing run-specific in it."""
+    desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
+    dim, stride_b = DIMS[desc]
+    tsharded = mode_name == "knn_target_sharded"
+    return {"workload": cfg, "descriptor": desc, "dim": dim, "n_src": n_src, "n_tgt": n_tgt, "k": k, "filter": mode_name,
+            "row_stride_bytes": stride_b,
+            "sharding": (("target-sharded (n_tgt rows per rank, %d in total), queries replicated, NCCL all-gather + merge"
+                          % (n_tgt * world)) if tsharded else
+                         ("query-sharded, target replicated" if world > 1 else "single GPU")),
+            "l2": ("inputs larger than L2 (no flush needed)" if n_tgt * dim * 2 > 126e6 else
+                   "inputs smaller than L2; the step rewrites >126 MB of operands/candidates between kNN passes")}
 
 
 # ------------------------------------------------------------------------------------------
@@ -211,10 +245,6 @@ def run_b200(args, wl):
     from lidar_global_registration_b200 import matcher as M
     from lidar_global_registration_b200 import synth
 
-    desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
-    tsharded = mode_name == "knn_target_sharded"
-    mode = {"mutual": M.MODE_MUTUAL, "ratio": M.MODE_RATIO, "one_sided": M.MODE_ONE_SIDED,
-            "knn_target_sharded": M.MODE_KNN_ONLY}[mode_name]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -222,12 +252,10 @@ def run_b200(args, wl):
         raise SystemExit("bench.py: no CUDA device; the B200 matcher has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    group = None
     if world > 1:
-        if "B200M_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["B200M_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)   # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line)
+        # NCCL_DEBUG stays as the caller set it; its log goes to stderr so that stdout carries the ONE JSON line only
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
@@ -235,23 +263,9 @@ def run_b200(args, wl):
     if world > 1:
         dist.barrier()
     be = D.GpuBackend(local_rank)
-    sm = D.ShardedMatcher(be, rank, world, group)
-
-    # target-sharded: every rank generates its own shard of n_tgt rows (seeded by rank), global row offset rank * n_tgt
-    src, tgt, dim = synth.make_pair_torch(desc, n_src, n_tgt, dev)
-    if tsharded and rank > 0:   # a different shard per rank: the common recipe, rows rotated and slightly rescaled
-        tgt = (torch.roll(tgt, shifts=1237 * rank, dims=0) * (1.0 + 2e-3 * rank)).contiguous()
-    stride_b = src.stride(0) * 4
-    t_off = rank * n_tgt if tsharded else 0
-    torch.cuda.synchronize()
-
-    def step_device():
-        be.upload_device(0, src, dim)
-        be.upload_device(1, tgt, dim, index_offset=t_off)
-        if tsharded:
-            idx, dst, cnt = sm.knn_target_sharded(k)
-            return idx, cnt.sum(), dst
-        return sm.match_query_sharded(k, mode)
+    sm = D.ShardedMatcher(be, rank, world, None)    # world > 1: attaches the library's own NCCL communicator
+    modes = {"mutual": M.MODE_MUTUAL, "ratio": M.MODE_RATIO, "one_sided": M.MODE_ONE_SIDED, "knn_target_sharded": M.MODE_KNN_ONLY}
+    pk = peaks()
 
     def barrier():
         torch.cuda.synchronize()
@@ -274,101 +288,172 @@ def run_b200(args, wl):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    # ---- device-resident value (per-kernel CUDA events are recorded on the stream without host syncs) ----
-    be.ctx.set_profiling(True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    be.ctx.reset_stats()
-    ms_total, out = timed(step_device, args.steps, sampler)
-    clocks = sampler.stop() if sampler else None
-    st = be.ctx.stats()
-    be.ctx.set_profiling(False)
-    launches = st["launches"]
-    n_corr = int(out[1].item())
-    value = n_src * args.steps / (ms_total * 1e-3)
+    def measure(wl, steps, warmup, with_e2e, with_clocks):
+        """Device-resident value + candidate-kernel roofline (+ e2e through the host-facing C-ABI) of one workload."""
+        desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
+        tsharded = mode_name == "knn_target_sharded"
+        mode = modes[mode_name]
+        # target-sharded: every rank generates its own shard of n_tgt rows, global row offset rank * n_tgt
+        src, tgt, dim = synth.make_pair_torch(desc, n_src, n_tgt, dev)
+        if tsharded and rank > 0:   # a different shard per rank: the common recipe, rows rotated and slightly rescaled
+            tgt = (torch.roll(tgt, shifts=1237 * rank, dims=0) * (1.0 + 2e-3 * rank)).contiguous()
+        stride_b = src.stride(0) * 4
+        t_off = rank * n_tgt if tsharded else 0
+        torch.cuda.synchronize()
 
-    # ---- end to end through the host-facing C-ABI ----
-    src_h = src.cpu().pin_memory()
-    tgt_h = tgt.cpu().pin_memory()
-    kk = k if mode == M.MODE_MUTUAL else 1
-    q0, q1 = D.shard_bounds(n_src, rank, world)
-    out_h = torch.empty((max((q1 - q0) * kk, 1), 4), dtype=torch.int32).pin_memory()
-    lists_h = None
-    if tsharded:
+        def step_device():
+            be.upload_device(0, src, dim)
+            be.upload_device(1, tgt, dim, index_offset=t_off)
+            if tsharded:
+                idx, dst, cnt = sm.knn_target_sharded(k)
+                return idx, cnt.sum(), dst
+            if world == 1:
+                return be.match_device(k, mode)
+            return sm.match_query_sharded(k, mode)      # this rank's slice of the records stays in HBM (see config.note)
+
+        # ---- device-resident value (per-kernel CUDA events are recorded on the stream without host syncs) ----
+        be.ctx.set_profiling(True)
+        sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
+        for _ in range(max(warmup, 3)):
+            step_device()
+        be.ctx.reset_stats()
+        ms_total, out = timed(step_device, steps, sampler)
+        clocks = sampler.stop() if sampler else None
+        st = be.ctx.stats()
+        be.ctx.set_profiling(False)
+        n_corr = int(out[1].item())
+        res = {"value": n_src * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps, "launches": int(st["launches"]),
+               "clocks": clocks, "dim": dim, "stride_b": stride_b, "n_corr": n_corr}
+
+        # ---- roofline of the dominant kernel (tcgen05 candidate pass): CUDA events around every launch of the timed
+        #      region above, on the stream the kernel is launched on ----
+        both = mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL)
+        q0, q1 = D.shard_bounds(n_src, rank, world)
+        t0, t1 = D.shard_bounds(n_tgt, rank, world)
+        pairs_per_step = float((q1 - q0) * n_tgt + ((t1 - t0) * n_src if both else 0))
+        if tsharded:   # every rank: all queries against its own target shard
+            pairs_per_step = float(n_src) * n_tgt
+        # the pairs the candidate kernel actually scored: the masked reverse pass answers only the target rows that forward
+        # lists name (st["pairs_scored"] = sum over the launches of rows searched x train rows)
+        if st.get("pairs_scored", 0) > 0:
+            pairs_per_step = st["pairs_scored"] / steps
+        flops_per_step = 2.0 * dim * pairs_per_step
+        kpad = (dim + 3 + 15) // 16 * 16           # K the tensor cores actually contract over: D + 3 norm columns, padded to K = 16 steps
+        cand_ms = st["ms_candidates"] / steps
+        achieved = flops_per_step / (cand_ms * 1e-3) / 1e12 if cand_ms > 0 else 0.0
+        n_launch = st["candidate_launches"] / steps
+        traffic, traffic_src = ncu_traffic(wl) if world == 1 else (None, None)
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        hw_peak = 148 * 8192.0 * sm_clock * 1e6 / 1e12      # tcgen05 kind::f16: 8192 dense FLOP per SM per cycle
+        roofline = {"bound": "tensor", "kernel": "tc_candidates_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    "peak_source": pk["source"] + ", bf16_tflops_sustained (kernel timed inside a long step; a cuBLAS measurement "
+                                   "under the power cap, so a kernel that sustains a higher clock can exceed it)",
+                    "frac_of_burst": achieved / pk["bf16_burst"],
+                    "frac_of_hw_peak_at_clock": achieved / hw_peak,
+                    "hw_peak_at_clock": {"value": hw_peak, "unit": "TFLOP/s", "sm_mhz": sm_clock,
+                                         "formula": "148 SMs x 8192 dense FP16 FLOP/cycle/SM x SM clock sampled under load"},
+                    "achieved_padded": achieved * kpad / dim,
+                    "padded_k": {"k_contracted": kpad, "dim": dim,
+                                 "note": "achieved counts 2*D*pairs (SURVEY 8d); the kernel contracts over D + 3 norm columns padded to 16"},
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "launch_ms": cand_ms / max(n_launch, 1), "launches_per_step": n_launch,
+                    "algorithmic_flops_per_step": flops_per_step,
+                    "breakdown_ms_per_step": {x: st[x] / steps for x in ("ms_pack", "ms_prepare", "ms_candidates", "ms_rerank",
+                                                                        "ms_fallback", "ms_filter")},
+                    "candidates_per_row": st["candidates"] / max(st.get("rows_answered") or st["rows_total"], 1),
+                    "query_rows_searched_frac": (st.get("rows_answered") or st["rows_total"]) / max(st["rows_total"], 1),
+                    "rows_overflowed_frac": st["rows_flagged"] / max(st["rows_total"], 1)}
+        # Second yardstick (SURVEY 8d: for short descriptors the limiter is the accumulator drain + select epilogue, not the
+        # tensor pipe): every (query, train) pair's accumulator has to pass the min pipe once.  Measured on this part
+        # (tools/ubench/min_ubench.cu): one three-input FMNMX3 (two new values per lane) per 2.25 cycles per scheduler.
+        select_peak = 148 * 4 * (64.0 / 2.25) * sm_clock * 1e6
+        select_ach = pairs_per_step / (cand_ms * 1e-3) if cand_ms > 0 else 0.0
+        roofline["select_epilogue"] = {"achieved": select_ach, "peak": select_peak, "unit": "pairs/s", "frac": select_ach / select_peak,
+                                       "peak_source": "148 SMs x 4 schedulers x 64 values per 2.25 cycles (measured FMNMX3 rate) x SM clock under load"}
+        res["roofline"] = roofline
+        if not with_e2e:
+            return res
+
+        # ---- end to end through the host-facing C-ABI: HOST descriptor buffers in, correspondence records on the host out ----
+        kk = k if mode == M.MODE_MUTUAL else 1
+        src_np, tgt_np = src.cpu().numpy(), tgt.cpu().numpy()              # pageable, as the reference's pcl::PointCloud is
+        src_pin, tgt_pin = torch.from_numpy(src_np).pin_memory(), torch.from_numpy(tgt_np).pin_memory()
+        e2e = {}
+        n_steps = max(2, min(steps, 5))
+        if world == 1:
+            # exactly the calls the C++ shim makes: b200m_upload x 2 + b200m_match (or b200m_knn for the raw k-lists)
+            out_np = np.empty(max(n_src * kk, 1), M.CORR_DTYPE)
+            for label, (s_h, t_h) in (("pinned", (src_pin.numpy(), tgt_pin.numpy())), ("pageable", (src_np, tgt_np))):
+                def step_e2e():
+                    be.ctx.upload(0, s_h, dim)
+                    be.ctx.upload(1, t_h, dim, index_offset=t_off)
+                    if tsharded:
+                        r = be.ctx.knn(k, 0)
+                        return (r[0].nbytes + r[1].nbytes + r[2].nbytes), None
+                    rec, _ = be.ctx.match(k, mode, out=out_np)
+                    return rec.shape[0] * 16 + 16, None
+                for _ in range(2):
+                    step_e2e()
+                ms, o = timed(step_e2e, n_steps)
+                e2e[label] = {"value": n_src * n_steps / (ms * 1e-3), "ms_per_step": ms / n_steps, "d2h": int(o[0])}
+            h2d = src_np.nbytes + tgt_np.nbytes
+            res["e2e"] = {"value": e2e["pinned"]["value"], "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": e2e["pinned"]["d2h"], "ms_per_step": e2e["pinned"]["ms_per_step"],
+                          "api": "b200m_upload x 2 + b200m_match (the calls include/b200match_shim.hpp makes), pinned host buffers",
+                          "pageable_host_buffers": {"value": e2e["pageable"]["value"], "ms_per_step": e2e["pageable"]["ms_per_step"],
+                                                    "note": "the same calls from ordinary (pageable) memory, as a pcl::PointCloud is"}}
+            return res
+        # N > 1: b200m_upload_replicated (1/N slice per rank over PCIe, NVLink all-gather) + b200m_match_sharded -- this rank's
+        # slice of the records lands in host memory; the slices in rank order are the single-GPU output
         lists_h = [torch.empty((n_src, k), dtype=torch.int32).pin_memory(), torch.empty((n_src, k), dtype=torch.float32).pin_memory(),
-                   torch.empty((n_src,), dtype=torch.int32).pin_memory()]
-    d2h = [0]
+                   torch.empty((n_src,), dtype=torch.int32).pin_memory()] if tsharded else None
+        moved = [0, 0]
 
-    h2d_rank = [0]
+        def step_e2e_multi():
+            if tsharded:   # queries replicated, this rank's own target shard
+                moved[0] = sm.upload_host_sharded(0, src_pin, dim) + be.upload_host(1, tgt_pin, dim, index_offset=t_off)
+                idx, dst, cnt = sm.knn_target_sharded(k)
+                lists_h[0].copy_(idx, non_blocking=True)
+                lists_h[1].copy_(dst, non_blocking=True)
+                lists_h[2].copy_(cnt, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                moved[1] = (lists_h[0].numel() + lists_h[1].numel() + lists_h[2].numel()) * 4 if rank == 0 else 0
+                return None, None
+            moved[0] = sm.upload_host_sharded(0, src_pin, dim) + sm.upload_host_sharded(1, tgt_pin, dim)
+            rec, _ = be.ctx.match_sharded(k, mode)
+            moved[1] = rec.shape[0] * 16 + 16
+            return None, None
+        for _ in range(2):
+            step_e2e_multi()
+        ms, _ = timed(step_e2e_multi, n_steps)
+        tot = torch.tensor(moved, device=dev, dtype=torch.int64)
+        dist.all_reduce(tot)
+        res["e2e"] = {"value": n_src * n_steps / (ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": int(tot[0].item()),
+                      "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": ms / n_steps,
+                      "api": "b200m_upload_replicated x 2 + b200m_match_sharded on every rank (pinned host buffers)",
+                      "replication": "each rank copies 1/N of a replicated set over PCIe, NCCL all-gather over NVLink"}
+        return res
 
-    def step_e2e():
-        if tsharded:   # queries replicated (slices over PCIe, all-gather over NVLink), this rank's own target shard
-            h2d_rank[0] = sm.upload_host_sharded(0, src_h, dim) + be.upload_host(1, tgt_h, dim, index_offset=t_off)
-        else:          # both sets replicated
-            h2d_rank[0] = sm.upload_host_sharded(0, src_h, dim) + sm.upload_host_sharded(1, tgt_h, dim)
-        if tsharded:
-            idx, dst, cnt = sm.knn_target_sharded(k)
-            lists_h[0].copy_(idx, non_blocking=True)
-            lists_h[1].copy_(dst, non_blocking=True)
-            lists_h[2].copy_(cnt, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            d2h[0] = (lists_h[0].numel() + lists_h[1].numel() + lists_h[2].numel()) * 4 if rank == 0 else 0
-            return idx, cnt, None
-        rec, n_out, _ = sm.match_query_sharded(k, mode)
-        n = int(n_out.item())                       # 8-byte D2H + sync: the count the caller needs
-        out_h[:n].copy_(rec[:n], non_blocking=True)
-        d2h[0] = n * 16 + 8
-        return rec, n_out, None
+    desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
+    tsharded = mode_name == "knn_target_sharded"
+    main = measure(wl, args.steps, args.warmup, True, True)
 
-    for _ in range(2):
-        step_e2e()
-    e2e_steps = max(2, min(args.steps, 5))
-    ms_e2e, _ = timed(step_e2e, e2e_steps)
-    e2e_value = n_src * e2e_steps / (ms_e2e * 1e-3)
-    d2h_t = torch.tensor([d2h[0], h2d_rank[0]], device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(d2h_t)
-    h2d = int(d2h_t[1].item())   # bytes all ranks together copied host -> device per step
-
-    # ---- roofline of the dominant kernel (tcgen05 candidate pass): CUDA events around every launch of the
-    #      timed region above, on the stream the kernel is launched on ----
-    both = mode in (M.MODE_MUTUAL, M.MODE_RATIO_MUTUAL)
-    t0, t1 = D.shard_bounds(n_tgt, rank, world)
-    flops_per_step = 2.0 * dim * ((q1 - q0) * n_tgt + ((t1 - t0) * n_src if both else 0))
-    if tsharded:   # every rank: all queries against its own target shard
-        flops_per_step = 2.0 * dim * n_src * n_tgt
-    # FLOPs the candidate kernel actually had to do: the masked reverse pass answers only the target rows that forward
-    # lists name (st["pairs_scored"] = sum over the launches of rows searched x train rows)
-    if st.get("pairs_scored", 0) > 0:
-        flops_per_step = 2.0 * dim * st["pairs_scored"] / args.steps
-    cand_ms_per_step = st["ms_candidates"] / args.steps
-    pk = peaks()
-    achieved = flops_per_step / (cand_ms_per_step * 1e-3) / 1e12 if cand_ms_per_step > 0 else 0.0
-    n_launch = st["candidate_launches"] / args.steps
-    roofline = {"bound": "tensor", "kernel": "tc_candidates_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(wl) if world == 1 else None,
-                "traffic_source": "bytes per launch, %s (ncu --set full, 1 GPU)" % NCU_TRAFFIC_SOURCE.get(wl, "-")
-                                  if world == 1 and wl in NCU_TRAFFIC_BYTES_PER_LAUNCH else None,
-                "peak_source": pk["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
-                "launch_ms": cand_ms_per_step / max(n_launch, 1), "launches_per_step": n_launch,
-                "algorithmic_flops_per_step": flops_per_step,
-                "breakdown_ms_per_step": {x: st[x] / args.steps for x in ("ms_pack", "ms_prepare", "ms_candidates", "ms_rerank",
-                                                                     "ms_fallback", "ms_filter")},
-                "candidates_per_row": st["candidates"] / max(st.get("rows_answered") or st["rows_total"], 1),
-                "query_rows_searched_frac": (st.get("rows_answered") or st["rows_total"]) / max(st["rows_total"], 1),
-                "rows_overflowed_frac": st["rows_flagged"] / max(st["rows_total"], 1)}
-
-    # Second yardstick (for short descriptors the limiter is the accumulator drain + select epilogue, not the
-    # tensor pipe): every (query, train) pair's accumulator has to pass the min pipe once.  Measured on this part
-    # (tools/ubench/min_ubench.cu): one three-input FMNMX3 (two new values per lane) per 2.25 cycles per scheduler.
-    pairs_per_step = flops_per_step / (2.0 * dim)
-    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    select_peak = 148 * 4 * (64.0 / 2.25) * sm_clock * 1e6
-    select_ach = pairs_per_step / (cand_ms_per_step * 1e-3) if cand_ms_per_step > 0 else 0.0
-    roofline["select_epilogue"] = {"achieved": select_ach, "peak": select_peak, "unit": "pairs/s", "frac": select_ach / select_peak,
-                                   "peak_source": "148 SMs x 4 schedulers x 64 values per 2.25 cycles (measured FMNMX3 rate) x SM clock under load"}
+    # the other single-GPU BASELINE configs, embedded so that a default run shows them too (fewer steps, no e2e)
+    others = {}
+    if world == 1 and wl == "c3" and not args.no_other_configs:
+        for owl, osteps in (("c2", 10), ("c4", 3)):
+            try:
+                torch.cuda.empty_cache()
+                o = measure(owl, osteps, 3, False, True)
+                od = WORKLOADS[owl]
+                others[owl] = {"metric": METRICS[owl], "value": o["value"], "unit": "queries/s", "ms_per_step": o["ms_per_step"],
+                               "steps": osteps, "config": workload_config(owl, world), "correspondences": o["n_corr"],
+                               "clocks": o["clocks"], "roofline": o["roofline"],
+                               "parity_note": "ratio filter: defined here, the reference's RatioMatcher is a stub (parity unpinned)"
+                                              if od[4] == "ratio" else None}
+            except Exception as e:   # an embedded extra must never cost the headline line
+                others[owl] = {"error": str(e)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -376,23 +461,18 @@ def run_b200(args, wl):
         cpu = {"value": r, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample, "seconds": secs}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        note = None
+        if world > 1 and not tsharded:
+            note = ("the timed step leaves every rank's slice of the records in its own HBM (ascending index_query; the slices in "
+                    "rank order are the single-GPU output); gathering them to one rank (8 MB for c3) is outside the timed region")
+        line = {"metric": METRICS[wl], "value": main["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak" if tsharded else "strong", "vs_baseline": None,
                 "dtype": "f32 (FP16 tensor-core candidates, exact FP32 re-rank)",
                 "data": "synthetic",
-                "config": {"workload": cfg, "descriptor": desc, "dim": dim, "n_src": n_src, "n_tgt": n_tgt, "k": k,
-                           "filter": mode_name, "row_stride_bytes": stride_b, "correspondences": n_corr,
-                           "sharding": ("target-sharded (n_tgt rows per rank, %d in total), queries replicated, NCCL all-gather + merge"
-                                        % (n_tgt * world)) if tsharded else
-                                       ("query-sharded, target replicated" if world > 1 else "single GPU"),
-                           "l2": "inputs larger than L2 (no flush needed)" if n_tgt * dim * 2 > 126e6 else
-                                 "inputs smaller than L2; the step rewrites >126 MB of operands/candidates between kNN passes"},
-                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h_t[0].item()), "ms_per_step": ms_e2e / e2e_steps,
-                        "replication": "each rank copies 1/N of a replicated set over PCIe, NCCL all-gather over NVLink"
-                                       if world > 1 else "single GPU"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "config": workload_config(wl, world), "correspondences": main["n_corr"], "note": note,
+                "e2e": main["e2e"], "gpu_launches": main["launches"], "clocks": main["clocks"], "roofline": main["roofline"],
+                "cpu_baseline": cpu, "other_configs": others or None}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -408,6 +488,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the embedded c2 / c4 lines of a default (c3, 1 GPU) run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, args.workload)

@@ -59,3 +59,18 @@ def test_short_region_falls_back_to_nearest_samples_and_says_so():
 def test_no_lines_is_reported():
     out = _sampler_with([], time.time()).stop()
     assert out["reasons"] == ["no samples"]
+
+
+def test_both_arms_describe_the_workload_with_the_same_config():
+    for wl in bench.WORKLOADS:
+        assert wl in bench.METRICS
+        for world in (1, 8):
+            c = bench.workload_config(wl, world)
+            assert c["workload"] == bench.WORKLOADS[wl][5] and c["dim"] in (33, 135, 352)
+            assert set(c) == {"workload", "descriptor", "dim", "n_src", "n_tgt", "k", "filter", "row_stride_bytes", "sharding", "l2"}
+
+
+def test_roofline_traffic_is_read_from_a_committed_profile():
+    b, src = bench.ncu_traffic("c3")
+    assert b and b > 1e9 and os.path.exists(os.path.join(ROOT, src.split(" ")[0]))
+    assert bench.ncu_traffic("no-such-workload") == (None, None)
