@@ -36,7 +36,7 @@ namespace {
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
-constexpr int kTailBytes = 3072;         // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B)
+constexpr int kTailBytes = 5120;         // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B) + row constants (2 KB)
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
@@ -262,7 +262,8 @@ struct RowState {
     float tk[KT];   // k smallest accumulator values this thread has seen (of distinct columns), ascending
     float T;        // tk[k - 1], cached: the k-th smallest (+inf until k values are known)
     float thr;      // effective append threshold: min(own threshold, the partner thread's published one)
-    float na, eta, slop, gfac;
+    uint32_t s_const;     // shared: the row's certificate constants {na, eta, slop, gfac} (read when the threshold is re-derived:
+                          // rare, so they stay out of the register file)
     int cnt;              // entries appended to this thread's own list (may run past cap: overflow)
     uint32_t s_thr_own;   // shared: where this thread publishes its own threshold (EH = 2: read by the thread that
                           // filters the other half of this row's columns)
@@ -302,7 +303,9 @@ __device__ __forceinline__ void tk_insert(RowState<KT> &st, float v) {
 template <int KT, int EH>
 __device__ __forceinline__ void retighten(RowState<KT> &st, int k) {
     st.T = kth_smallest<KT>(st, k);
-    const float thr_own = cand_threshold(st.T, st.na, st.eta, st.slop, st.gfac);
+    float na, eta, slop, gfac;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(na), "=f"(eta), "=f"(slop), "=f"(gfac) : "r"(st.s_const) : "memory");
+    const float thr_own = cand_threshold(st.T, na, eta, slop, gfac);
     st.thr = fminf(st.thr, thr_own);
     if (EH == 2) sts_f32(st.s_thr_own, thr_own);
 }
@@ -425,6 +428,9 @@ __device__ __forceinline__ void process128(const uint32_t (&r0)[32], const uint3
 // columns under the threshold -- two-level: eight-column group minima first, so that a typical hit costs 16 + 8 compares
 // instead of 64) and what does not (apply64: appends from the masks, k-smallest list, threshold).  The alternating-tile
 // epilogue runs only scan64 of its first batch before the accumulators go back to the MMA issuer.
+// (Tried and measured slower, C2 launch 3.78 -> 5.50 ms: moving 12 of every 32 columns of the "any column under the
+// threshold?" test to FMA-pipe indicators sat(2^40 (thr - v)) summed with FADDs, to relieve the half-rate ALU pipe the four
+// epilogue warps of a scheduler share -- profiles/r02_notes.md.)
 struct Hit64 {
     uint32_t mask0, mask1;   // columns of the two 32-column chunks under the threshold at scan time
     float m0, m1;            // chunk minima
@@ -545,6 +551,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t bar_tempty0 = bar_tfull0 + 8u * kAcc;                  // SPLITN: index buf * 2 + half
     const uint32_t tmem_slot = bar_tempty0 + 8u * kAcc;
     const uint32_t s_thr = (tmem_slot + 8u + 15u) & ~15u;                // published thresholds: [2][128] f32 per column half; ALT: [128][4]
+    const uint32_t s_rowc = s_thr + 2048u;                               // [128][4] f32: per-row certificate constants
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -684,14 +691,22 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint32_t nk = nk_last;
                 uint32_t ph = 0;
                 int lt = 0;
+                // trace builds: cycle stamps of kTraceTiles tiles -- before the waits, operands landed, half handed back, issued
+                const bool trace = kTraceBuild && (dflags & 1024) && blockIdx.x == 0 && blockIdx.y == 0;
+                long long tr[kTraceBuild ? kTraceTiles : 1][4];
                 while (lt < nt) {
 #pragma unroll
                     for (int i = 0; i < kMaxStages; ++i) {
                         if (lt + i < nt) {
                             const uint32_t buf = (uint32_t) (i & 1);
+                            const int ti = lt + i - kTraceTile0;
+                            const bool tr_on = trace && ti >= 0 && ti < kTraceTiles;
+                            if (kTraceBuild && tr_on) tr[ti][0] = clock64();
                             mbar_wait(bar_full0 + 8u * (uint32_t) i, ph);
+                            if (kTraceBuild && tr_on) tr[ti][1] = clock64();
                             mbar_wait(bar_tempty0 + 8u * (buf * 2u + hf), (uint32_t) (((i >> 1) & 1) ^ 1));
                             tc_fence_after();
+                            if (kTraceBuild && tr_on) tr[ti][2] = clock64();
                             if (elect_one()) {
                                 const uint64_t db = desc_bh + (uint64_t) ((uint32_t) i * (uint32_t) ((kStageBytes / 2) >> 4));
                                 const uint32_t tmem_d = tmem_h + buf * (uint32_t) B200M_TILE_N;
@@ -703,11 +718,16 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                                 tc_commit_2sm_mcast(bar_tfull0 + 8u * (buf * 2u + hf), (uint16_t) 3);
                             }
                             __syncwarp();
+                            if (kTraceBuild && tr_on) tr[ti][3] = clock64();
                         }
                     }
                     lt += kMaxStages;
                     ph ^= 1u;
                 }
+                if (kTraceBuild && trace && lane == 0)
+                    for (int i = 0; i < kTraceTiles && kTraceTile0 + i < nt; ++i)
+                        printf("b200match trace issuer half %u tile %d: %lld %lld %lld %lld\n", hf, kTraceTile0 + i, tr[i][0], tr[i][1],
+                               tr[i][2], tr[i][3]);
             } else if (PAIR && EH == 2 && p.lean && !(DBG && (dflags & ~(1 | 32 | 256 | 512 | 131072 | 262144)))) {
                 // One-atom descriptors (FPFH-33: 3 MMAs = 384 tensor-pipe cycles per tile).  The general loop below costs
                 // this warp ~100 dependent instructions per tile (stage index in a vector register: R2UR moves, address
@@ -836,10 +856,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
             const float ab = sqrtf(na) + p.bmax;
-            st.na = na;
-            st.eta = ab * 4.8828125e-4f * 1.001953125f + 2.384185791015625e-7f * sqrtf((float) p.dim);
-            st.slop = ab * ab * 1.52587890625e-5f + 1e-6f;
-            st.gfac = 1.f + 2.2f * (float) (p.dim + 4) * 5.9604644775390625e-8f;
+            st.s_const = s_rowc + 16u * (uint32_t) row_in_tile;
+            // every thread of the row writes the same four values
+            sts_f32(st.s_const, na);
+            sts_f32(st.s_const + 4u, ab * 4.8828125e-4f * 1.001953125f + 2.384185791015625e-7f * sqrtf((float) p.dim));
+            sts_f32(st.s_const + 8u, ab * ab * 1.52587890625e-5f + 1e-6f);
+            sts_f32(st.s_const + 12u, 1.f + 2.2f * (float) (p.dim + 4) * 5.9604644775390625e-8f);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // shared row state initialised
         // every epilogue thread owns a private candidate list: [split][column half][row][cap]
@@ -886,7 +908,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
                 if (dflags & (1 | 32)) continue;
                 if (dflags & 256) {   // timing experiment: fast path only
-                    if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                    if (fminf(min32(r0), min32(r1)) < st.thr) st.cnt += 1;
                     continue;
                 }
                 process64<KT>(r0, r1, col_base, st, k, out, cap);
@@ -906,6 +928,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const bool prof = DBG && (dflags & 512) != 0;
             long long cyc[2][3] = {{0, 0, 0}, {0, 0, 0}};
             int hits[2][2] = {{0, 0}, {0, 0}};
+            // trace builds: accumulators seen, first batch scanned, second batch in registers, handed back, iteration done
+            const bool etrace = kTraceBuild && (dflags & 1024) && blockIdx.x < 2 && blockIdx.y == 0;
+            long long etr[kTraceBuild ? kTraceTiles / 2 + 1 : 1][5];
             for (int lt = bsel; lt < t1 - t0; lt += 2, col_base += 2 * B200M_TILE_N) {
                 const int ph = lt < 64 ? 0 : 1;
                 long long c0 = prof ? clock64() : 0;
@@ -913,6 +938,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 par ^= 1u;
                 tc_fence_after();
                 if (prof) { const long long c1 = clock64(); cyc[ph][0] += c1 - c0; c0 = c1; }
+                const int eti = (lt - kTraceTile0) >> 1;
+                const bool etr_on = kTraceBuild && etrace && lt >= kTraceTile0 && lt < kTraceTile0 + kTraceTiles;
+                if (kTraceBuild && etr_on) etr[eti][0] = clock64();
                 Hit64 h0;
                 bool hit0 = false;
                 if (!(dflags & 1)) {
@@ -921,19 +949,29 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tmem_ld_wait();
                     if (!(dflags & 32)) {
                         if (dflags & 256) {   // timing experiment: fast path only
-                            if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                            if (fminf(min32(r0), min32(r1)) < st.thr) st.cnt += 1;
+                        } else if ((dflags & (2048 | 4096)) && st.T != INFINITY) {
+                            // timing experiments (results invalid): no hit masks for the first batch -- the hand-off chain
+                            // carries the plain min pass only; threshold upkeep from the chunk minima stays
+                            h0.m0 = min32(r0);
+                            h0.m1 = min32(r1);
+                            h0.mask0 = h0.mask1 = 0u;
+                            hit0 = fminf(h0.m0, h0.m1) < st.thr;
                         } else {
                             hit0 = scan64<KT>(r0, r1, col_base, st, k, out, cap, h0);
                         }
                     }
+                    if (kTraceBuild && etr_on) etr[eti][1] = clock64();
                     tmem_ld_32x32b_x32(taddr + 64u, r0);
                     tmem_ld_32x32b_x32(taddr + 96u, r1);
                     tmem_ld_wait();
+                    if (kTraceBuild && etr_on) etr[eti][2] = clock64();
                 }
                 // all 128 columns are in registers or reduced to masks: the half goes back to its MMA issuer
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(e_tempty);
+                if (kTraceBuild && etr_on) etr[eti][3] = clock64();
                 if (prof) {
                     const long long c1 = clock64();
                     cyc[ph][1] += c1 - c0;
@@ -942,7 +980,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
                 if (dflags & (1 | 32)) continue;
                 if (dflags & 256) {
-                    if (fminf(min32(r0), min32(r1)) < st.thr) st.na += 1.f;
+                    if (fminf(min32(r0), min32(r1)) < st.thr) st.cnt += 1;
                     continue;
                 }
                 if (hit0) apply64<KT>(h0, col_base, st, k, out, cap);
@@ -951,7 +989,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
                     st.thr = fminf(st.thr, fminf(fminf(t0_, t1_), fminf(t2_, t3_)));
                 }
-                if (prof) {
+                if ((dflags & 4096) && st.T != INFINITY) {   // timing experiment: no masks / appends for the second batch either
+                    Hit64 h1;
+                    h1.m0 = min32(r0);
+                    h1.m1 = min32(r1);
+                    h1.mask0 = h1.mask1 = 0u;
+                    if (fminf(h1.m0, h1.m1) < st.thr) apply64<KT>(h1, col_base + 128, st, k, out, cap);
+                } else if (prof) {
                     Hit64 h1;
                     const bool hit1 = scan64<KT>(r0, r1, col_base + 128, st, k, out, cap, h1);
                     if (hit1) apply64<KT>(h1, col_base + 128, st, k, out, cap);
@@ -960,7 +1004,15 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 } else {
                     process64<KT>(r0, r1, col_base + 128, st, k, out, cap);
                 }
+                if (kTraceBuild && etr_on) etr[eti][4] = clock64();
             }
+            if (kTraceBuild && etrace && lane == 0)
+                for (int i = 0; i < kTraceTiles / 2; ++i) {
+                    const int tile = kTraceTile0 + 2 * i + ((bsel ^ (kTraceTile0 & 1)) & 1);
+                    if (tile < t1 - t0)
+                        printf("b200match trace epi cta %d warp %d buf %d half %d tile %d: %lld %lld %lld %lld %lld\n", blockIdx.x, warp, bsel,
+                               half, tile, etr[i][0], etr[i][1], etr[i][2], etr[i][3], etr[i][4]);
+                }
             if (prof && lane == 0 && blockIdx.x < 2 && blockIdx.y == 0)
                 printf("b200match epi-prof cta %d warp %2d (buf %d half %d) tiles<64: wait %lld chain %lld after %lld hits %d/%d | rest: "
                        "wait %lld chain %lld after %lld hits %d/%d of %d batches each\n", blockIdx.x, warp, bsel, half, cyc[0][0],
@@ -1028,7 +1080,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 if (dflags & 256) {   // timing experiment: fast path only
                     float m = fminf(fminf(min32(r0), min32(r1)), min32(r2));
                     if (!skip4) m = fminf(m, min32(r3));
-                    if (m < st.thr) st.na += 1.f;
+                    if (m < st.thr) st.cnt += 1;
                     if (tr_on) tr[ti][3] = clock64();
                     continue;
                 }
@@ -1051,7 +1103,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 printf("b200match trace epi cta %d warp %d tile %d: %lld %lld %lld %lld\n", blockIdx.x, warp, kTraceTile0 + i,
                        tr[i][0], tr[i][1], tr[i][2], tr[i][3]);
         }   // !ALT
-        if ((dflags & 256) && st.na == -1.f) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
+        if ((dflags & 256) && st.cnt == -1) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
         if (active && !dump) {
             p.cand_cnt[list_row] = st.cnt;
             if (EH == 1) p.cand_thr[list_row] = st.thr;
@@ -1205,7 +1257,10 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
     // ... with sixteen epilogue warps of 64 accumulators each: B200M_TC_ALT=2 (default) quarter columns of every tile,
     // hand-back before filtering; =1 alternating tiles; =0 eight warps of 128 accumulators, every warp on every tile
-    const int epi = splitn ? (ctx->tc_alt == 1 ? 1 : ctx->tc_alt != 0 ? 2 : 0) : 0;
+    // (measured, profiles/r02_cand_epilogue_modes.log: C2 k = 2 launch 4.10 / 3.78 / 4.02 ms and C4 k = 5 466 / 454 / 445 ms for
+    // eight warps / alternating tiles / quarter columns)
+    const int alt_pick = ctx->tc_alt >= 0 ? ctx->tc_alt : (k <= 4 ? 1 : 2);
+    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick != 0 ? 2 : 0) : 0;
     const bool alt = epi != 0;
     const int lists_per_split = eh * (alt ? 2 : 1);
     int n_splits = 1;
