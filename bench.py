@@ -254,8 +254,8 @@ def run_b200(args, wl):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # NCCL_DEBUG stays as the caller set it; its log goes to stderr so that stdout carries the ONE JSON line only
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # (the version banner included, whatever NCCL_DEBUG is or defaults to on the box)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
