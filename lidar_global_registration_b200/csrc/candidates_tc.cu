@@ -36,9 +36,9 @@ namespace {
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
-constexpr int kTailBytes = 14336;        // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B) + row
+constexpr int kTailBytes = 17696;        // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B) + row
                                          // constants (2 KB) + the hit ring of the worker-warp epilogue (control, flags, headers,
-                                         // 48 x 128 B of values) + 512 list counters
+                                         // 48 x 128 B of values) + 512 list counters + the lists' published smallest values (4 KB)
 constexpr int kRingCap = 48;             // hit-ring slots
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
@@ -269,6 +269,8 @@ struct RowState {
     uint32_t s_const;     // shared: the row's certificate constants {na, eta, slop, gfac} (read when the threshold is re-derived:
                           // rare, so they stay out of the register file)
     int cnt;              // entries appended to this thread's own list (may run past cap: overflow)
+    uint32_t s_pub_own;   // shared (EH = 2): where this thread publishes its two smallest values; the row's slots (one per list,
+                          // 8 bytes each) sit in one 32-byte line, so the other lists' slots follow from this address
     uint32_t s_thr_own;   // shared: where this thread publishes its own threshold (EH = 2: read by the thread that
                           // filters the other half of this row's columns)
 };
@@ -304,12 +306,33 @@ __device__ __forceinline__ void tk_insert(RowState<KT> &st, float v) {
         st.tk[s] = lo;
     }
 }
+// The threads that share a row (EH = 2: two or four private lists over disjoint columns) each know only the k smallest
+// values of their OWN columns; the k-th smallest of the row is at most the k-th smallest of any set of values of distinct
+// columns, so a thread merges the two smallest values the other lists have published into a copy of its own list before it
+// derives the threshold -- without this every list converges like a search over a quarter of the columns and the row
+// collects about twice the candidates (and hits) it needs.  Stale values only make the bound looser.
 template <int KT, int EH>
 __device__ __forceinline__ void retighten(RowState<KT> &st, int k) {
     st.T = kth_smallest<KT>(st, k);
+    float T = st.T;
+    if (EH == 2) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(st.s_pub_own), "f"(st.tk[0]), "f"(KT > 1 ? st.tk[KT > 1 ? 1 : 0] : INFINITY) : "memory");
+        RowState<KT> m;
+#pragma unroll
+        for (int s = 0; s < KT; ++s) m.tk[s] = st.tk[s];
+        const uint32_t row_slots = st.s_pub_own & ~31u, li = (st.s_pub_own >> 3) & 3u;
+#pragma unroll
+        for (uint32_t j = 1; j < 4; ++j) {
+            float a, b;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(row_slots + 8u * ((li + j) & 3u)) : "memory");
+            tk_insert<KT>(m, a);
+            tk_insert<KT>(m, b);
+        }
+        T = kth_smallest<KT>(m, k);
+    }
     float na, eta, slop, gfac;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(na), "=f"(eta), "=f"(slop), "=f"(gfac) : "r"(st.s_const) : "memory");
-    const float thr_own = cand_threshold(st.T, na, eta, slop, gfac);
+    const float thr_own = cand_threshold(T, na, eta, slop, gfac);
     st.thr = fminf(st.thr, thr_own);
     if (EH == 2) sts_f32(st.s_thr_own, thr_own);
 }
@@ -691,6 +714,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     ring.hdr = ring.ready + 4u * (uint32_t) kRingCap;
     ring.vals = ring.hdr + 16u * (uint32_t) kRingCap;
     ring.cnt = ring.vals + 128u * (uint32_t) kRingCap;
+    const uint32_t s_pub = (ring.cnt + 2048u + 31u) & ~31u;              // [128 rows][4 lists] x {smallest, second smallest} f32; a row's
+                                                                         // four slots share one 32-byte line (retighten relies on it)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
@@ -1007,6 +1032,11 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t s_thr_peer = ALT ? s_thr + 16u * (uint32_t) row_in_tile   // the row's four published thresholds
                                         : s_thr + 4u * (uint32_t) ((half ^ 1) * B200M_TILE_M + row_in_tile);
         sts_f32(st.s_thr_own, st.thr);
+        st.s_pub_own = s_pub + 32u * (uint32_t) row_in_tile + 8u * (uint32_t) (bsel * 2 + half);
+        if (EH == 2) {   // nothing published yet (slots of lists that do not exist stay at +inf)
+            if (!ALT) asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(st.s_pub_own + 16u), "f"(INFINITY) : "memory");
+            asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(st.s_pub_own), "f"(INFINITY) : "memory");
+        }
         const uint32_t list_slot = (uint32_t) ((bsel * 2 + half) * B200M_TILE_M + row_in_tile);   // EPI = 3: ring.cnt index
         if (RING) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring.cnt + 4u * list_slot), "r"(0u) : "memory");
         {
