@@ -222,6 +222,48 @@ def run_reference(args, wl):
 DIMS = {"fpfh": (33, 132), "shot": (352, 1444), "rops": (135, 540)}   # descriptor length, sizeof(FeatureT) as PCL lays it out
 
 
+def measure_local(torch, D, M, synth, dev, timed, n=200000, k=2, radius=2.5, box=100.0):
+    """queries/s of the guess-gated kNN (b200m_knn_local_device), descriptors and keypoints resident in HBM: FPFH-33
+    n x n, keypoints uniform in a box^3 cube (about n * 4/3 pi r^3 / box^3 = 13 train keypoints pass each query's gate)."""
+    import ctypes as C
+    src, tgt, dim = synth.make_pair_torch("fpfh", n, n, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(566)
+    qx = torch.zeros((n, 4), device=dev)
+    tx = torch.zeros((n, 4), device=dev)
+    qx[:, :3] = torch.rand((n, 3), device=dev, generator=g) * box
+    tx[:, :3] = torch.rand((n, 3), device=dev, generator=g) * box
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    dst = torch.empty((n, k), dtype=torch.float32, device=dev)
+    cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+    out = {"metric": "descriptor queries/sec (FPFH-33 k=2, matchLocal with match_search_radius)", "unit": "queries/s",
+           "config": {"workload": "FPFH-33 %d x %d k=%d, 3-D gate radius %.1f in a %.0f^3 cube (matchLocal, include/matching.h:637-678)"
+                                  % (n, n, k, radius, box), "n_src": n, "n_tgt": n, "k": k}}
+    for label, min_rows in (("cell_list", "1"), ("gate_against_all_rows", "1000000000")):
+        os.environ["B200M_LOCAL_MIN_ROWS"] = min_rows
+        be = D.GpuBackend(dev.index)
+        try:
+            be.upload_device(0, src, dim)
+            be.upload_device(1, tgt, dim)
+            p = be.ctx._params(k, M.MODE_KNN_ONLY)
+            v = C.c_void_p
+
+            def step():
+                be.ctx._ck(be.ctx._L.b200m_knn_local_device(be.ctx._h, C.byref(p), 0, v(qx.data_ptr()), v(tx.data_ptr()), 16,
+                                                            float(radius), v(idx.data_ptr()), v(dst.data_ptr()), v(cnt.data_ptr())))
+                return None, cnt
+            for _ in range(2):
+                step()
+            steps = 5 if label == "cell_list" else 2
+            ms, o = timed(step, steps)
+            out[label] = {"value": n * steps / (ms * 1e-3), "ms_per_call": ms / steps, "neighbours_found_per_query": float(cnt.float().mean().item())}
+        finally:
+            be.close()
+    os.environ.pop("B200M_LOCAL_MIN_ROWS", None)
+    out["value"] = out["cell_list"]["value"]
+    return out
+
+
 def workload_config(wl, world):
     """`config` of a workload: identical on both arms (the driver compares them), nothing run-specific in it."""
     desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
@@ -454,6 +496,14 @@ def run_b200(args, wl):
                                               if od[4] == "ratio" else None}
             except Exception as e:   # an embedded extra must never cost the headline line
                 others[owl] = {"error": str(e)[:300]}
+
+    # matchLocal with a finite search radius (include/matching.h:637-678) on the C2 shape: cell list vs the gate tested
+    # against every train row
+    if world == 1 and wl == "c3" and not args.no_other_configs:
+        try:
+            others["c2_local"] = measure_local(torch, D, M, synth, dev, timed)
+        except Exception as e:
+            others["c2_local"] = {"error": str(e)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

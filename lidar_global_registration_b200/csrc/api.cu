@@ -125,6 +125,7 @@ int b200m_create(b200m_ctx **out, int device) {
     if (const char *e = getenv("B200M_TC_SPLITN")) ctx->tc_splitn = atoi(e);
     if (const char *e = getenv("B200M_TC_ALT")) ctx->tc_alt = atoi(e);
     if (const char *e = getenv("B200M_TC_RING_FROM")) ctx->tc_ring_from = atoi(e);
+    if (const char *e = getenv("B200M_LOCAL_MIN_ROWS")) ctx->local_min_rows = atoi(e);
     if (const char *e = getenv("B200M_MASKED_MIN_PAIRS")) ctx->masked_min_pairs = atof(e);
     if (const char *e = getenv("B200M_TC_MODE")) {
         if (!strcmp(e, "mcast")) ctx->tc_pair = 0;
@@ -156,6 +157,7 @@ void b200m_destroy(b200m_ctx *ctx) {
     cluster_release(ctx);
     wide_release(ctx);
     comm_release(ctx);
+    local_release(ctx);
     if (ctx->pool) {
         if (ctx->pool->created)
             for (int i = 0; i < 2 * EventPool::kPairs; ++i) cudaEventDestroy(ctx->pool->ev[i]);
@@ -556,6 +558,14 @@ int b200m_knn_local_device(b200m_ctx *ctx, const b200m_params *p, int direction,
     }
     if (!d_query_xyz || !d_train_xyz) return b200m_fail_msg(ctx, "b200m_knn_local: null keypoint coordinates");
     StatTimer tf(ctx, &ctx->stats.ms_fallback);
+    {   // a radius that is small against the cloud: cell list of the train keypoints (local.cu)
+        const int rc = launch_local_cells(ctx, direction, d_query_xyz, d_train_xyz, xyz_stride_bytes, radius, p->k, d_idx, d_dist, d_count);
+        if (rc == 1) return 1;
+        if (rc == 0) {
+            tf.stop();
+            return 0;
+        }
+    }
     CK(launch_local_rows(q.f32.as<float>(), q.valid.as<uint8_t>(), q.dp, t.f32.as<float>(), t.valid.as<uint8_t>(), t.n,
                          t.index_offset, q.n, d_query_xyz, d_train_xyz, xyz_stride_bytes, radius, p->k, d_idx, d_dist, d_count,
                          1 << 30, ctx->stream));

@@ -69,6 +69,8 @@ struct b200m_ctx {
     void *cluster = nullptr;      // ClusterState (cluster.cu)
     void *wide = nullptr;         // WideState (wide.cu)
     void *comm = nullptr;         // Comm (multi.cu): this context's rank in an NCCL communicator
+    void *local = nullptr;        // LocalState (local.cu): the cell list of the gated kNN
+    int local_min_rows = 4096;    // B200M_LOCAL_MIN_ROWS: train sets below this use the brute-force gate kernel
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     double masked_min_pairs = 1e9;   // B200M_MASKED_MIN_PAIRS: b200m_match skips unreferenced target rows in the reverse pass
                                      // from this many (source, target) pairs on (below, the row selection's host round trip
@@ -196,6 +198,12 @@ void wide_release(b200m_ctx *ctx);
 
 // multi.cu
 void comm_release(b200m_ctx *ctx);
+
+// local.cu: matchLocal with a finite radius over a cell list of the train keypoints; 0 = done, 1 = error, 2 = not worth a
+// grid (the caller runs launch_local_rows)
+void local_release(b200m_ctx *ctx);
+int launch_local_cells(b200m_ctx *ctx, int direction, const float *d_query_xyz, const float *d_train_xyz, size_t xyz_stride_bytes,
+                       float radius, int k, int32_t *d_idx, float *d_dist, int32_t *d_count);
 
 // api.cu: kNN of query rows [row_begin, row_begin + n_rows) of `direction` on device buffers; with d_flags only the flagged
 // (and valid) rows are answered, the others get empty lists.  Outputs are indexed by (row - row_begin).

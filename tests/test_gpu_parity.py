@@ -516,10 +516,14 @@ def test_cluster_matcher_equals_oracle(desc, nq, nt, k, ck):
 
 @pytest.mark.parametrize("desc,nq,nt,k,radius", [("fpfh", 900, 1200, 2, 1.5), ("shot", 300, 500, 5, 3.0), ("rops", 250, 300, 1, 0.4),
                                                  ("fpfh", 400, 300, 3, 100.0)])
-def test_match_local_with_search_radius_equals_oracle(desc, nq, nt, k, radius):
+@pytest.mark.parametrize("path", ["cell-list", "all-rows"])
+def test_match_local_with_search_radius_equals_oracle(monkeypatch, desc, nq, nt, k, radius, path):
     """matchLocal with a finite match_search_radius (reference include/matching.h:637-678): only train rows whose keypoint
     is within the radius of the (transformed) query keypoint compete; lists shorter than k where the gate leaves fewer
-    rows; the last case's radius covers everything (== plain kNN up to the order of exactly tied distances)."""
+    rows; the last case's radius covers everything (== plain kNN up to the order of exactly tied distances).  Both device
+    paths: the cell list of the train keypoints (csrc/local.cu; radii 3.0 and 100 are too large for a grid of this cloud
+    and fall through to the other kernel by themselves) and the gate tested against every train row (csrc/exact.cu)."""
+    monkeypatch.setenv("B200M_LOCAL_MIN_ROWS", "1" if path == "cell-list" else "1000000000")
     src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
     rng = np.random.default_rng(5)
     qx = np.zeros((nq, 4), np.float32)
@@ -547,6 +551,31 @@ def test_match_local_with_search_radius_equals_oracle(desc, nq, nt, k, radius):
     got2 = M.match_local(src, tgt, params, dim=dim, query_kps_xyz=moved, train_kps_xyz=tx, guess=guess, match_search_radius=radius)
     back = moved[:, :3] @ guess[:3, :3].T + guess[:3, 3]
     _same(got2, orc.match_local(_dense(src, dim), _dense(tgt, dim), k, back, tx[:, :3], radius))
+
+
+@pytest.mark.parametrize("desc,nq,nt,k,radius", [("fpfh", 6000, 20000, 2, 0.9), ("shot", 1500, 9000, 3, 2.5)])
+def test_match_local_cell_list_on_a_clustered_cloud(monkeypatch, desc, nq, nt, k, radius):
+    """The cell-list path on a cloud big enough to use it by default: keypoints with dense clumps and empty space, NaN
+    coordinates, queries outside the train cloud's bounding box -- records equal the oracle's in both directions."""
+    src, tgt, dim = synth.make_pair(desc, nq, nt, nan_frac=0.01)
+    rng = np.random.default_rng(9)
+    qx = np.zeros((nq, 4), np.float32)
+    tx = np.zeros((nt, 4), np.float32)
+    tx[:, :3] = rng.random((nt, 3)) * np.float32([40, 25, 8])
+    tx[: nt // 5, :3] = tx[0, :3] + 0.3 * rng.standard_normal((nt // 5, 3)).astype(np.float32)     # a dense clump
+    qx[:, :3] = rng.random((nq, 3)) * np.float32([44, 27, 9]) - np.float32([2, 1, 0.5])                # some outside the box
+    qx[: nq // 5, :3] = tx[0, :3] + 0.4 * rng.standard_normal((nq // 5, 3)).astype(np.float32)
+    qx[7, 0] = np.nan
+    tx[11, 1] = np.nan
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        got = ctx.knn_local(k, qx, tx, radius)
+        got_rev = ctx.knn_local(k, tx, qx, radius, direction=1)
+    exp = orc.match_local(_dense(src, dim), _dense(tgt, dim), k, qx[:, :3], tx[:, :3], radius)
+    _same(got, exp)
+    _same(got_rev, orc.match_local(_dense(tgt, dim), _dense(src, dim), k, tx[:, :3], qx[:, :3], radius))
+    assert (exp[2] == 0).any() and (exp[2] == k).any() and got[2][7] == 0
 
 
 @pytest.mark.parametrize("workload", ["c2", "c3", "c4"])
