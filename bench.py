@@ -483,14 +483,18 @@ def run_b200(args, wl):
 
     # the other single-GPU BASELINE configs, embedded so that a default run shows them too (fewer steps, no e2e)
     others = {}
-    if world == 1 and wl == "c3" and not args.no_other_configs:
-        for owl, osteps in (("c2", 10), ("c4", 3)):
+    if wl == "c3" and not args.no_other_configs and (world == 1 or args.other_configs):
+        # 1 GPU: the two FPFH configs; several GPUs (only with --other-configs: a collective that fails on one rank must
+        # never cost the headline line): the two multi-GPU configs (C4 query-sharded, C5 target-sharded with n_tgt rows per
+        # rank -- 8M rows at 8 ranks, BASELINE configs[4])
+        for owl, osteps in ((("c2", 10), ("c4", 3)) if world == 1 else (("c4", 3), ("c5", 3))):
             try:
                 torch.cuda.empty_cache()
                 o = measure(owl, osteps, 3, False, True)
                 od = WORKLOADS[owl]
                 others[owl] = {"metric": METRICS[owl], "value": o["value"], "unit": "queries/s", "ms_per_step": o["ms_per_step"],
-                               "steps": osteps, "config": workload_config(owl, world), "correspondences": o["n_corr"],
+                               "steps": osteps, "n_gpus": world, "scaling": "weak" if od[4] == "knn_target_sharded" else "strong",
+                               "config": workload_config(owl, world), "correspondences": o["n_corr"],
                                "clocks": o["clocks"], "roofline": o["roofline"],
                                "parity_note": "ratio filter: defined here, the reference's RatioMatcher is a stub (parity unpinned)"
                                               if od[4] == "ratio" else None}
@@ -539,6 +543,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the embedded c2 / c4 lines of a default (c3, 1 GPU) run")
+    ap.add_argument("--other-configs", action="store_true", help="several GPUs: also embed the c4 (query-sharded) and c5 (target-sharded) lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, args.workload)
