@@ -70,6 +70,7 @@ struct b200m_ctx {
     void *wide = nullptr;         // WideState (wide.cu)
     void *comm = nullptr;         // Comm (multi.cu): this context's rank in an NCCL communicator
     void *local = nullptr;        // LocalState (local.cu): the cell list of the gated kNN
+    void *stage = nullptr;        // StagePool (api.cu): pinned bounce buffers for uploads from pageable host memory
     int local_min_rows = 4096;    // B200M_LOCAL_MIN_ROWS: train sets below this use the brute-force gate kernel
     int tc_cluster = 0;    // 0 = default; test/tuning override of the multicast cluster size (B200M_TC_CLUSTER)
     double masked_min_pairs = 1e9;   // B200M_MASKED_MIN_PAIRS: b200m_match skips unreferenced target rows in the reverse pass

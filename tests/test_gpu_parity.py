@@ -578,6 +578,20 @@ def test_match_local_cell_list_on_a_clustered_cloud(monkeypatch, desc, nq, nt, k
     assert (exp[2] == 0).any() and (exp[2] == k).any() and got[2][7] == 0
 
 
+def test_upload_from_pageable_memory_goes_through_the_bounce_buffers():
+    """b200m_upload of a large set from ordinary (pageable) host memory -- what a pcl::PointCloud is -- is staged through
+    pinned bounce buffers by several host threads (csrc/api.cu staged_h2d; 40 MB here = three chunks, the last one
+    partial): the descriptors must arrive intact, so the kNN against them equals the oracle's."""
+    src, tgt, dim = synth.make_pair("fpfh", 300000, 1500, nan_frac=0.001)
+    src = np.ascontiguousarray(src)          # numpy memory is pageable
+    assert src.nbytes >= 32 << 20
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        got = ctx.knn(2, 1)                  # the 1500 target rows against all 300k uploaded source rows
+    _same(got, orc.knn(_dense(tgt, dim), _dense(src, dim), 2))
+
+
 @pytest.mark.parametrize("workload", ["c2", "c3", "c4"])
 def test_full_size_workloads_match_oracle_on_sampled_rows(workload):
     """BASELINE.json's full sizes (C2 FPFH-33 200k x 200k k=2, C3 SHOT-352 500k x 500k k=2, C4 FPFH-33 2M x 2M k=5): the
