@@ -509,7 +509,8 @@ int b200m_knn_rows(b200m_ctx *ctx, const b200m_params *p, int direction, size_t 
                          ctx->ws_cand_cnt.as<int32_t>(), n_lists, cap,
                          has_values ? ctx->ws_cand_val.as<float>() : nullptr,
                          has_values ? ctx->ws_cand_thr.as<float>() : nullptr, d_idx, d_dist, d_count,
-                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), ctx->sm_count, row_map, st));
+                         ctx->ws_flag_rows.as<int32_t>(), ctx->ws_counters.as<int32_t>(), ctx->sm_count, row_map,
+                         has_values == 2 ? 1 : 0, st));
         ctx->stats.launches += 1;
         tr.stop();
     }

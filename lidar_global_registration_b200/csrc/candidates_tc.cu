@@ -230,6 +230,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, tied to the 32 registers of the load it completes: in the software-pipelined drain of the chunk epilogue
+// (EPI = 4) arithmetic on OTHER registers sits between a load and its wait, so nothing but this dependency keeps the
+// compiler from scheduling the uses of r[] in front of the wait.
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
 // start>>4 | LBO(ignored for swizzled K-major)=1 <<16 | SBO = 1024 B (8 rows x 128 B) >>4 <<32 | version 1 <<46 |
@@ -649,6 +659,41 @@ __device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32
     if (scan64<KT>(r0, r1, col0, st, k, out, cap, h)) apply64<KT>(h, col0, st, k, out, cap);
 }
 
+// ---- chunk entries (EPI = 4) ----------------------------------------------------------------------------------------------
+// A list entry is a 32-column CHUNK (its first train row and its minimum), not a column: the epilogue never finds out WHICH
+// column of a chunk is under the threshold -- that search (group minima, 8..32 compares, bit masks, one append per column:
+// 50-150 ALU-pipe instructions run by one lane of a diverged warp) was most of the hit path, and the hit path was a third of
+// the instructions of the FPFH kernel.  The accumulators are dead as soon as their chunk minimum exists, so nothing of the
+// hit path sits between a TMEM load and the hand-back, and no value registers are live in it.  The re-rank drops every entry
+// whose minimum is not under the row's FINAL threshold (about k + margin of the ~k ln(N/k) entries survive) and runs the
+// exact FP32 distance over all 32 train rows of a surviving chunk (one contiguous bulk copy: rerank_chunks_kernel, exact.cu).
+// Superset argument: an exact top-k member j has v_j < thr(T_final) <= thr(T_run); its chunk's minimum is <= v_j, so the
+// chunk was appended and survives the pruning.  The k-smallest list holds chunk minima: values of distinct columns.
+template <int KT>
+__device__ __forceinline__ void append_entry(float m, int col, RowState<KT> &st, int32_t *__restrict__ out,
+                                             float *__restrict__ out_v, int cap) {
+    const int slot = st.cnt++;
+    if (slot < cap) {
+        out[slot] = col;
+        out_v[slot] = m;
+    }
+}
+template <int KT>
+__device__ __forceinline__ void chunk_hits(float m0, float m1, float m2, float m3, int c0, int c1, int c2, int c3,
+                                           RowState<KT> &st, int k, int32_t *__restrict__ out, float *__restrict__ out_v,
+                                           int cap) {
+    tk_offer<KT>(st, m0);
+    tk_offer<KT>(st, m1);
+    tk_offer<KT>(st, m2);
+    tk_offer<KT>(st, m3);
+    retighten_if_moved<KT, 2>(st, k);   // (fewer than k values known: T and thr stay +inf, every chunk is appended)
+    const float thr = st.thr;
+    if (m0 < thr) append_entry<KT>(m0, c0, st, out, out_v, cap);
+    if (m1 < thr) append_entry<KT>(m1, c1, st, out, out_v, cap);
+    if (m2 < thr) append_entry<KT>(m2, c2, st, out, out_v, cap);
+    if (m3 < thr) append_entry<KT>(m3, c3, st, out, out_v, cap);
+}
+
 // PAIR: CTA-pair mode (tcgen05.mma cta_group::2, M = 256 across two SMs, each CTA holds half of every train tile).
 // EH:   epilogue column halves.  1 = four epilogue warps, a thread owns a whole row; 2 = eight warps (two per
 //       scheduler), warp w drains TMEM lanes 32*(w%4).. (hardware rule) and the column half (w-2)/4 of every tile.
@@ -677,6 +722,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     constexpr bool ALT = EPI != 0;   // the sixteen-warp layouts (warp roles, register re-division, four lists per row)
     constexpr bool QE = EPI == 2;
     constexpr bool RING = EPI == 3;  // alternating tiles + hit chunks handed to the worker warp (service warp 3)
+    constexpr bool CHK = EPI == 4;   // alternating tiles, list entries are 32-column chunks (first train row, minimum)
     constexpr int kEpiWarps = 4 * EH * (ALT ? 2 : 1);
     constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr int kListsPerSplit = EH * (ALT ? 2 : 1);   // private candidate lists per row and train split
@@ -856,7 +902,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint64_t desc_bh = desc_b0 + (uint64_t) (hf * (uint32_t) ((64 * 128) >> 4));
                 const uint32_t tmem_h = tmem_base + hf * (uint32_t) (B200M_TILE_N / 2);
                 const int nt = t1 - t0;
-                const uint32_t nk = nk_last;
+                // (timing experiment, debug instantiation: (n << 12) forces n K steps per tile)
+                const uint32_t nk = (DBG && (dflags & 2) == 0 && (((uint32_t) dflags >> 12) & 7u)) ? (((uint32_t) dflags >> 12) & 7u) : nk_last;
                 uint32_t ph = 0;
                 int lt = 0;
                 // trace builds: cycle stamps of kTraceTiles tiles -- before the waits, operands landed, half handed back, issued
@@ -1053,13 +1100,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // every epilogue thread owns a private candidate list: [split][column half][row][cap]
         const size_t list_row = (size_t) (split * kListsPerSplit + bsel * 2 + half) * p.n_rows + (active ? local : 0);
         int32_t *const out = p.cand_idx + list_row * p.cap;
-        float *const out_v = EH == 1 ? p.cand_val + list_row * p.cap : nullptr;
+        float *const out_v = (EH == 1 || CHK) ? p.cand_val + list_row * p.cap : nullptr;
         const int k = p.k, cap = p.cap;
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         // SPLITN: this warp's hand-off barriers are those of its column half (index buf * 2 + half)
         const uint32_t acc_stride = SPLITN ? 16u : 8u;
-        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3) ? 16u * (uint32_t) bsel : 0u);
-        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3) ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || EPI == 4) ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || EPI == 4) ? 16u * (uint32_t) bsel : 0u);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(tempty_mine, 0) : tempty_mine;
         // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
         // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
@@ -1098,6 +1145,48 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     continue;
                 }
                 process64<KT>(r0, r1, col_base, st, k, out, cap);
+            }
+        } else if constexpr (CHK) {
+            // ===== chunk-entry epilogue: alternating tiles (this warp owns accumulator buffer `bsel`), drained one 32-column
+            // chunk at a time with the next chunk's TMEM load in flight under the min chain of the current one; the half goes
+            // back to its MMA issuer when the fourth load has landed; the whole hit path runs after that, on four floats. =====
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = e_tmem + (uint32_t) bsel * (uint32_t) B200M_TILE_N;
+            // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c
+            int col_base = (t0 + bsel) * B200M_TILE_N + half * 64;
+            uint32_t par = 0;
+            for (int lt = bsel; lt < t1 - t0; lt += 2, col_base += 2 * B200M_TILE_N) {
+                mbar_wait(e_tfull, par);
+                par ^= 1u;
+                tc_fence_after();
+                float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+                if (!(dflags & 1)) {
+                    tmem_ld_32x32b_x32(taddr, r0);
+                    tmem_ld_wait_for(r0);
+                    tmem_ld_32x32b_x32(taddr + 32u, r1);
+                    if (!(dflags & 32)) m0 = min32(r0);
+                    tmem_ld_wait_for(r1);
+                    tmem_ld_32x32b_x32(taddr + 64u, r0);
+                    if (!(dflags & 32)) m1 = min32(r1);
+                    tmem_ld_wait_for(r0);
+                    tmem_ld_32x32b_x32(taddr + 96u, r1);
+                    if (!(dflags & 32)) m2 = min32(r0);
+                    tmem_ld_wait_for(r1);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(e_tempty);
+                if (dflags & (1 | 32)) continue;
+                m3 = min32(r1);
+                {   // what the row's other three threads have learnt (own entry included: harmless)
+                    float t0_, t1_, t2_, t3_;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
+                    st.thr = fminf(st.thr, fminf(fminf(t0_, t1_), fminf(t2_, t3_)));
+                }
+                if (fminf(min3(m0, m1, m2), m3) < st.thr) {   // inactive rows carry thr = -inf
+                    if (dflags & 256) { st.cnt += 1; continue; }   // timing experiment: fast path only
+                    chunk_hits<KT>(m0, m1, m2, m3, col_base, col_base + 32, col_base + 128, col_base + 160, st, k, out, out_v, cap);
+                }
             }
         } else if constexpr (ALT) {
             // ===== alternating-tile epilogue: this warp owns accumulator buffer `bsel`, i.e. tiles bsel, bsel + 2, ...
@@ -1303,7 +1392,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if ((dflags & 256) && st.cnt == -1) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
         if (active && !dump && !RING) {   // (EPI = 3: the worker owns the list counters)
             p.cand_cnt[list_row] = st.cnt;
-            if (EH == 1) p.cand_thr[list_row] = st.thr;
+            if (EH == 1 || CHK) p.cand_thr[list_row] = st.thr;
         }
     }
     tc_fence_before();
@@ -1457,7 +1546,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // (measured, profiles/r02_cand_epilogue_modes.log: C2 k = 2 launch 4.10 / 3.78 / 4.02 ms and C4 k = 5 466 / 454 / 445 ms for
     // eight warps / alternating tiles / quarter columns)
     const int alt_pick = ctx->tc_alt >= 0 ? ctx->tc_alt : (k <= 4 ? 1 : 2);
-    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick == 3 ? 3 : alt_pick != 0 ? 2 : 0) : 0;
+    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick == 3 ? 3 : alt_pick == 4 ? 4 : alt_pick != 0 ? 2 : 0) : 0;
     const bool alt = epi != 0;
     const int lists_per_split = eh * (alt ? 2 : 1);
     int n_splits = 1;
@@ -1506,13 +1595,15 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
     p.cand_val = nullptr;
     p.cand_thr = nullptr;
-    if (eh == 1) {
-        CK(ctx->ws_cand_val.reserve(sizeof(float) * (size_t) n_splits * n_rows * (size_t) cap));
-        CK(ctx->ws_cand_thr.reserve(sizeof(float) * (size_t) n_splits * n_rows));
+    if (eh == 1 || epi == 4) {
+        CK(ctx->ws_cand_val.reserve(sizeof(float) * (size_t) n_lists * n_rows * (size_t) cap));
+        CK(ctx->ws_cand_thr.reserve(sizeof(float) * (size_t) n_lists * n_rows));
         p.cand_val = ctx->ws_cand_val.as<float>();
         p.cand_thr = ctx->ws_cand_thr.as<float>();
     }
-    *has_values_out = eh == 1 ? 1 : 0;
+    // 0: column entries without values; 1: column entries + accumulator values + final thresholds (the re-rank prunes);
+    // 2: CHUNK entries (first train row of a 32-row chunk, chunk minimum) + final thresholds
+    *has_values_out = epi == 4 ? 2 : eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
     p.ring_from_tile = ctx->tc_ring_from;
@@ -1523,7 +1614,8 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     int rc;
     const bool dbg = dump != nullptr || ctx->tc_debug != 0;
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \
-    rc = pair ? (eh == 2 ? (epi == 3 ? launch_tc<KT_, true, 2, true, 3, DBG_>(ctx, mq, mt, p, grid, smem)        \
+    rc = pair ? (eh == 2 ? (epi == 4 ? launch_tc<KT_, true, 2, true, 4, DBG_>(ctx, mq, mt, p, grid, smem)        \
+                            : epi == 3 ? launch_tc<KT_, true, 2, true, 3, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 2 ? launch_tc<KT_, true, 2, true, 2, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 1 ? launch_tc<KT_, true, 2, true, 1, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : splitn ? launch_tc<KT_, true, 2, true, 0, DBG_>(ctx, mq, mt, p, grid, smem)        \

@@ -673,6 +673,198 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
         atomicAdd(reinterpret_cast<unsigned long long *>(counters + 2), blk_cands);
 }
 
+// ---- re-rank over CHUNK entries (candidate kernel EPI = 4) ---------------------------------------------------------------
+// A list entry names 32 consecutive train rows (a chunk of the candidate kernel's columns) and carries the chunk's smallest
+// accumulator.  Entries whose minimum is not under the row's final threshold are dropped (no exact top-k
+// member lives in such a chunk); every surviving chunk is fetched by ONE bulk copy (32 contiguous FP32 rows, 4.6 KB for
+// FPFH-33) and lane l runs the reference's sequential FP32 chain over row l of every chunk of the pass -- up to four chains
+// per lane in flight.  Same per-lane sorted lists and warp arg-min as rerank_kernel; same metadata pipeline.
+constexpr int kChunkRows = 32;
+constexpr int kChunkPassMax = 4;
+__host__ __device__ inline int chunk_pass(int dp) {
+    const int g = 18432 / (kChunkRows * dp * 4);
+    return g < 1 ? 1 : g > kChunkPassMax ? kChunkPassMax : g;
+}
+__host__ __device__ inline size_t chunk_warp_bytes(int dp) { return (size_t) (chunk_pass(dp) * kChunkRows + 1) * dp * 4; }   // + the query
+
+template <int KMAX>
+__global__ void __launch_bounds__(512)
+rerank_chunks_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_valid, int dp, int dim,
+                     const float *__restrict__ t_f32, const uint8_t *__restrict__ t_valid, size_t nt, long long t_off,
+                     size_t row_begin, size_t n_rows, int k,
+                     const int32_t *__restrict__ cand_idx, const int32_t *__restrict__ cand_cnt, int n_lists, int cap,
+                     const float *__restrict__ cand_val, const float *__restrict__ cand_thr,
+                     int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count,
+                     int32_t *__restrict__ flag_rows, int32_t *__restrict__ counters, const int32_t *__restrict__ row_map) {
+    extern __shared__ __align__(128) uint8_t rr_smem[];
+    __shared__ unsigned long long blk_cands;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t) dp * 4u;
+    const uint32_t chunk_bytes = (uint32_t) kChunkRows * row_bytes;
+    const int G = chunk_pass(dp);
+    // per-warp slab: [G chunks][32 rows][dp] then the query row; the warps' mbarriers sit behind all slabs
+    uint8_t *slab = rr_smem + (size_t) warp * chunk_warp_bytes(dp);
+    const uint32_t slab_u = smem_addr(slab);
+    const uint32_t sq_u = slab_u + (uint32_t) G * chunk_bytes;
+    const float4 *sq4 = reinterpret_cast<const float4 *>(slab + (size_t) G * chunk_bytes);
+    const float4 *my4 = reinterpret_cast<const float4 *>(slab + (size_t) lane * row_bytes);   // row `lane` of chunk 0
+    const int chunk4 = (int) (chunk_bytes / 16u);
+    const uint32_t bar = smem_addr(rr_smem + (size_t) n_warps * chunk_warp_bytes(dp)) + 8u * (uint32_t) warp;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x == 0) blk_cands = 0ull;
+    __syncthreads();
+    uint32_t phase = 0;
+    unsigned long long my_cands = 0ull;
+    const size_t stride = (size_t) gridDim.x * n_warps;
+    size_t local = (size_t) blockIdx.x * n_warps + warp;
+    RerankRow cur = rerank_fetch_row(rerank_fetch_lens(local, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map), local,
+                                     n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+    RerankLens nxt_lens = rerank_fetch_lens(local + stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
+    for (; local < n_rows; local += stride) {
+        const size_t qi = (size_t) cur.qi;
+        const size_t orow = qi - row_begin;
+        int32_t *oi = idx + orow * k;
+        float *od = dist + orow * k;
+        const bool work = cur.qv && !cur.overflow;
+        float ld[KMAX];
+        int li[KMAX];
+#pragma unroll
+        for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; li[m] = INT_MAX; }
+        bool first = true;   // the query row rides with the first pass that gathers anything
+        RerankRow nxt;
+        if (work && cur.total > 0) {
+            for (int base = 0; base < cur.total; base += 32) {
+                int j = cur.j0;
+                if (base > 0) {   // list positions beyond the first 32 (rare): fetched on the spot
+                    int l_sel, c_sel;
+                    rerank_locate(base + lane, cur.my_len, n_lists, l_sel, c_sel);
+                    j = -1;
+                    if (base + lane < cur.total) {
+                        const size_t e = ((size_t) l_sel * n_rows + local) * cap + c_sel;
+                        j = cand_idx[e];
+                        if (j < 0 || (size_t) j >= nt || !(cand_val[e] < cur.thr)) j = -1;
+                    }
+                }
+                const unsigned live = __ballot_sync(0xffffffffu, j >= 0);
+                const int n_live = __popc(live);
+                const int slot = __popc(live & ((1u << lane) - 1u));
+                my_cands += (unsigned long long) n_live * kChunkRows;   // train rows evaluated exactly
+                for (int p0 = 0; p0 < n_live; p0 += G) {
+                    const int n_pass = n_live - p0 < G ? n_live - p0 : G;
+                    const bool mine = j >= 0 && slot >= p0 && slot < p0 + n_pass;
+                    const unsigned my_rows = mine ? (nt - (size_t) j < (size_t) kChunkRows ? (unsigned) (nt - (size_t) j) : (unsigned) kChunkRows) : 0u;
+                    const unsigned pass_rows = __reduce_add_sync(0xffffffffu, my_rows);
+                    // earlier (generic-proxy) reads of the slab are ordered before the asynchronous writes that follow
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t tx = (pass_rows + (first ? 1u : 0u)) * row_bytes;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+                        if (first) bulk_g2s(sq_u, q_f32 + qi * (size_t) dp, row_bytes, bar);
+                    }
+                    __syncwarp();   // the expectation is posted before any copy can complete
+                    if (mine) bulk_g2s(slab_u + (uint32_t) (slot - p0) * chunk_bytes, t_f32 + (size_t) j * dp, my_rows * row_bytes, bar);
+                    if (first) {
+                        nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+                        nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
+                        first = false;
+                    }
+                    // first train row of every chunk of the pass (the n-th live lane holds slot n)
+                    int cj[kChunkPassMax];
+#pragma unroll
+                    for (int i = 0; i < kChunkPassMax; ++i)
+                        cj[i] = i < n_pass ? __shfl_sync(0xffffffffu, j, (int) __fns(live, 0, p0 + i + 1)) : -1;
+                    bar_wait_parity(bar, phase);
+                    phase ^= 1u;
+                    float s[kChunkPassMax];
+#pragma unroll
+                    for (int i = 0; i < kChunkPassMax; ++i) s[i] = 0.f;
+#pragma unroll 2
+                    for (int d4 = 0; d4 < dp / 4; ++d4) {
+                        const float4 a = sq4[d4];
+#pragma unroll
+                        for (int i = 0; i < kChunkPassMax; ++i) {
+                            if (i < n_pass) {   // warp-uniform
+                                const float4 b = my4[i * chunk4 + d4];
+                                float df = __fsub_rn(a.x, b.x);
+                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                                df = __fsub_rn(a.y, b.y);
+                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                                df = __fsub_rn(a.z, b.z);
+                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                                df = __fsub_rn(a.w, b.w);
+                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < kChunkPassMax; ++i) {
+                        if (i < n_pass && (size_t) (cj[i] + lane) < nt) {
+                            float cd = __fsqrt_rn(s[i]);
+                            int ci = cj[i] + lane;
+                            // invalid (non-finite) train rows are never candidates (reference :661); only such a row -- or an
+                            // overflowing sum -- can give a non-finite distance, so validity is looked up on that path alone
+                            const bool ok = cd < INFINITY || t_valid[ci] != 0;
+                            if (ok && lex_less(cd, ci, ld[KMAX - 1], li[KMAX - 1])) {
+#pragma unroll
+                                for (int m = 0; m < KMAX; ++m) {
+                                    if (lex_less(cd, ci, ld[m], li[m])) {
+                                        float td = ld[m]; int ti = li[m];
+                                        ld[m] = cd; li[m] = ci;
+                                        cd = td; ci = ti;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (first) {   // nothing was gathered for this row
+            nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+            nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
+        }
+        // k rounds of warp arg-min over the per-lane list heads
+        int head = 0, found = 0;
+        if (work) {
+            for (int round = 0; round < k; ++round) {
+                float hd = INFINITY;
+                int hi = INT_MAX;
+#pragma unroll
+                for (int m = 0; m < KMAX; ++m)
+                    if (m == head) { hd = ld[m]; hi = li[m]; }
+                float wd = hd;
+                int wi = hi;
+                for (int o = 16; o > 0; o >>= 1) {
+                    float od2 = __shfl_xor_sync(0xffffffffu, wd, o);
+                    int oi2 = __shfl_xor_sync(0xffffffffu, wi, o);
+                    if (lex_less(od2, oi2, wd, wi)) { wd = od2; wi = oi2; }
+                }
+                if (wi == INT_MAX) break;
+                if (hi == wi) head++;   // a train row is evaluated once per query row (chunks are disjoint)
+                if (lane == 0) { oi[round] = (int32_t) (wi + t_off); od[round] = wd; }
+                found = round + 1;
+            }
+        }
+        for (int m = found + lane; m < k; m += 32) { oi[m] = -1; od[m] = 0.f; }
+        if (lane == 0) {
+            count[orow] = found;
+            if (cur.qv && cur.overflow) {
+                int pos = atomicAdd(counters, 1);
+                flag_rows[pos] = (int32_t) local;
+            }
+        }
+        cur = nxt;
+    }
+    if (lane == 0 && my_cands) atomicAdd(&blk_cands, my_cands);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_cands)
+        atomicAdd(reinterpret_cast<unsigned long long *>(counters + 2), blk_cands);
+}
+
 template <int KMAX>
 cudaError_t launch_exact_t(const float *q_f32, const uint8_t *q_valid, int dp, int dim, const float *t_f32,
                            const uint8_t *t_valid, size_t nt, int64_t t_off, size_t row_begin, size_t n_rows,
@@ -750,9 +942,38 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
                           const int32_t *cand_idx, const int32_t *cand_cnt, int n_lists, int cap,
                           const float *cand_val, const float *cand_thr,
                           int32_t *idx, float *dist, int32_t *count,
-                          int32_t *flag_rows, int32_t *counters, int sm_count, const int32_t *row_map, cudaStream_t st) {
+                          int32_t *flag_rows, int32_t *counters, int sm_count, const int32_t *row_map, int chunk_entries,
+                          cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     if (n_lists > kMaxLists) return cudaErrorInvalidValue;
+    if (chunk_entries) {
+        if (!cand_val || !cand_thr) return cudaErrorInvalidValue;
+        const size_t per_warp = chunk_warp_bytes(dp) + 8;
+        int warps = (int) ((220 * 1024) / per_warp);
+        if (warps > 16) warps = 16;
+        if (warps < 1) return cudaErrorInvalidValue;
+        const size_t smem = (size_t) warps * per_warp;
+        const size_t want = (n_rows + warps - 1) / warps;
+        const unsigned blocks = (unsigned) (want < (size_t) sm_count ? want : (size_t) sm_count);
+#define B200M_RERANK_CHUNK_CASE(K)                                                                              \
+    do {                                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(rerank_chunks_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int) smem);                                                       \
+        if (e != cudaSuccess) return e;                                                                         \
+        rerank_chunks_kernel<K><<<blocks, warps * 32, smem, st>>>(                                              \
+            q_f32, q_valid, dp, dim, t_f32, t_valid, nt, (long long) t_index_offset, row_begin, n_rows, k,      \
+            cand_idx, cand_cnt, n_lists, cap, cand_val, cand_thr, idx, dist, count, flag_rows, counters,        \
+            row_map);                                                                                           \
+        return cudaGetLastError();                                                                              \
+    } while (0)
+        if (k <= 1) B200M_RERANK_CHUNK_CASE(1);
+        if (k <= 2) B200M_RERANK_CHUNK_CASE(2);
+        if (k <= 4) B200M_RERANK_CHUNK_CASE(4);
+        if (k <= 8) B200M_RERANK_CHUNK_CASE(8);
+        if (k <= 16) B200M_RERANK_CHUNK_CASE(16);
+        B200M_RERANK_CHUNK_CASE(32);
+#undef B200M_RERANK_CHUNK_CASE
+    }
     // one CTA per SM holding as many warps (each with its own gather slab) as shared memory allows
     const size_t per_warp = rerank_warp_bytes(dp) + 8;
     int warps = (int) ((220 * 1024) / per_warp);

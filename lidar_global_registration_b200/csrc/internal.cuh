@@ -151,7 +151,9 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
                           const float *cand_val, const float *cand_thr /* both null: no pruning */,
                           int32_t *idx, float *dist, int32_t *count,
                           int32_t *flag_rows, int32_t *counters /*[0]=flagged rows, [1..2]=candidate pairs (u64)*/,
-                          int sm_count, const int32_t *row_map, cudaStream_t st);
+                          int sm_count, const int32_t *row_map,
+                          int chunk_entries /* 1: an entry is the first of 32 consecutive train rows + the chunk's minimum */,
+                          cudaStream_t st);
 
 // filter.cu
 cudaError_t launch_filter(int mode, int k, float ratio_thr, float distance_thr, size_t row_begin, size_t n_rows,
@@ -170,7 +172,8 @@ cudaError_t launch_merge(int k, int n_lists, size_t nq, const int32_t *idx_in, c
 // candidates_tc.cu
 // Fills ws_cand_idx [n_lists][n_rows][cap] and ws_cand_cnt [n_lists][n_rows] (entries appended per list; a
 // count above cap marks an overflowed list).  dump != nullptr: single tile, raw accumulators to dump[128][256].
-// *has_values_out = 1: ws_cand_val [n_lists][n_rows][cap] and ws_cand_thr [n_lists][n_rows] are filled too.
+// *has_values_out = 1: ws_cand_val [n_lists][n_rows][cap] and ws_cand_thr [n_lists][n_rows] are filled too;
+// = 2: the same, and every entry is a 32-row CHUNK (first train row, smallest accumulator of the chunk).
 // q_ops != null: the query rows are rows 0..n_rows of this compact [q_pad][kp] operand array (norms in q_norm) instead of
 // rows row_begin.. of the query side's own array.
 int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows, int k, int cap_request,
