@@ -229,6 +229,30 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+// the same load with the destination registers tied to their previous contents ("+r"): the software-pipelined drain of
+// the chunk epilogue loads into the SAME two register windows over and over, and with plain outputs ptxas gives every
+// load a fresh 32-register tuple that overlaps a live one (35 register moves per tile to shuffle values out of the way)
+__device__ __forceinline__ void tmem_ld_32x32b_x32_inplace(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // The same wait, tied to the 32 registers of the load it completes: in the software-pipelined drain of the chunk epilogue
 // (EPI = 4) arithmetic on OTHER registers sits between a load and its wait, so nothing but this dependency keeps the
@@ -659,6 +683,16 @@ __device__ __forceinline__ void process64(const uint32_t (&r0)[32], const uint32
     if (scan64<KT>(r0, r1, col0, st, k, out, cap, h)) apply64<KT>(h, col0, st, k, out, cap);
 }
 
+// minimum of a 32-column chunk held as two 16-register halves: 16 min ops
+__device__ __forceinline__ float min16x2(const uint32_t (&a)[16], const uint32_t (&b)[16]) {
+    float m = min3(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]));
+#pragma unroll
+    for (int i = 3; i < 15; i += 2) m = min3(m, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+    m = min3(m, __uint_as_float(a[15]), __uint_as_float(b[0]));
+#pragma unroll
+    for (int i = 1; i < 15; i += 2) m = min3(m, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
+    return fminf(m, __uint_as_float(b[15]));
+}
 // ---- chunk entries (EPI = 4) ----------------------------------------------------------------------------------------------
 // A list entry is a 32-column CHUNK (its first train row and its minimum), not a column: the epilogue never finds out WHICH
 // column of a chunk is under the threshold -- that search (group minima, 8..32 compares, bit masks, one append per column:
@@ -722,7 +756,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     constexpr bool ALT = EPI != 0;   // the sixteen-warp layouts (warp roles, register re-division, four lists per row)
     constexpr bool QE = EPI == 2;
     constexpr bool RING = EPI == 3;  // alternating tiles + hit chunks handed to the worker warp (service warp 3)
-    constexpr bool CHK = EPI == 4;   // alternating tiles, list entries are 32-column chunks (first train row, minimum)
+    constexpr bool CHK = EPI == 4 || EPI == 5;   // alternating tiles, list entries are 32-column chunks (first train row, minimum);
+                                                 // 4: chunk-by-chunk drain (next load in flight under a min chain), 5: two loads per wait
     constexpr int kEpiWarps = 4 * EH * (ALT ? 2 : 1);
     constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr int kListsPerSplit = EH * (ALT ? 2 : 1);   // private candidate lists per row and train split
@@ -1105,8 +1140,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         // SPLITN: this warp's hand-off barriers are those of its column half (index buf * 2 + half)
         const uint32_t acc_stride = SPLITN ? 16u : 8u;
-        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || EPI == 4) ? 16u * (uint32_t) bsel : 0u);
-        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || EPI == 4) ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || CHK) ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || CHK) ? 16u * (uint32_t) bsel : 0u);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(tempty_mine, 0) : tempty_mine;
         // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
         // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
@@ -1151,6 +1186,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             // chunk at a time with the next chunk's TMEM load in flight under the min chain of the current one; the half goes
             // back to its MMA issuer when the fourth load has landed; the whole hit path runs after that, on four floats. =====
             uint32_t r0[32], r1[32];
+            uint32_t qa[16], qb[16], qc[16], qd[16];   // EPI = 5: the same drain in 16-column loads
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;   // (the in-place loads formally read their destinations)
             const uint32_t taddr = e_tmem + (uint32_t) bsel * (uint32_t) B200M_TILE_N;
             // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c
             int col_base = (t0 + bsel) * B200M_TILE_N + half * 64;
@@ -1160,16 +1198,34 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 par ^= 1u;
                 tc_fence_after();
                 float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
-                if (!(dflags & 1)) {
-                    tmem_ld_32x32b_x32(taddr, r0);
+                if (EPI == 5) {
+                    if (!(dflags & 1)) {
+                        tmem_ld_32x32b_x16(taddr, qa);
+                        tmem_ld_32x32b_x16(taddr + 16u, qb);
+                        tmem_ld_wait();
+                        tmem_ld_32x32b_x16(taddr + 32u, qc);
+                        tmem_ld_32x32b_x16(taddr + 48u, qd);
+                        if (!(dflags & 32)) m0 = min16x2(qa, qb);
+                        tmem_ld_wait();
+                        tmem_ld_32x32b_x16(taddr + 64u, qa);
+                        tmem_ld_32x32b_x16(taddr + 80u, qb);
+                        if (!(dflags & 32)) m1 = min16x2(qc, qd);
+                        tmem_ld_wait();
+                        tmem_ld_32x32b_x16(taddr + 96u, qc);
+                        tmem_ld_32x32b_x16(taddr + 112u, qd);
+                        if (!(dflags & 32)) m2 = min16x2(qa, qb);
+                        tmem_ld_wait();
+                    }
+                } else if (!(dflags & 1)) {
+                    tmem_ld_32x32b_x32_inplace(taddr, r0);
                     tmem_ld_wait_for(r0);
-                    tmem_ld_32x32b_x32(taddr + 32u, r1);
+                    tmem_ld_32x32b_x32_inplace(taddr + 32u, r1);
                     if (!(dflags & 32)) m0 = min32(r0);
                     tmem_ld_wait_for(r1);
-                    tmem_ld_32x32b_x32(taddr + 64u, r0);
+                    tmem_ld_32x32b_x32_inplace(taddr + 64u, r0);
                     if (!(dflags & 32)) m1 = min32(r1);
                     tmem_ld_wait_for(r0);
-                    tmem_ld_32x32b_x32(taddr + 96u, r1);
+                    tmem_ld_32x32b_x32_inplace(taddr + 96u, r1);
                     if (!(dflags & 32)) m2 = min32(r0);
                     tmem_ld_wait_for(r1);
                 }
@@ -1177,7 +1233,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(e_tempty);
                 if (dflags & (1 | 32)) continue;
-                m3 = min32(r1);
+                m3 = EPI == 5 ? min16x2(qc, qd) : min32(r1);
                 {   // what the row's other three threads have learnt (own entry included: harmless)
                     float t0_, t1_, t2_, t3_;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0_), "=f"(t1_), "=f"(t2_), "=f"(t3_) : "r"(e_peer) : "memory");
@@ -1541,12 +1597,14 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // split-N (two 128-column halves per accumulator, an issuer warp per half) for one-atom descriptors: C2 launch
     // 4.18 -> 3.92 ms; B200M_TC_SPLITN=0 selects the single N = 256 MMA per tile (comparison)
     const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
-    // ... with sixteen epilogue warps of 64 accumulators each: B200M_TC_ALT=2 (default) quarter columns of every tile,
-    // hand-back before filtering; =1 alternating tiles; =0 eight warps of 128 accumulators, every warp on every tile
-    // (measured, profiles/r02_cand_epilogue_modes.log: C2 k = 2 launch 4.10 / 3.78 / 4.02 ms and C4 k = 5 466 / 454 / 445 ms for
-    // eight warps / alternating tiles / quarter columns)
-    const int alt_pick = ctx->tc_alt >= 0 ? ctx->tc_alt : (k <= 4 ? 1 : 2);
-    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick == 3 ? 3 : alt_pick == 4 ? 4 : alt_pick != 0 ? 2 : 0) : 0;
+    // ... with sixteen epilogue warps of 64 accumulators each.  B200M_TC_ALT: 4 / 5 (default) alternating tiles with CHUNK
+    // entries -- a list entry is a 32-column chunk and its minimum, the re-rank evaluates the surviving chunks' rows -- drained
+    // by 32-column (4) or 16-column (5) TMEM loads; 1 alternating tiles, 2 quarter columns of every tile, 3 alternating tiles +
+    // worker warp (all three: column entries); 0 eight warps of 128 accumulators, every warp on every tile.  Measured per
+    // launch, same boxes (profiles/r02_cand_epilogue_modes.log, r02_cand_chunk_entries.log): C2 k = 2 -- 4.10 (0) / 3.75 (1) /
+    // 3.85 (2) / 3.08 (4) / 3.03 ms (5); C4 k = 5 -- 492 (0) / 530 (1) / 438 (2) / 398 (4) / 459 ms (5: spills at KT = 8).
+    const int alt_pick = ctx->tc_alt >= 0 ? ctx->tc_alt : (k <= 2 ? 5 : 4);
+    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick == 3 ? 3 : alt_pick == 4 ? 4 : alt_pick == 5 ? 5 : alt_pick != 0 ? 2 : 0) : 0;
     const bool alt = epi != 0;
     const int lists_per_split = eh * (alt ? 2 : 1);
     int n_splits = 1;
@@ -1595,7 +1653,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.cand_cnt = ctx->ws_cand_cnt.as<int32_t>();
     p.cand_val = nullptr;
     p.cand_thr = nullptr;
-    if (eh == 1 || epi == 4) {
+    if (eh == 1 || epi >= 4) {
         CK(ctx->ws_cand_val.reserve(sizeof(float) * (size_t) n_lists * n_rows * (size_t) cap));
         CK(ctx->ws_cand_thr.reserve(sizeof(float) * (size_t) n_lists * n_rows));
         p.cand_val = ctx->ws_cand_val.as<float>();
@@ -1603,7 +1661,7 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     }
     // 0: column entries without values; 1: column entries + accumulator values + final thresholds (the re-rank prunes);
     // 2: CHUNK entries (first train row of a 32-row chunk, chunk minimum) + final thresholds
-    *has_values_out = epi == 4 ? 2 : eh == 1 ? 1 : 0;
+    *has_values_out = epi >= 4 ? 2 : eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
     p.ring_from_tile = ctx->tc_ring_from;
@@ -1614,7 +1672,8 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     int rc;
     const bool dbg = dump != nullptr || ctx->tc_debug != 0;
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \
-    rc = pair ? (eh == 2 ? (epi == 4 ? launch_tc<KT_, true, 2, true, 4, DBG_>(ctx, mq, mt, p, grid, smem)        \
+    rc = pair ? (eh == 2 ? (epi == 5 ? launch_tc<KT_, true, 2, true, 5, DBG_>(ctx, mq, mt, p, grid, smem)        \
+                            : epi == 4 ? launch_tc<KT_, true, 2, true, 4, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 3 ? launch_tc<KT_, true, 2, true, 3, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 2 ? launch_tc<KT_, true, 2, true, 2, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 1 ? launch_tc<KT_, true, 2, true, 1, DBG_>(ctx, mq, mt, p, grid, smem)      \

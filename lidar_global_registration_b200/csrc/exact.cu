@@ -15,6 +15,7 @@
 //                       pass (a certified superset of the exact top-k, see candidates_tc.cu):
 //                       exact distances and the final (dist, idx) order.
 #include <float.h>
+#include <stdlib.h>
 #include <limits.h>
 #include <math.h>
 
@@ -673,19 +674,25 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
         atomicAdd(reinterpret_cast<unsigned long long *>(counters + 2), blk_cands);
 }
 
-// ---- re-rank over CHUNK entries (candidate kernel EPI = 4) ---------------------------------------------------------------
+// ---- re-rank over CHUNK entries (candidate kernel EPI = 4 / 5) ---------------------------------------------------------
 // A list entry names 32 consecutive train rows (a chunk of the candidate kernel's columns) and carries the chunk's smallest
 // accumulator.  Entries whose minimum is not under the row's final threshold are dropped (no exact top-k
-// member lives in such a chunk); every surviving chunk is fetched by ONE bulk copy (32 contiguous FP32 rows, 4.6 KB for
-// FPFH-33) and lane l runs the reference's sequential FP32 chain over row l of every chunk of the pass -- up to four chains
-// per lane in flight.  Same per-lane sorted lists and warp arg-min as rerank_kernel; same metadata pipeline.
+// member lives in such a chunk) -- of the ~k ln(N/k) entries of a row about k + margin survive, scattered over the lists, so
+// the survivors of ALL list positions are first compacted into a small per-warp array and then fetched G chunks per pass:
+// every chunk by ONE bulk copy (32 contiguous FP32 rows, 4.6 KB for FPFH-33), lane l runs the reference's sequential FP32
+// chain over row l of every chunk of the pass -- up to four chains per lane in flight.  Same per-lane sorted lists and warp
+// arg-min as rerank_kernel; same metadata pipeline for the first 32 list positions, the rest are loaded four groups at a time.
 constexpr int kChunkRows = 32;
 constexpr int kChunkPassMax = 4;
-__host__ __device__ inline int chunk_pass(int dp) {
-    const int g = 18432 / (kChunkRows * dp * 4);
+constexpr int kChunkPassBytes = 9216;   // slab bytes per warp and pass: two FPFH-33 chunks, so that sixteen warps fit an SM
+constexpr int kSurvCap = 64;
+inline int chunk_pass(int dp) {
+    static const int forced = getenv("B200M_CHUNK_PASS") ? atoi(getenv("B200M_CHUNK_PASS")) : 0;   // tuning override: 1..4
+    const int g = forced > 0 ? forced : kChunkPassBytes / (kChunkRows * dp * 4);
     return g < 1 ? 1 : g > kChunkPassMax ? kChunkPassMax : g;
 }
-__host__ __device__ inline size_t chunk_warp_bytes(int dp) { return (size_t) (chunk_pass(dp) * kChunkRows + 1) * dp * 4; }   // + the query
+// slab of G chunks + the query row + the survivor array
+__host__ __device__ inline size_t chunk_warp_bytes(int dp, int G) { return (size_t) (G * kChunkRows + 1) * dp * 4 + kSurvCap * 4; }
 
 template <int KMAX>
 __global__ void __launch_bounds__(512)
@@ -695,21 +702,22 @@ rerank_chunks_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict_
                      const int32_t *__restrict__ cand_idx, const int32_t *__restrict__ cand_cnt, int n_lists, int cap,
                      const float *__restrict__ cand_val, const float *__restrict__ cand_thr,
                      int32_t *__restrict__ idx, float *__restrict__ dist, int32_t *__restrict__ count,
-                     int32_t *__restrict__ flag_rows, int32_t *__restrict__ counters, const int32_t *__restrict__ row_map) {
+                     int32_t *__restrict__ flag_rows, int32_t *__restrict__ counters, const int32_t *__restrict__ row_map,
+                     int G /* chunks per pass */) {
     extern __shared__ __align__(128) uint8_t rr_smem[];
     __shared__ unsigned long long blk_cands;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t row_bytes = (uint32_t) dp * 4u;
     const uint32_t chunk_bytes = (uint32_t) kChunkRows * row_bytes;
-    const int G = chunk_pass(dp);
-    // per-warp slab: [G chunks][32 rows][dp] then the query row; the warps' mbarriers sit behind all slabs
-    uint8_t *slab = rr_smem + (size_t) warp * chunk_warp_bytes(dp);
+    // per-warp: [G chunks][32 rows][dp], the query row, the survivors' first train rows; the warps' mbarriers sit behind all of it
+    uint8_t *slab = rr_smem + (size_t) warp * chunk_warp_bytes(dp, G);
     const uint32_t slab_u = smem_addr(slab);
     const uint32_t sq_u = slab_u + (uint32_t) G * chunk_bytes;
     const float4 *sq4 = reinterpret_cast<const float4 *>(slab + (size_t) G * chunk_bytes);
+    volatile int *surv = reinterpret_cast<volatile int *>(slab + (size_t) G * chunk_bytes + row_bytes);
     const float4 *my4 = reinterpret_cast<const float4 *>(slab + (size_t) lane * row_bytes);   // row `lane` of chunk 0
     const int chunk4 = (int) (chunk_bytes / 16u);
-    const uint32_t bar = smem_addr(rr_smem + (size_t) n_warps * chunk_warp_bytes(dp)) + 8u * (uint32_t) warp;
+    const uint32_t bar = smem_addr(rr_smem + (size_t) n_warps * chunk_warp_bytes(dp, G)) + 8u * (uint32_t) warp;
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -735,93 +743,117 @@ rerank_chunks_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict_
         for (int m = 0; m < KMAX; ++m) { ld[m] = INFINITY; li[m] = INT_MAX; }
         bool first = true;   // the query row rides with the first pass that gathers anything
         RerankRow nxt;
-        if (work && cur.total > 0) {
-            for (int base = 0; base < cur.total; base += 32) {
-                int j = cur.j0;
-                if (base > 0) {   // list positions beyond the first 32 (rare): fetched on the spot
-                    int l_sel, c_sel;
-                    rerank_locate(base + lane, cur.my_len, n_lists, l_sel, c_sel);
-                    j = -1;
-                    if (base + lane < cur.total) {
-                        const size_t e = ((size_t) l_sel * n_rows + local) * cap + c_sel;
-                        j = cand_idx[e];
-                        if (j < 0 || (size_t) j >= nt || !(cand_val[e] < cur.thr)) j = -1;
-                    }
+        // exact distances of the rows of the compacted survivors surv[0 .. n_surv)
+        auto gather = [&](int n_surv) {
+            __syncwarp();   // surv[] written
+            my_cands += (unsigned long long) n_surv * kChunkRows;   // train rows evaluated exactly
+            for (int p0 = 0; p0 < n_surv; p0 += G) {
+                const int n_pass = n_surv - p0 < G ? n_surv - p0 : G;
+                const bool mine = lane < n_pass;
+                const int j = mine ? surv[p0 + lane] : 0;
+                const unsigned my_rows = mine ? (nt - (size_t) j < (size_t) kChunkRows ? (unsigned) (nt - (size_t) j) : (unsigned) kChunkRows) : 0u;
+                const unsigned pass_rows = __reduce_add_sync(0xffffffffu, my_rows);
+                // earlier (generic-proxy) reads of the slab are ordered before the asynchronous writes that follow
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t tx = (pass_rows + (first ? 1u : 0u)) * row_bytes;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+                    if (first) bulk_g2s(sq_u, q_f32 + qi * (size_t) dp, row_bytes, bar);
                 }
-                const unsigned live = __ballot_sync(0xffffffffu, j >= 0);
-                const int n_live = __popc(live);
-                const int slot = __popc(live & ((1u << lane) - 1u));
-                my_cands += (unsigned long long) n_live * kChunkRows;   // train rows evaluated exactly
-                for (int p0 = 0; p0 < n_live; p0 += G) {
-                    const int n_pass = n_live - p0 < G ? n_live - p0 : G;
-                    const bool mine = j >= 0 && slot >= p0 && slot < p0 + n_pass;
-                    const unsigned my_rows = mine ? (nt - (size_t) j < (size_t) kChunkRows ? (unsigned) (nt - (size_t) j) : (unsigned) kChunkRows) : 0u;
-                    const unsigned pass_rows = __reduce_add_sync(0xffffffffu, my_rows);
-                    // earlier (generic-proxy) reads of the slab are ordered before the asynchronous writes that follow
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (lane == 0) {
-                        const uint32_t tx = (pass_rows + (first ? 1u : 0u)) * row_bytes;
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-                        if (first) bulk_g2s(sq_u, q_f32 + qi * (size_t) dp, row_bytes, bar);
-                    }
-                    __syncwarp();   // the expectation is posted before any copy can complete
-                    if (mine) bulk_g2s(slab_u + (uint32_t) (slot - p0) * chunk_bytes, t_f32 + (size_t) j * dp, my_rows * row_bytes, bar);
-                    if (first) {
-                        nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
-                        nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
-                        first = false;
-                    }
-                    // first train row of every chunk of the pass (the n-th live lane holds slot n)
-                    int cj[kChunkPassMax];
+                __syncwarp();   // the expectation is posted before any copy can complete
+                if (mine) bulk_g2s(slab_u + (uint32_t) lane * chunk_bytes, t_f32 + (size_t) j * dp, my_rows * row_bytes, bar);
+                if (first) {
+                    // metadata of the rows behind this one: their loads land while this row's slab fills
+                    nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
+                    nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
+                    first = false;
+                }
+                int cj[kChunkPassMax];   // first train row of every chunk of the pass
 #pragma unroll
-                    for (int i = 0; i < kChunkPassMax; ++i)
-                        cj[i] = i < n_pass ? __shfl_sync(0xffffffffu, j, (int) __fns(live, 0, p0 + i + 1)) : -1;
-                    bar_wait_parity(bar, phase);
-                    phase ^= 1u;
-                    float s[kChunkPassMax];
+                for (int i = 0; i < kChunkPassMax; ++i) cj[i] = i < n_pass ? surv[p0 + i] : -1;
+                bar_wait_parity(bar, phase);
+                phase ^= 1u;
+                float s[kChunkPassMax];
 #pragma unroll
-                    for (int i = 0; i < kChunkPassMax; ++i) s[i] = 0.f;
+                for (int i = 0; i < kChunkPassMax; ++i) s[i] = 0.f;
 #pragma unroll 2
-                    for (int d4 = 0; d4 < dp / 4; ++d4) {
-                        const float4 a = sq4[d4];
-#pragma unroll
-                        for (int i = 0; i < kChunkPassMax; ++i) {
-                            if (i < n_pass) {   // warp-uniform
-                                const float4 b = my4[i * chunk4 + d4];
-                                float df = __fsub_rn(a.x, b.x);
-                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
-                                df = __fsub_rn(a.y, b.y);
-                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
-                                df = __fsub_rn(a.z, b.z);
-                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
-                                df = __fsub_rn(a.w, b.w);
-                                s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
-                            }
-                        }
-                    }
+                for (int d4 = 0; d4 < dp / 4; ++d4) {
+                    const float4 a = sq4[d4];
 #pragma unroll
                     for (int i = 0; i < kChunkPassMax; ++i) {
-                        if (i < n_pass && (size_t) (cj[i] + lane) < nt) {
-                            float cd = __fsqrt_rn(s[i]);
-                            int ci = cj[i] + lane;
-                            // invalid (non-finite) train rows are never candidates (reference :661); only such a row -- or an
-                            // overflowing sum -- can give a non-finite distance, so validity is looked up on that path alone
-                            const bool ok = cd < INFINITY || t_valid[ci] != 0;
-                            if (ok && lex_less(cd, ci, ld[KMAX - 1], li[KMAX - 1])) {
+                        if (i < n_pass) {   // warp-uniform
+                            const float4 b = my4[i * chunk4 + d4];
+                            float df = __fsub_rn(a.x, b.x);
+                            s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                            df = __fsub_rn(a.y, b.y);
+                            s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                            df = __fsub_rn(a.z, b.z);
+                            s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                            df = __fsub_rn(a.w, b.w);
+                            s[i] = __fadd_rn(s[i], __fmul_rn(df, df));
+                        }
+                    }
+                }
 #pragma unroll
-                                for (int m = 0; m < KMAX; ++m) {
-                                    if (lex_less(cd, ci, ld[m], li[m])) {
-                                        float td = ld[m]; int ti = li[m];
-                                        ld[m] = cd; li[m] = ci;
-                                        cd = td; ci = ti;
-                                    }
+                for (int i = 0; i < kChunkPassMax; ++i) {
+                    if (i < n_pass && (size_t) (cj[i] + lane) < nt) {
+                        float cd = __fsqrt_rn(s[i]);
+                        int ci = cj[i] + lane;
+                        // invalid (non-finite) train rows are never candidates (reference :661); only such a row -- or an
+                        // overflowing sum -- can give a non-finite distance, so validity is looked up on that path alone
+                        const bool ok = cd < INFINITY || t_valid[ci] != 0;
+                        if (ok && lex_less(cd, ci, ld[KMAX - 1], li[KMAX - 1])) {
+#pragma unroll
+                            for (int m = 0; m < KMAX; ++m) {
+                                if (lex_less(cd, ci, ld[m], li[m])) {
+                                    float td = ld[m]; int ti = li[m];
+                                    ld[m] = cd; li[m] = ci;
+                                    cd = td; ci = ti;
                                 }
                             }
                         }
                     }
-                    __syncwarp();
+                }
+                __syncwarp();   // slab and surv[] reads done before the next pass / the next compaction
+            }
+        };
+        if (work && cur.total > 0) {
+            int n_surv = 0;
+            const int n_groups = (cur.total + 31) >> 5;
+            for (int g0 = 0; g0 < n_groups; g0 += 4) {
+                // the entries of up to four groups of 32 list positions: all loads in flight before the first is looked at
+                int jg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u;
+                    jg[u] = -1;
+                    if (g == 0) jg[u] = cur.j0;   // came with the metadata pipeline
+                    else if (g < n_groups) {
+                        int l_sel, c_sel;
+                        rerank_locate(g * 32 + lane, cur.my_len, n_lists, l_sel, c_sel);
+                        if (g * 32 + lane < cur.total) {
+                            const size_t e = ((size_t) l_sel * n_rows + local) * cap + c_sel;
+                            const int j = cand_idx[e];
+                            const float v = cand_val[e];
+                            jg[u] = (j < 0 || (size_t) j >= nt || !(v < cur.thr)) ? -1 : j;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (g0 + u < n_groups) {
+                        const unsigned live = __ballot_sync(0xffffffffu, jg[u] >= 0);
+                        const int n = __popc(live);
+                        if (n_surv + n > kSurvCap) {
+                            gather(n_surv);
+                            n_surv = 0;
+                        }
+                        if (jg[u] >= 0) surv[n_surv + __popc(live & ((1u << lane) - 1u))] = jg[u];
+                        n_surv += n;
+                    }
                 }
             }
+            gather(n_surv);
         }
         if (first) {   // nothing was gathered for this row
             nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
@@ -948,7 +980,8 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
     if (n_lists > kMaxLists) return cudaErrorInvalidValue;
     if (chunk_entries) {
         if (!cand_val || !cand_thr) return cudaErrorInvalidValue;
-        const size_t per_warp = chunk_warp_bytes(dp) + 8;
+        const int G = chunk_pass(dp);
+        const size_t per_warp = chunk_warp_bytes(dp, G) + 8;
         int warps = (int) ((220 * 1024) / per_warp);
         if (warps > 16) warps = 16;
         if (warps < 1) return cudaErrorInvalidValue;
@@ -963,7 +996,7 @@ cudaError_t launch_rerank(const float *q_f32, const uint8_t *q_valid, int dp, in
         rerank_chunks_kernel<K><<<blocks, warps * 32, smem, st>>>(                                              \
             q_f32, q_valid, dp, dim, t_f32, t_valid, nt, (long long) t_index_offset, row_begin, n_rows, k,      \
             cand_idx, cand_cnt, n_lists, cap, cand_val, cand_thr, idx, dist, count, flag_rows, counters,        \
-            row_map);                                                                                           \
+            row_map, G);                                                                                        \
         return cudaGetLastError();                                                                              \
     } while (0)
         if (k <= 1) B200M_RERANK_CHUNK_CASE(1);
