@@ -109,15 +109,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A wedged pipeline traps after ~2 s instead of hanging the GPU (the launch then fails with cudaErrorLaunchFailure).  No
+// printf on the time-out path: with a call there ptxas keeps nothing in uniform registers across the waits and re-derives
+// every MMA descriptor per tile (126 instead of 81 instructions between two tiles' first MMAs in the issuer warps, a
+// 32-byte larger stack frame) -- no measurable change in kernel time, but nothing to pay for (profiles/r02_notes.md 11).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > kWaitLimitCycles) {
-            printf("b200match: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-                   blockIdx.y, threadIdx.x, bar, parity);
-            __trap();
-        }
+        if (clock64() - t0 > kWaitLimitCycles) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1) {
@@ -964,8 +964,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                                 tc_mma<PAIR>(tmem_d, desc_a0 + 2, db + 2, idesc_h, 1u, (uint32_t) (nk > 1));
                                 tc_mma<PAIR>(tmem_d, desc_a0 + 4, db + 4, idesc_h, 1u, (uint32_t) (nk > 2));
                                 tc_mma<PAIR>(tmem_d, desc_a0 + 6, db + 6, idesc_h, 1u, (uint32_t) (nk > 3));
-                                tc_commit_2sm_mcast(bar_empty0 + 8u * (uint32_t) i, (uint16_t) 3);
+                                // the accumulator's commit first: it is on the hand-off chain, the operand ring is 12 stages deep
                                 tc_commit_2sm_mcast(bar_tfull0 + 8u * (buf * 2u + hf), (uint16_t) 3);
+                                tc_commit_2sm_mcast(bar_empty0 + 8u * (uint32_t) i, (uint16_t) 3);
                             }
                             __syncwarp();
                             if (kTraceBuild && tr_on) tr[ti][3] = clock64();
