@@ -403,6 +403,7 @@ def run_b200(args, wl):
                     "algorithmic_flops_per_step": flops_per_step,
                     "breakdown_ms_per_step": {x: st[x] / steps for x in ("ms_pack", "ms_prepare", "ms_candidates", "ms_rerank",
                                                                         "ms_fallback", "ms_filter")},
+                    # train rows the re-rank scored exactly per query row (FPFH kernels: 32 per surviving chunk entry)
                     "candidates_per_row": st["candidates"] / max(st.get("rows_answered") or st["rows_total"], 1),
                     "query_rows_searched_frac": (st.get("rows_answered") or st["rows_total"]) / max(st["rows_total"], 1),
                     "rows_overflowed_frac": st["rows_flagged"] / max(st["rows_total"], 1)}

@@ -559,7 +559,6 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
             nxt = rerank_fetch_row(nxt_lens, local + stride, n_rows, cand_idx, cand_val, n_lists, cap, nt, lane);
             nxt_lens = rerank_fetch_lens(local + 2 * stride, n_rows, row_begin, cand_cnt, cand_thr, q_valid, n_lists, lane, row_map);
         } else {
-            my_cands += (unsigned long long) cur.total;
             for (int base = 0; base < cur.total; base += 32) {
                 int j = cur.j0;
                 if (base > 0) {   // list positions beyond the first 32 (rare): fetched on the spot
@@ -576,6 +575,7 @@ rerank_kernel(const float *__restrict__ q_f32, const uint8_t *__restrict__ q_val
                 const unsigned live = __ballot_sync(0xffffffffu, j >= 0);
                 const int n_live = __popc(live);
                 const int slot = __popc(live & ((1u << lane) - 1u));
+                my_cands += (unsigned long long) n_live;   // train rows evaluated exactly (entries the final threshold pruned are not)
                 for (int p0 = 0; p0 < n_live; p0 += G) {
                     const bool mine = j >= 0 && slot >= p0 && slot < p0 + G;
                     // earlier (generic-proxy) reads of the slab are ordered before the asynchronous writes that follow
