@@ -36,10 +36,8 @@ namespace {
 constexpr int kATileBytes = B200M_TILE_M * 128;   // one 64-half K atom of the query tile
 constexpr int kStageBytes = B200M_TILE_N * 128;   // one 64-half K atom of a train tile
 constexpr int kTmemCols = 512;
-constexpr int kTailBytes = 17696;        // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B) + row
-                                         // constants (2 KB) + the hit ring of the worker-warp epilogue (control, flags, headers,
-                                         // 48 x 128 B of values) + 512 list counters + the lists' published smallest values (4 KB)
-constexpr int kRingCap = 48;             // hit-ring slots
+constexpr int kTailBytes = 8576;         // barriers (<= 33 x 8 B) + TMEM slot + published thresholds (up to 4 x 128 x 4 B) + row
+                                         // constants (2 KB) + the lists' published smallest values (4 KB)
 constexpr int kMaxStages = 12;
 constexpr int kMaxKAtoms = 10;
 constexpr int kMaxLists = 16;
@@ -75,7 +73,6 @@ struct TcParams {
     float *cand_val;      // [n_lists][n_rows][cap] accumulator value of every entry, or null (EH = 1 kernels only)
     float *cand_thr;      // [n_lists][n_rows] the row's final append threshold (written when cand_val is)
     float *dump;          // debug: raw accumulators of one tile [128][256]
-    int ring_from_tile;   // EPI = 3: hit chunks go to the worker warp from this tile of the sweep on
     int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
                           // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages, 32 = epilogue only
                           // drains TMEM (no filtering), 64 / 128 = force EH = 1 / 2, 256 = fast path only,
@@ -538,134 +535,6 @@ __device__ __forceinline__ bool scan64(const uint32_t (&r0)[32], const uint32_t 
     if (h.m1 < st.thr) h.mask1 = mask_below(r1, st.thr);
     return true;
 }
-// ---- the hit ring (EPI = 3): hit chunks go to a worker warp ------------------------------------------------------------
-// What makes a hit expensive is not the bookkeeping but finding WHICH columns are under the threshold: ~50-150 ALU-pipe
-// instructions executed by a diverged warp while the other three warps of its scheduler stream their min chains through
-// the same half-rate pipe (~10 cycles per instruction, profiles/r02_notes.md), and every hand-back waits for the slowest
-// of 8 warps.  Here a hitting lane only COPIES the chunk's 32 values (eight 16-byte shared-memory stores: LSU, not ALU)
-// with a 16-byte header into a ring; the otherwise idle fourth service warp pops items -- lane i takes column i: one
-// compare, one ballot -- and appends the columns under the item's threshold to the item's list.  The k-smallest list and
-// the threshold stay with the producing thread (they need only the chunk minimum).  List counters live in shared memory
-// and belong to the worker from the producer's first push on (the producer's warm-up appends come before it).
-struct HitRing {
-    uint32_t ctl;     // [0] head (worker), [1] tail (producers, atomic), [2] epilogue warps finished
-    uint32_t ready;   // [kRingCap] u32: lap number + 1 of the item the slot holds
-    uint32_t hdr;     // [kRingCap] x 16 B: list slot (list * 128 + row), first train row of the chunk, threshold bits
-    uint32_t vals;    // [kRingCap] x 128 B
-    uint32_t cnt;     // [4 lists][128 rows] i32: entries appended per list
-};
-__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_volatile_u32(uint32_t a, uint32_t v) {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-// slot layout: the eight 16-byte pieces of an item are rotated by the slot number, so that 32 worker lanes reading piece c
-// of 32 consecutive items spread over all bank groups (4-way instead of 32-way conflicts)
-__device__ __forceinline__ void ring_push(const HitRing &q, const uint32_t (&r)[32], uint32_t list_slot, int col0, float thr) {
-    uint32_t slot;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(q.ctl + 4u) : "memory");
-    if ((int) (slot - lds_volatile_u32(q.ctl)) >= kRingCap) {   // ring full: wait for the worker
-        const long long t0 = clock64();
-        while ((int) (slot - lds_volatile_u32(q.ctl)) >= kRingCap) {
-            if (clock64() - t0 > kWaitLimitCycles) {
-                printf("b200match: hit ring stuck (block %d,%d thread %d slot %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, slot);
-                __trap();
-            }
-        }
-    }
-    const uint32_t pos = slot % (uint32_t) kRingCap, va = q.vals + pos * 128u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(va + 16u * (((uint32_t) j + pos) & 7u)), "r"(r[4 * j]),
-                     "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                     : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q.hdr + pos * 16u), "r"(list_slot), "r"((uint32_t) col0),
-                 "r"(__float_as_uint(thr)), "r"(0u)
-                 : "memory");
-    __threadfence_block();
-    sts_volatile_u32(q.ready + pos * 4u, slot / (uint32_t) kRingCap + 1u);
-}
-// The worker: every lane takes ONE of the next (up to 32) published items -- 32 compares, a reservation in the item's
-// list (atomic: two lanes may hold items of the same list), the appends -- until every epilogue warp has finished and the
-// ring is empty.  `lists` = this CTA's lists, list `l` of row `row` at lists[(l * n_rows + row0 + row) * cap].
-__device__ void ring_worker(const HitRing &q, int lane, int n_epi_warps, int32_t *__restrict__ lists, size_t n_rows, int row0,
-                            int cap) {
-    uint32_t head = 0;
-    long long t_idle = 0;
-    for (;;) {
-        const uint32_t my = head + (uint32_t) lane, pos = my % (uint32_t) kRingCap;
-        const bool rdy = lds_volatile_u32(q.ready + pos * 4u) == my / (uint32_t) kRingCap + 1u;
-        const uint32_t rm = __ballot_sync(0xffffffffu, rdy);
-        const int n = rm == 0xffffffffu ? 32 : __ffs((int) ~rm) - 1;   // published items in a row, starting at head
-        if (n == 0) {
-            // finished: all epilogue warps have left their tile loops (their pushes are published before that) and nothing
-            // is left between head and tail
-            if (lds_volatile_u32(q.ctl + 8u) == (uint32_t) n_epi_warps && lds_volatile_u32(q.ctl + 4u) == head) break;
-            __nanosleep(256);   // a polling warp takes issue slots from the four epilogue warps of its scheduler
-            const long long now = clock64();
-            if (t_idle == 0) t_idle = now;
-            if (now - t_idle > kWaitLimitCycles) {
-                printf("b200match: hit-ring worker stuck (block %d,%d head %u)\n", blockIdx.x, blockIdx.y, head);
-                __trap();
-            }
-            continue;
-        }
-        t_idle = 0;
-        __threadfence_block();
-        if (lane < n) {
-            uint32_t h0, h1, h2, h3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(q.hdr + pos * 16u) : "memory");
-            (void) h3;
-            const float thr = __uint_as_float(h2);
-            const uint32_t va = q.vals + pos * 128u;
-            uint32_t mask = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float a, b, c, d;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(va + 16u * (((uint32_t) j + pos) & 7u)) : "memory");
-                mask |= (a < thr ? 1u : 0u) << (4 * j) | (b < thr ? 2u : 0u) << (4 * j) | (c < thr ? 4u : 0u) << (4 * j) | (d < thr ? 8u : 0u) << (4 * j);
-            }
-            if (mask) {
-                int slot;
-                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(q.cnt + 4u * h0), "r"((uint32_t) __popc(mask)) : "memory");
-                int32_t *const out = lists + ((size_t) (h0 >> 7) * n_rows + (size_t) (row0 + (int) (h0 & 127u))) * (size_t) cap;
-                while (mask) {
-                    const int i = __ffs((int) mask) - 1;
-                    mask &= mask - 1;
-                    if (slot < cap) out[slot] = (int) h1 + i;
-                    ++slot;
-                }
-            }
-        }
-        __syncwarp();
-        head += (uint32_t) n;
-        if (lane == 0) sts_volatile_u32(q.ctl, head);   // the slots are free again
-    }
-}
-// scan64 for the worker-warp epilogue: hit chunks are pushed, the minima stay for the threshold upkeep (apply64 with empty masks)
-// `own`: the thread still appends by itself (the first tiles of a sweep, where nearly every batch has hits in many lanes and
-// the ring would only fill up); the list counter moves to the worker with the thread's first push (st.cnt < 0 from then on).
-template <int KT>
-__device__ __forceinline__ bool scan64_ring(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int col0, RowState<KT> &st, int k,
-                                            int32_t *__restrict__ out, int cap, Hit64 &h, const HitRing &q, uint32_t list_slot,
-                                            bool own) {
-    if (own || st.T == INFINITY) return scan64<KT>(r0, r1, col0, st, k, out, cap, h);
-    h.m0 = min32(r0);
-    h.m1 = min32(r1);
-    h.mask0 = h.mask1 = 0u;
-    if (!(fminf(h.m0, h.m1) < st.thr)) return false;   // inactive rows carry thr = -inf
-    if (st.cnt >= 0) {   // hand the list counter over
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(q.cnt + 4u * list_slot), "r"((uint32_t) st.cnt) : "memory");
-        st.cnt = -1;
-    }
-    if (h.m0 < st.thr) ring_push(q, r0, list_slot, col0, st.thr);
-    if (h.m1 < st.thr) ring_push(q, r1, list_slot, col0 + 32, st.thr);
-    return true;
-}
-
 // needs only the masks and minima: may run after the accumulators have gone back (the masks were taken with a threshold
 // at least as loose as the current one, so the list stays a superset)
 template <int KT>
@@ -747,6 +616,8 @@ __device__ __forceinline__ void chunk_hits(float m0, float m1, float m2, float m
 //         fast path only 2.78 ms, full kernel 3.91 ms -- the append / threshold path of the first batch stalls the chain).
 //       2 ("quarter columns"): a warp owns 64 columns of EVERY tile; the half of the accumulator (N = 128 MMA) goes back
 //         as soon as both of its 64-column warps have their values in registers, all filtering happens off the chain.
+//       4, 5 ("chunk entries", the default): alternating tiles, but a list entry is a 32-column chunk (first train row,
+//         minimum) instead of a column -- see chunk_hits; drained by 32-column (4) or 16-column (5) TMEM loads.
 template <int KT, bool PAIR, int EH, bool SPLITN, int EPI, bool DBG>
 __global__ void __launch_bounds__(EPI ? 640 : 64 + 128 * EH + (SPLITN ? 32 : 0), 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
@@ -755,7 +626,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     float *const dump = DBG ? p.dump : nullptr;
     constexpr bool ALT = EPI != 0;   // the sixteen-warp layouts (warp roles, register re-division, four lists per row)
     constexpr bool QE = EPI == 2;
-    constexpr bool RING = EPI == 3;  // alternating tiles + hit chunks handed to the worker warp (service warp 3)
     constexpr bool CHK = EPI == 4 || EPI == 5;   // alternating tiles, list entries are 32-column chunks (first train row, minimum);
                                                  // 4: chunk-by-chunk drain (next load in flight under a min chain), 5: two loads per wait
     constexpr int kEpiWarps = 4 * EH * (ALT ? 2 : 1);
@@ -789,13 +659,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t tmem_slot = bar_tempty0 + 8u * kAcc;
     const uint32_t s_thr = (tmem_slot + 8u + 15u) & ~15u;                // published thresholds: [2][128] f32 per column half; ALT: [128][4]
     const uint32_t s_rowc = s_thr + 2048u;                               // [128][4] f32: per-row certificate constants
-    HitRing ring;                                                        // EPI = 3 (see ring_push / ring_worker)
-    ring.ctl = s_rowc + 2048u;
-    ring.ready = ring.ctl + 16u;
-    ring.hdr = ring.ready + 4u * (uint32_t) kRingCap;
-    ring.vals = ring.hdr + 16u * (uint32_t) kRingCap;
-    ring.cnt = ring.vals + 128u * (uint32_t) kRingCap;
-    const uint32_t s_pub = (ring.cnt + 2048u + 31u) & ~31u;              // [128 rows][4 lists] x {smallest, second smallest} f32; a row's
+    const uint32_t s_pub = (s_rowc + 2048u + 31u) & ~31u;                // [128 rows][4 lists] x {smallest, second smallest} f32; a row's
                                                                          // four slots share one 32-byte line (retighten relies on it)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -834,10 +698,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                          : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
-    }
-    if (RING && warp == 3) {
-        for (int i = lane; i < kRingCap; i += 32) sts_volatile_u32(ring.ready + 4u * (uint32_t) i, 0u);
-        if (lane < 3) sts_volatile_u32(ring.ctl + 4u * (uint32_t) lane, 0u);
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
@@ -1081,17 +941,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             }   // general issue loop
         }
-    } else if (RING && warp == 3) {
-        // ===== hit-ring worker: appends the columns of the pushed chunks that are under the item's threshold =====
-        const int row0 = qtile * B200M_TILE_M;
-        ring_worker(ring, lane, kEpiWarps, p.cand_idx + (size_t) split * kListsPerSplit * (size_t) p.n_rows * (size_t) p.cap,
-                    (size_t) p.n_rows, row0, p.cap);
-        // the lists' final lengths (a count above cap marks an overflowed list)
-        for (int i = lane; i < kListsPerSplit * B200M_TILE_M; i += 32) {
-            const int row = row0 + (i & (B200M_TILE_M - 1));
-            if (row < p.n_rows)
-                p.cand_cnt[(size_t) (split * kListsPerSplit + (i >> 7)) * p.n_rows + row] = (int32_t) lds_u32(ring.cnt + 4u * (uint32_t) i);
-        }
     }
     } else {
         if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
@@ -1120,8 +969,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             if (!ALT) asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(st.s_pub_own + 16u), "f"(INFINITY) : "memory");
             asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(st.s_pub_own), "f"(INFINITY) : "memory");
         }
-        const uint32_t list_slot = (uint32_t) ((bsel * 2 + half) * B200M_TILE_M + row_in_tile);   // EPI = 3: ring.cnt index
-        if (RING) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring.cnt + 4u * list_slot), "r"(0u) : "memory");
         {
             const float na = active ? p.q_norm16[p.q_row0 + local] : 0.f;
             const float ab = sqrtf(na) + p.bmax;
@@ -1141,8 +988,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) (half * kColsPerWarp);
         // SPLITN: this warp's hand-off barriers are those of its column half (index buf * 2 + half)
         const uint32_t acc_stride = SPLITN ? 16u : 8u;
-        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || CHK) ? 16u * (uint32_t) bsel : 0u);
-        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || EPI == 3 || CHK) ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tfull_mine = bar_tfull0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || CHK) ? 16u * (uint32_t) bsel : 0u);
+        const uint32_t tempty_mine = bar_tempty0 + (SPLITN ? 8u * (uint32_t) half : 0u) + ((EPI == 1 || CHK) ? 16u * (uint32_t) bsel : 0u);
         const uint32_t tempty_dst0 = PAIR ? map_to_cta(tempty_mine, 0) : tempty_mine;
         // The addresses the tile loop needs, as opaque register values: left to itself ptxas re-derives them on every tile
         // (shared-window base from %cluster_ctaid, kernel parameters from constant memory, threadIdx: ~40 instructions,
@@ -1289,8 +1136,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                             h0.m1 = min32(r1);
                             h0.mask0 = h0.mask1 = 0u;
                             hit0 = fminf(h0.m0, h0.m1) < st.thr;
-                        } else if (RING) {
-                            hit0 = scan64_ring<KT>(r0, r1, col_base, st, k, out, cap, h0, ring, list_slot, lt < p.ring_from_tile);
                         } else {
                             hit0 = scan64<KT>(r0, r1, col_base, st, k, out, cap, h0);
                         }
@@ -1335,19 +1180,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (hit1) apply64<KT>(h1, col_base + 128, st, k, out, cap);
                     if (__any_sync(0xffffffffu, hit1)) ++hits[ph][1];
                     cyc[ph][2] += clock64() - c0;
-                } else if (RING) {
-                    Hit64 h1;
-                    if (scan64_ring<KT>(r0, r1, col_base + 128, st, k, out, cap, h1, ring, list_slot, lt < p.ring_from_tile))
-                        apply64<KT>(h1, col_base + 128, st, k, out, cap);
                 } else {
                     process64<KT>(r0, r1, col_base + 128, st, k, out, cap);
                 }
                 if (kTraceBuild && etr_on) etr[eti][4] = clock64();
-            }
-            if (RING) {   // this warp's pushes are published: tell the worker
-                if (st.cnt >= 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring.cnt + 4u * list_slot), "r"((uint32_t) st.cnt) : "memory");
-                __syncwarp();
-                if (lane == 0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(ring.ctl + 8u) : "memory");
             }
             if (kTraceBuild && etrace && lane == 0)
                 for (int i = 0; i < kTraceTiles / 2; ++i) {
@@ -1447,7 +1283,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                        tr[i][0], tr[i][1], tr[i][2], tr[i][3]);
         }   // !ALT
         if ((dflags & 256) && st.cnt == -1) p.cand_cnt[0] = 0;   // keeps the experiment's arithmetic alive
-        if (active && !dump && !RING) {   // (EPI = 3: the worker owns the list counters)
+        if (active && !dump) {
             p.cand_cnt[list_row] = st.cnt;
             if (EH == 1 || CHK) p.cand_thr[list_row] = st.thr;
         }
@@ -1600,12 +1436,13 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     const bool splitn = p.lean && eh == 2 && ctx->tc_splitn != 0 && !dump;
     // ... with sixteen epilogue warps of 64 accumulators each.  B200M_TC_ALT: 4 / 5 (default) alternating tiles with CHUNK
     // entries -- a list entry is a 32-column chunk and its minimum, the re-rank evaluates the surviving chunks' rows -- drained
-    // by 32-column (4) or 16-column (5) TMEM loads; 1 alternating tiles, 2 quarter columns of every tile, 3 alternating tiles +
-    // worker warp (all three: column entries); 0 eight warps of 128 accumulators, every warp on every tile.  Measured per
+    // by 32-column (4) or 16-column (5) TMEM loads; 1 alternating tiles, 2 quarter columns of every tile (both: column entries);
+    // 0 eight warps of 128 accumulators, every warp on every tile.  (A third column-entry layout, hit chunks handed to a worker
+    // warp through a shared-memory ring, was exact and slower -- profiles/r02_notes.md section 5 -- and is gone.)  Measured per
     // launch, same boxes (profiles/r02_cand_epilogue_modes.log, r02_cand_chunk_entries.log): C2 k = 2 -- 4.10 (0) / 3.75 (1) /
     // 3.85 (2) / 3.08 (4) / 3.03 ms (5); C4 k = 5 -- 492 (0) / 530 (1) / 438 (2) / 398 (4) / 459 ms (5: spills at KT = 8).
     const int alt_pick = ctx->tc_alt >= 0 ? ctx->tc_alt : (k <= 2 ? 5 : 4);
-    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick == 3 ? 3 : alt_pick == 4 ? 4 : alt_pick == 5 ? 5 : alt_pick != 0 ? 2 : 0) : 0;
+    const int epi = splitn ? (alt_pick == 1 ? 1 : alt_pick == 4 ? 4 : alt_pick == 5 ? 5 : alt_pick != 0 ? 2 : 0) : 0;
     const bool alt = epi != 0;
     const int lists_per_split = eh * (alt ? 2 : 1);
     int n_splits = 1;
@@ -1665,7 +1502,6 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     *has_values_out = epi >= 4 ? 2 : eh == 1 ? 1 : 0;
     p.dump = dump;
     p.debug_flags = ctx->tc_debug;
-    p.ring_from_tile = ctx->tc_ring_from;
     if (dump) p.tiles_per_split = (int) dump_t_tile;
     const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + kTailBytes;
     dim3 grid((unsigned) (dump ? cluster : (n_qtiles + cluster - 1) / cluster * cluster), (unsigned) n_splits, 1);
@@ -1675,7 +1511,6 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
 #define B200M_TC_CASE2(KT_, DBG_)                                                             \
     rc = pair ? (eh == 2 ? (epi == 5 ? launch_tc<KT_, true, 2, true, 5, DBG_>(ctx, mq, mt, p, grid, smem)        \
                             : epi == 4 ? launch_tc<KT_, true, 2, true, 4, DBG_>(ctx, mq, mt, p, grid, smem)      \
-                            : epi == 3 ? launch_tc<KT_, true, 2, true, 3, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 2 ? launch_tc<KT_, true, 2, true, 2, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : epi == 1 ? launch_tc<KT_, true, 2, true, 1, DBG_>(ctx, mq, mt, p, grid, smem)      \
                             : splitn ? launch_tc<KT_, true, 2, true, 0, DBG_>(ctx, mq, mt, p, grid, smem)        \

@@ -78,9 +78,9 @@ struct b200m_ctx {
                                      // costs more than it saves)
     int tc_splits = 0;     // B200M_TC_SPLITS: 0 = chosen per launch (wave balance); > 0 forces the number of train splits
     int tc_splitn = 1;     // split-N candidate kernel for one-atom descriptors (B200M_TC_SPLITN=0: one N = 256 MMA per tile)
-    int tc_alt = -1;       // B200M_TC_ALT: epilogue layout of the split-N kernel (1 alternating tiles, 2 quarter columns, 0 eight
-                           // warps); -1 = by measurement: alternating tiles up to k = 4, quarter columns beyond
-    int tc_ring_from = 64; // B200M_TC_RING_FROM: worker-warp epilogue (B200M_TC_ALT=3) takes over from this tile of a sweep on
+    int tc_alt = -1;       // B200M_TC_ALT: epilogue layout of the split-N kernel (4 / 5 chunk entries drained by 32- / 16-column
+                           // TMEM loads; column entries: 1 alternating tiles, 2 quarter columns, 0 eight warps);
+                           // -1 = by measurement: 5 up to k = 2, 4 beyond
     int tc_lean = 1;       // B200M_TC_LEAN=0: general MMA issue loop also for one-atom descriptors (comparison)
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
     int tc_pair = 1;       // 1 = CTA-pair (cta_group::2) candidate kernel; 0 = cta_group::1 + multicast (B200M_TC_MODE=mcast)

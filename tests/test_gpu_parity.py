@@ -323,18 +323,18 @@ def test_properties_at_bench_scale():
     _same((idx[rows], dist[rows], cnt[rows]), eo)
 
 
-@pytest.mark.parametrize("layout", ["eight-warps", "alternating-tiles", "quarter-columns", "worker-warp", "chunk-entries", "chunk-entries-x16"])
+FPFH_LAYOUTS = {"eight-warps": 0, "alternating-tiles": 1, "quarter-columns": 2, "chunk-entries": 4, "chunk-entries-x16": 5}
+
+
+@pytest.mark.parametrize("layout", list(FPFH_LAYOUTS))
 @pytest.mark.parametrize("nq,nt,k", [(2500, 40000, 2), (700, 21000, 5), (300, 600, 1), (900, 12345, 11)])
 def test_fpfh_epilogue_layouts(monkeypatch, layout, nq, nt, k):
     """The production (split-N) FPFH candidate kernel with each epilogue layout -- eight warps of 128 accumulators, sixteen
-    warps bound to one accumulator buffer (alternating tiles), sixteen warps of 64 columns of every tile, and alternating
-    tiles with the hit chunks handed to a worker warp through a shared-memory ring (from tile 4 on here, so that the hand-over
-    of the list counters happens inside the test's sweep), and alternating tiles with 32-column chunks as list entries (the
-    re-rank evaluates every train row of a surviving chunk; 12345 train rows: a ragged last chunk; drained by 32- or by
-    16-column TMEM loads) -- oracle-exact lists in both directions."""
-    monkeypatch.setenv("B200M_TC_ALT", str(["eight-warps", "alternating-tiles", "quarter-columns", "worker-warp", "chunk-entries",
-                                            "chunk-entries-x16"].index(layout)))
-    monkeypatch.setenv("B200M_TC_RING_FROM", "4")
+    warps bound to one accumulator buffer (alternating tiles), sixteen warps of 64 columns of every tile (all three with
+    columns as list entries), and the default: alternating tiles with 32-column CHUNKS as list entries (the re-rank evaluates
+    every train row of a surviving chunk; 12345 train rows: a ragged last chunk), drained by 32- or by 16-column TMEM loads
+    -- oracle-exact lists in both directions."""
+    monkeypatch.setenv("B200M_TC_ALT", str(FPFH_LAYOUTS[layout]))
     src, tgt, dim = synth.make_pair("fpfh", nq, nt, nan_frac=0.01)
     with M.Context(0) as ctx:
         ctx.upload(0, src, dim)
