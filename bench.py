@@ -14,6 +14,8 @@ across ranks, both descriptor sets replicated; one NCCL all-gather of the revers
 cannot be built here: PCL/OpenCV/FLANN absent) on the host cores, bounded sample per step.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -546,10 +548,29 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the embedded c2 / c4 lines of a default (c3, 1 GPU) run")
     ap.add_argument("--other-configs", action="store_true", help="several GPUs: also embed the c4 (query-sharded) and c5 (target-sharded) lines")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args, args.workload)
-    else:
-        run_b200(args, args.workload)
+    # stdout carries the ONE JSON line and nothing else: whatever a library prints through C stdio or fd 1 during the run
+    # (NCCL's "NCCL version ..." banner does, on boxes where NCCL_DEBUG defaults to VERSION, NCCL_DEBUG_FILE or not) goes to
+    # stderr; the line itself is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args, args.workload)
+            else:
+                run_b200(args, args.workload)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.strip()]
+    for ln in lines[:-1]:            # anything python printed besides the line: to stderr
+        sys.stderr.write(ln + "\n")
+    if lines:
+        sys.stdout.write(lines[-1] + "\n")
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
