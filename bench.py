@@ -465,12 +465,21 @@ def run_b200(args, wl):
                 torch.cuda.current_stream().synchronize()
                 moved[1] = (lists_h[0].numel() + lists_h[1].numel() + lists_h[2].numel()) * 4 if rank == 0 else 0
                 return None, None
-            moved[0] = sm.upload_host_sharded(0, src_pin, dim) + sm.upload_host_sharded(1, tgt_pin, dim)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]   # the library queues on torch's current stream
+            ev[0].record()
+            moved[0] = sm.upload_host_sharded(0, src_pin, dim)
+            ev[1].record()
+            moved[0] += sm.upload_host_sharded(1, tgt_pin, dim)
+            ev[2].record()
             rec, _ = be.ctx.match_sharded(k, mode)
+            ev[3].record()
+            phases.append(ev)
             moved[1] = rec.shape[0] * 16 + 16
             return None, None
+        phases = []
         for _ in range(2):
             step_e2e_multi()
+        del phases[:]
         ms, _ = timed(step_e2e_multi, n_steps)
         tot = torch.tensor(moved, device=dev, dtype=torch.int64)
         dist.all_reduce(tot)
@@ -478,6 +487,24 @@ def run_b200(args, wl):
                       "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": ms / n_steps,
                       "api": "b200m_upload_replicated x 2 + b200m_match_sharded on every rank (pinned host buffers)",
                       "replication": "each rank copies 1/N of a replicated set over PCIe, NCCL all-gather over NVLink"}
+        if phases:
+            # where rank 0's end-to-end step goes (CUDA events between the three calls), and what its two transfers cost when
+            # nothing else runs: this rank's 1/N slice host -> device, and an all-gather of a replicated set's raw rows
+            torch.cuda.synchronize()
+            names = ("upload_replicated_src", "upload_replicated_tgt", "match_sharded_incl_result_copy")
+            res["e2e"]["rank0_breakdown_ms"] = {nm: sum(p[i].elapsed_time(p[i + 1]) for p in phases) / len(phases) for i, nm in enumerate(names)}
+            lo, hi = D.shard_bounds(n_src, rank, world)
+            slab = torch.empty((hi - lo, src_pin.shape[1]), dtype=torch.float32, device=dev)
+            rows = (n_src + world - 1) // world
+            full = torch.empty((rows * world, src_pin.shape[1]), dtype=torch.float32, device=dev)
+            part = torch.zeros((rows, src_pin.shape[1]), dtype=torch.float32, device=dev)
+            alone = {}
+            for nm, fn in (("h2d_slice_alone", lambda: slab.copy_(src_pin[lo:hi], non_blocking=True)),
+                           ("allgather_raw_rows_alone", lambda: dist.all_gather_into_tensor(full, part))):
+                fn()
+                t_ms, _ = timed(fn, 3)
+                alone[nm] = t_ms / 3
+            res["e2e"]["rank0_breakdown_ms"].update(alone)
         return res
 
     desc, n_src, n_tgt, k, mode_name, cfg = WORKLOADS[wl]
