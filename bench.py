@@ -196,6 +196,28 @@ class CpuReference:
         return nq / secs, self.cores, sample, secs
 
 
+def opencv_knn(q, t, k, block=10000):
+    """k nearest train rows of every query row with cv2.BFMatcher(NORM_L2).knnMatch over train blocks of `block` rows, the
+    per-block lists merged in block order (stable: an earlier block's entry stays in front of an equal later one) ->
+    (idx [nq, k] int64, -1 padded; dist [nq, k] float32, +inf padded).  tests/test_bench_host.py checks it against the oracle."""
+    import cv2
+    matcher = cv2.BFMatcher(cv2.NORM_L2)
+    nq = q.shape[0]
+    bd = np.full((nq, k), np.inf, np.float32)
+    bi = np.full((nq, k), -1, np.int64)
+    for t0 in range(0, t.shape[0], block):
+        res = matcher.knnMatch(q, t[t0:t0 + block], k)
+        d = np.full((nq, k), np.inf, np.float32)
+        i = np.full((nq, k), -1, np.int64)
+        for r, lst in enumerate(res):
+            for c, m in enumerate(lst):
+                d[r, c], i[r, c] = m.distance, m.trainIdx + t0
+        alld, alli = np.concatenate([bd, d], 1), np.concatenate([bi, i], 1)
+        order = np.argsort(alld, 1, kind="stable")[:, :k]
+        bd, bi = np.take_along_axis(alld, order, 1), np.take_along_axis(alli, order, 1)
+    return bi, bd
+
+
 def opencv_bfmatcher_rate(ref, budget_s, block=10000):
     """The third-party routine the reference's matchBF calls -- cv::BFMatcher(NORM_L2).knnMatch, here through Python's cv2 -- in
     the reference's blocking (bf_block_size = 10000 train rows per call, include/matching.h:594-634) with the per-block results
@@ -207,29 +229,12 @@ def opencv_bfmatcher_rate(ref, budget_s, block=10000):
     except ImportError:
         return None
     cv2.setNumThreads(ref.cores)
-    matcher = cv2.BFMatcher(cv2.NORM_L2)
-
-    def knn(q, t):
-        nq = q.shape[0]
-        bd = np.full((nq, ref.k), np.inf, np.float32)
-        bi = np.full((nq, ref.k), -1, np.int64)
-        for t0 in range(0, t.shape[0], block):
-            res = matcher.knnMatch(q, t[t0:t0 + block], ref.k)
-            d = np.full((nq, ref.k), np.inf, np.float32)
-            i = np.full((nq, ref.k), -1, np.int64)
-            for r, lst in enumerate(res):
-                for c, m in enumerate(lst):
-                    d[r, c], i[r, c] = m.distance, m.trainIdx + t0
-            alld, alli = np.concatenate([bd, d], 1), np.concatenate([bi, i], 1)
-            order = np.argsort(alld, 1, kind="stable")[:, :ref.k]
-            bd, bi = np.take_along_axis(alld, order, 1), np.take_along_axis(alli, order, 1)
-        return bi, bd
 
     def run(nq):
         t_0 = time.perf_counter()
-        knn(ref.s[:nq], ref.t)
+        opencv_knn(ref.s[:nq], ref.t, ref.k, block)
         if ref.both:
-            knn(ref.t[:nq], ref.s)
+            opencv_knn(ref.t[:nq], ref.s, ref.k, block)
         return time.perf_counter() - t_0
     nq = max(ref.cores * 8, 128)
     secs = run(nq)

@@ -3,6 +3,9 @@ import os
 import sys
 import time
 
+import numpy as np
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
@@ -74,3 +77,22 @@ def test_roofline_traffic_is_read_from_a_committed_profile():
     b, src = bench.ncu_traffic("c3")
     assert b and b > 1e9 and os.path.exists(os.path.join(ROOT, src.split(" ")[0]))
     assert bench.ncu_traffic("no-such-workload") == (None, None)
+
+
+def test_opencv_baseline_path_agrees_with_the_oracle():
+    """bench.py's second CPU engine -- cv2.BFMatcher in the reference's blocking, the routine matchBF calls -- returns the
+    oracle's neighbours (indices on tie-free data, distances within the 1e-5 the north star states) on small random
+    descriptors: the two CPU baselines time the same computation."""
+    cv2 = pytest.importorskip("cv2")
+    import bench
+    from oracle import oracle as orc
+    rng = np.random.default_rng(5)
+    for dim, k in ((33, 2), (352, 5)):
+        q = rng.random((300, dim), dtype=np.float32)
+        t = rng.random((2500, dim), dtype=np.float32)
+        idx, dist = bench.opencv_knn(q, t, k, block=1000)
+        oi, od, oc = orc.knn(q, t, k)
+        assert np.array_equal(idx, oi.astype(np.int64))
+        assert np.allclose(dist, od, rtol=1e-5, atol=0)
+        assert np.all(oc == k)
+    assert cv2.__version__
