@@ -154,7 +154,7 @@ void b200m_destroy(b200m_ctx *ctx) {
                     &ctx->ws_out, &ctx->ws_misc, &ctx->ws_fidx, &ctx->ws_fdist, &ctx->ws_fcnt, &ctx->ws_ridx,
                     &ctx->ws_rdist, &ctx->ws_rcnt, &ctx->ws_corr, &ctx->ws_totals, &ctx->ws_part_i, &ctx->ws_part_d,
                     &ctx->ws_done, &ctx->ws_cand_val, &ctx->ws_cand_thr, &ctx->ws_row_list, &ctx->ws_row_flags,
-                    &ctx->ws_sel_ops, &ctx->ws_sel_norm};
+                    &ctx->ws_sel_ops, &ctx->ws_sel_norm, &ctx->ws_sweep_hint};
     for (DevBuf *b : ws) b->release();
     tc_release(ctx);
     multiscale_release(ctx);

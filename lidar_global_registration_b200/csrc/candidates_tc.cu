@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "internal.cuh"
 
@@ -73,6 +74,9 @@ struct TcParams {
     float *cand_val;      // [n_lists][n_rows][cap] accumulator value of every entry, or null (EH = 1 kernels only)
     float *cand_thr;      // [n_lists][n_rows] the row's final append threshold (written when cand_val is)
     float *dump;          // debug: raw accumulators of one tile [128][256]
+    int sweep_lag;        // tiles between consecutive followers of the rotated sweep; 0: every pair starts at tile 0
+    int *sweep_hint;      // [train splits] how many tiles the most advanced CTA pair of a split has swept since the launch began
+                          // (chunk-entry kernels: a pair starts a fixed distance behind it and wraps around)
     int debug_flags;      // timing experiments only (B200M_TC_DEBUG): 1 = epilogue skips its work, 2 = no MMAs issued,
                           // 4 = no B loads (pair mode), 8 / 16 = ring limited to 4 / 6 stages, 32 = epilogue only
                           // drains TMEM (no filtering), 64 / 128 = force EH = 1 / 2, 256 = fast path only,
@@ -657,6 +661,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t bar_tfull0 = bar_a + 8u;
     const uint32_t bar_tempty0 = bar_tfull0 + 8u * kAcc;                  // SPLITN: index buf * 2 + half
     const uint32_t tmem_slot = bar_tempty0 + 8u * kAcc;
+    const uint32_t s_start = tmem_slot + 4u;                              // first tile of this CTA pair's sweep (CHK kernels)
     const uint32_t s_thr = (tmem_slot + 8u + 15u) & ~15u;                // published thresholds: [2][128] f32 per column half; ALT: [128][4]
     const uint32_t s_rowc = s_thr + 2048u;                               // [128][4] f32: per-row certificate constants
     const uint32_t s_pub = (s_rowc + 2048u + 31u) & ~31u;                // [128 rows][4 lists] x {smallest, second smallest} f32; a row's
@@ -699,12 +704,35 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
+    // Chunk-entry kernels can sweep the train tiles of their split in ROTATED order (the selection does not care in which
+    // order the tiles come).  Started at tile 0, the CTA pairs of a long launch spread over the whole operand array (C4:
+    // 256 MB against 126 MB of L2) and re-read it from DRAM -- 577 GB per launch against 0.5 GB of operands
+    // (profiles/r02d_ncu_c4_cand.txt).  With p.sweep_lag > 0 every pair follows the most advanced one at a distance of its
+    // own: the leaders report how far they have come (a running maximum of "tiles since the launch began"), a pair that starts
+    // reads it and begins 16 + lag * (pair number mod 64) tiles behind -- everybody moves at the same speed, so all running
+    // pairs stay inside one window (lag 20: ~1300 tiles, 42 MB), the front runner's misses fill L2 for the rest, and no two
+    // pairs ask for the same line at the same time (pairs in exact lockstep do: their misses are not merged and DRAM traffic
+    // doubles).  Measured on C4: DRAM reads 577 -> 88 GB per launch, 417 -> 372 ms; a window that is too narrow (lag 8) or
+    // wider than L2 (lag 48+) is slower than no rotation.  The leader publishes the start tile to both CTAs of the pair.
+    if (CHK && threadIdx.x == 0 && (p.cluster == 1 || cluster_ctarank() == 0u)) {
+        const int nt_all = t1 - t0;
+        int v_start = 0;
+        if (!dump && nt_all > 1 && p.sweep_lag > 0) {
+            int front;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(front) : "l"(p.sweep_hint + split) : "memory");
+            v_start = front - 16 - p.sweep_lag * (int) ((blockIdx.x >> 1) & 63u);
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_start), "r"(v_start) : "memory");
+        if (p.cluster > 1) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(map_to_cta(s_start, 1)), "r"(v_start) : "memory");
+    }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = lds_u32(tmem_slot);
     const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+    const int sweep_v0 = CHK ? (int) lds_u32(s_start) : 0;   // this pair's position when it starts, in tiles since the launch began
+    const int sweep_start = CHK && t1 - t0 > 1 ? ((sweep_v0 % (t1 - t0)) + (t1 - t0)) % (t1 - t0) : 0;   // ... as a tile of the split
     const uint16_t cmask = (uint16_t) ((1u << p.cluster) - 1u);
 
     // setmaxnreg is a warpgroup-aligned instruction: all four warps of a warpgroup execute the SAME instruction, so the
@@ -732,7 +760,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             uint32_t r_empty = bar_empty0, r_full = bar_full0, r_lead_full = lead_full0, r_sb = sB_u;
             asm volatile("" : "+r"(r_empty), "+r"(r_full), "+r"(r_lead_full), "+r"(r_sb));
             const uint32_t stage_bytes = (uint32_t) (kStageBytes / 2);   // pair mode: half a train tile per CTA
-            for (int t = (dflags & 65536) ? t1 : t0; t < t1; ++t) {
+            int t = t0 + sweep_start;   // rotated sweep (chunk-entry kernels; 0 otherwise): t0 + start, ..., t1 - 1, t0, ...
+            for (int lt = (dflags & 65536) ? t1 - t0 : 0; lt < t1 - t0; ++lt) {
                 for (int a = 0; a < ka; ++a) {
                     mbar_wait(r_empty + 8u * s, ph);
                     if (elect_one()) {
@@ -743,10 +772,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                             tma_load_2d_2sm(r_sb + s * stage_bytes, &tmap_t, r_lead_full + 8u * s, a * 64,
                                             t * B200M_TILE_N + row_off);
                         }
+                        // every 32 tiles the leader says where it is: pairs that start from now on start there
+                        if (CHK && crank == 0 && a == 0 && (lt & 31) == 16 && !dump && p.sweep_lag > 0)
+                            asm volatile("red.relaxed.gpu.global.max.s32 [%0], %1;" ::"l"(p.sweep_hint + split), "r"(sweep_v0 + lt) : "memory");
                     }
                     __syncwarp();
                     if (++s == (uint32_t) stages) { s = 0; ph ^= 1u; }
                 }
+                if (++t == t1) t = t0;
             }
         } else {
             if (elect_one()) {
@@ -1038,10 +1071,16 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
             for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;   // (the in-place loads formally read their destinations)
             const uint32_t taddr = e_tmem + (uint32_t) bsel * (uint32_t) B200M_TILE_N;
-            // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c
-            int col_base = (t0 + bsel) * B200M_TILE_N + half * 64;
+            // train rows of the warp's columns: 0..63 -> tile row half*64 + c (CTA 0's stage rows), 64..127 -> 128 + half*64 + c;
+            // the sweep is rotated: local tile lt is train tile t0 + (sweep_start + lt) mod (t1 - t0)
+            // (kept as ONE running register: the wrap test compares against t1 * 256, half * 64 < 256 does not disturb it)
+            int col_next = (t0 + sweep_start + bsel) * B200M_TILE_N + half * 64;
+            if (col_next >= t1 * B200M_TILE_N) col_next -= (t1 - t0) * B200M_TILE_N;
             uint32_t par = 0;
-            for (int lt = bsel; lt < t1 - t0; lt += 2, col_base += 2 * B200M_TILE_N) {
+            for (int lt = bsel; lt < t1 - t0; lt += 2) {
+                const int col_base = col_next;
+                col_next += 2 * B200M_TILE_N;
+                if (col_next >= t1 * B200M_TILE_N) col_next -= (t1 - t0) * B200M_TILE_N;
                 mbar_wait(e_tfull, par);
                 par ^= 1u;
                 tc_fence_after();
@@ -1501,6 +1540,16 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     // 2: CHUNK entries (first train row of a 32-row chunk, chunk minimum) + final thresholds
     *has_values_out = epi >= 4 ? 2 : eh == 1 ? 1 : 0;
     p.dump = dump;
+    CK(ctx->ws_sweep_hint.reserve(sizeof(int) * 64));   // per launch: the front runner's progress starts at zero
+    if (epi >= 4) CK(cudaMemsetAsync(ctx->ws_sweep_hint.p, 0, sizeof(int) * 64, ctx->stream));
+    {
+        static const int lag_env = getenv("B200M_TC_SWEEP_LAG") ? atoi(getenv("B200M_TC_SWEEP_LAG")) : -1;
+        // default: rotate when the train operands do NOT fit L2 (C4: 256 MB; measured 417 -> 372 ms per launch with 16-24 tiles
+        // between followers, 8 and >= 48 are slower than no rotation; operands that fit L2 show no difference) --
+        // profiles/r02_notes.md section 14
+        p.sweep_lag = lag_env >= 0 ? lag_env : ((size_t) t.n_pad * (size_t) t.kp * 2 > (size_t) 96 << 20 ? 20 : 0);
+    }
+    p.sweep_hint = ctx->ws_sweep_hint.as<int>();
     p.debug_flags = ctx->tc_debug;
     if (dump) p.tiles_per_split = (int) dump_t_tile;
     const size_t smem = (size_t) p.ka * kATileBytes + (size_t) stages * p.stage_bytes + 1024 + kTailBytes;

@@ -60,6 +60,7 @@ struct b200m_ctx {
     TcPrep prep;
     DevBuf ws_cand_idx, ws_cand_cnt, ws_flag_rows, ws_counters, ws_scan, ws_out, ws_misc;
     DevBuf ws_part_i, ws_part_d, ws_done, ws_cand_val, ws_cand_thr;
+    DevBuf ws_sweep_hint;   // [<= 64 train splits] int: where the candidate kernel's CTA pairs currently are in their sweep
     DevBuf ws_row_list, ws_row_flags, ws_sel_ops, ws_sel_norm;   // row selection (masked kNN)
     bool done_init = false;
     DevBuf ws_fidx, ws_fdist, ws_fcnt, ws_ridx, ws_rdist, ws_rcnt, ws_thr[2], ws_corr, ws_totals;
