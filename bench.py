@@ -576,10 +576,15 @@ def run_b200(args, wl):
         for owl, osteps in ((("c2", 10), ("c4", 3)) if world == 1 else (("c4", 3), ("c5", 3))):
             try:
                 torch.cuda.empty_cache()
+                # an independent workload: it does not inherit the clock state of the one before it (after a second of the
+                # SHOT kernel at the 1 kW cap the SM clock stays near 1.5 GHz for a while; a 4 ms FPFH launch measured right
+                # behind it runs 10 % slower than on an idle GPU)
+                torch.cuda.synchronize()
+                time.sleep(3.0)
                 o = measure(owl, osteps, 3, False, True)
                 od = WORKLOADS[owl]
                 others[owl] = {"metric": METRICS[owl], "value": o["value"], "unit": "queries/s", "ms_per_step": o["ms_per_step"],
-                               "steps": osteps, "n_gpus": world, "scaling": "weak" if od[4] == "knn_target_sharded" else "strong",
+                               "steps": osteps, "n_gpus": world, "idle_before_s": 3.0, "scaling": "weak" if od[4] == "knn_target_sharded" else "strong",
                                "config": workload_config(owl, world), "correspondences": o["n_corr"],
                                "clocks": o["clocks"], "roofline": o["roofline"],
                                "parity_note": "ratio filter: defined here, the reference's RatioMatcher is a stub (parity unpinned)"
