@@ -129,6 +129,7 @@ int b200m_create(b200m_ctx **out, int device) {
     if (const char *e = getenv("B200M_TC_LEAN")) ctx->tc_lean = atoi(e);
     if (const char *e = getenv("B200M_TC_SPLITN")) ctx->tc_splitn = atoi(e);
     if (const char *e = getenv("B200M_TC_ALT")) ctx->tc_alt = atoi(e);
+    if (const char *e = getenv("B200M_TC_SWEEP_LAG")) ctx->tc_sweep_lag = atoi(e);
     if (const char *e = getenv("B200M_LOCAL_MIN_ROWS")) ctx->local_min_rows = atoi(e);
     if (const char *e = getenv("B200M_MASKED_MIN_PAIRS")) ctx->masked_min_pairs = atof(e);
     if (const char *e = getenv("B200M_TC_MODE")) {

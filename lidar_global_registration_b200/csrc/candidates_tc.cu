@@ -1542,13 +1542,10 @@ int tc_candidates(b200m_ctx *ctx, int direction, size_t row_begin, size_t n_rows
     p.dump = dump;
     CK(ctx->ws_sweep_hint.reserve(sizeof(int) * 64));   // per launch: the front runner's progress starts at zero
     if (epi >= 4) CK(cudaMemsetAsync(ctx->ws_sweep_hint.p, 0, sizeof(int) * 64, ctx->stream));
-    {
-        static const int lag_env = getenv("B200M_TC_SWEEP_LAG") ? atoi(getenv("B200M_TC_SWEEP_LAG")) : -1;
-        // default: rotate when the train operands do NOT fit L2 (C4: 256 MB; measured 417 -> 372 ms per launch with 16-24 tiles
-        // between followers, 8 and >= 48 are slower than no rotation; operands that fit L2 show no difference) --
-        // profiles/r02_notes.md section 14
-        p.sweep_lag = lag_env >= 0 ? lag_env : ((size_t) t.n_pad * (size_t) t.kp * 2 > (size_t) 96 << 20 ? 20 : 0);
-    }
+    // default: rotate when the train operands do NOT fit L2 (C4: 256 MB; measured 417 -> 372 ms per launch with 16-24 tiles
+    // between followers, 8 and >= 48 are slower than no rotation; operands that fit L2 show no difference) --
+    // profiles/r02_notes.md section 14.  B200M_TC_SWEEP_LAG overrides (0 = off).
+    p.sweep_lag = ctx->tc_sweep_lag >= 0 ? ctx->tc_sweep_lag : ((size_t) t.n_pad * (size_t) t.kp * 2 > (size_t) 96 << 20 ? 20 : 0);
     p.sweep_hint = ctx->ws_sweep_hint.as<int>();
     p.debug_flags = ctx->tc_debug;
     if (dump) p.tiles_per_split = (int) dump_t_tile;

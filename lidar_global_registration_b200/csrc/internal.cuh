@@ -82,6 +82,7 @@ struct b200m_ctx {
     int tc_alt = -1;       // B200M_TC_ALT: epilogue layout of the split-N kernel (4 / 5 chunk entries drained by 32- / 16-column
                            // TMEM loads; column entries: 1 alternating tiles, 2 quarter columns, 0 eight warps);
                            // -1 = by measurement: 5 up to k = 2, 4 beyond
+    int tc_sweep_lag = -1; // B200M_TC_SWEEP_LAG: tiles between followers of the chunk-entry kernels' rotated sweep (0 = off, -1 = by size)
     int tc_lean = 1;       // B200M_TC_LEAN=0: general MMA issue loop also for one-atom descriptors (comparison)
     int tc_debug = 0;      // B200M_TC_DEBUG: timing experiments (results are NOT valid when set)
     int tc_pair = 1;       // 1 = CTA-pair (cta_group::2) candidate kernel; 0 = cta_group::1 + multicast (B200M_TC_MODE=mcast)

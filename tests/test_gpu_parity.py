@@ -344,6 +344,31 @@ def test_fpfh_epilogue_layouts(monkeypatch, layout, nq, nt, k):
         assert ctx.stats()["rows_flagged"] == 0
 
 
+@pytest.mark.parametrize("lag", [1, 5, 20])
+@pytest.mark.parametrize("layout", ["chunk-entries", "chunk-entries-x16"])
+@pytest.mark.parametrize("nq,nt,k,splits", [(30000, 9000, 2, 0), (40000, 1300, 5, 0), (700, 70000, 3, 3)])
+def test_fpfh_rotated_sweep(monkeypatch, layout, lag, nq, nt, k, splits):
+    """The chunk-entry kernels with the rotated sweep forced on (by default only train sets beyond L2 use it): several waves
+    of CTA pairs (30000 rows = 118 pairs on 74 slots) so that late starters read a non-zero front position, train sets
+    shorter than the followers' distances (5 tiles: every start wraps around, negative positions), and several train
+    splits -- oracle-exact lists in both directions."""
+    monkeypatch.setenv("B200M_TC_ALT", str(FPFH_LAYOUTS[layout]))
+    monkeypatch.setenv("B200M_TC_SWEEP_LAG", str(lag))
+    if splits:
+        monkeypatch.setenv("B200M_TC_SPLITS", str(splits))
+    src, tgt, dim = synth.make_pair("fpfh", nq, nt, nan_frac=0.01)
+    with M.Context(0) as ctx:
+        ctx.upload(0, src, dim)
+        ctx.upload(1, tgt, dim)
+        rows = np.random.default_rng(3).choice(nq, min(nq, 3000), replace=False)
+        idx, dist, cnt = ctx.knn(k, 0)
+        _same((idx[rows], dist[rows], cnt[rows]), orc.knn(np.ascontiguousarray(src[rows, :dim]), _dense(tgt, dim), k))
+        rows = np.random.default_rng(4).choice(nt, min(nt, 3000), replace=False)
+        idx, dist, cnt = ctx.knn(k, 1)
+        _same((idx[rows], dist[rows], cnt[rows]), orc.knn(np.ascontiguousarray(tgt[rows, :dim]), _dense(src, dim), k))
+        assert ctx.stats()["rows_flagged"] == 0
+
+
 @pytest.mark.parametrize("epi", ["eh1", "eh2"])
 @pytest.mark.parametrize("mode", ["pair", "mcast1", "mcast2", "mcast4"])
 @pytest.mark.parametrize("desc,nq,nt,k", [("fpfh", 3000, 9000, 2), ("shot", 1100, 2600, 5)])
