@@ -96,3 +96,23 @@ def test_opencv_baseline_path_agrees_with_the_oracle():
         assert np.allclose(dist, od, rtol=1e-5, atol=0)
         assert np.all(oc == k)
     assert cv2.__version__
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """The driver parses stdout as ONE JSON line: run the CPU (reference) arm on the small C1 workload and check that
+    stdout is exactly that -- whatever the libraries print goes to stderr -- and that the line carries the contract's keys."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[:2000]
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "queries/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("FPFH-33 20k")
